@@ -1,0 +1,121 @@
+"""ctypes binding of liboctic_b200.so (the C ABI declared in include/octic_b200.h).
+
+PyTorch is used for device memory and streams only: every call passes raw `data_ptr()`s and the current CUDA
+stream handle.  There is no fallback: if the shared library is missing, or a call returns an error code, an
+exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "liboctic_b200.so"
+
+OCTIC_MAX_GROUPS = 8
+F32, BF16 = 0, 1
+EPI_BF16, EPI_RESID, EPI_F32, EPI_GELU_BF16 = 0, 1, 2, 3
+
+
+class OcticError(RuntimeError):
+    pass
+
+
+class GemmGroup(C.Structure):
+    _fields_ = [("a_col", C.c_int), ("k", C.c_int), ("b_map", C.c_int), ("b_row", C.c_int), ("n", C.c_int),
+                ("c_col", C.c_int), ("bias_off", C.c_int)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("a", C.c_void_p), ("lda", C.c_long), ("a_cols", C.c_long), ("M", C.c_int),
+        ("b0", C.c_void_p), ("b0_rows", C.c_long), ("b0_cols", C.c_long), ("b0_ld", C.c_long),
+        ("b1", C.c_void_p), ("b1_rows", C.c_long), ("b1_cols", C.c_long), ("b1_ld", C.c_long),
+        ("num_groups", C.c_int), ("groups", GemmGroup * OCTIC_MAX_GROUPS),
+        ("block_n", C.c_int), ("mode", C.c_int),
+        ("out", C.c_void_p), ("ldo", C.c_long),
+        ("bias", C.c_void_p), ("gamma", C.c_void_p),
+        ("resid_in", C.c_void_p), ("resid_out", C.c_void_p), ("ldr", C.c_long),
+        ("row_scale", C.c_void_p), ("rows_per_sample", C.c_int),
+        ("branch_out", C.c_void_p), ("ldb", C.c_long),
+        ("remap_group", C.c_int), ("remap_extra", C.c_int), ("remap_off", C.c_int),
+    ]
+
+
+class WgradGroup(C.Structure):
+    _fields_ = [("dy_col", C.c_int), ("x_col", C.c_int), ("n_out", C.c_int), ("k_in", C.c_int),
+                ("dw", C.c_void_p), ("ldw", C.c_long)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("dy", C.c_void_p), ("ld_dy", C.c_long), ("dy_cols", C.c_long),
+        ("x", C.c_void_p), ("ld_x", C.c_long), ("x_cols", C.c_long),
+        ("T", C.c_int), ("num_groups", C.c_int), ("groups", WgradGroup * OCTIC_MAX_GROUPS),
+        ("block_n", C.c_int), ("splits", C.c_int),
+    ]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+# name -> argtypes; every function returns int.  Keep in sync with include/octic_b200.h (tests check that every
+# prototype in the header is exported by the library and listed here).
+SIGNATURES = {
+    "octic_gemm_bf16": [C.POINTER(GemmDesc), _P],
+    "octic_gemm_wgrad_bf16": [C.POINTER(WgradDesc), _P],
+    "octic_linear_d8_pack_weights": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
+    "octic_linear_d8_fwd": [_P, _I, _I, _I, _P, _P, _P, C.POINTER(GemmDesc), _P],
+    "octic_linear_d8_dgrad": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "octic_linear_d8_wgrad": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "octic_linear_pack_weights": [_P, _I, _I, _P, _P, _P],
+    "octic_gelu_d8_fwd": [_P, _L, _P, _L, _L, _I, _I, _P],
+    "octic_gelu_d8_bwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P],
+    "octic_gelu_bwd": [_P, _P, _P, _L, _I, _P, _P],
+    "octic_layernorm_d8_fwd": [_P, _L, _P, _P, _F, _P, _L, _I, _P, _L, _I, _P],
+    "octic_layernorm_d8_bwd": [_P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _I, _P],
+    "octic_layernorm_fwd": [_P, _L, _P, _P, _F, _P, _L, _I, _P, _L, _I, _P],
+    "octic_layernorm_bwd": [_P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _I, _P],
+    "octic_layerscale_bwd": [_P, _L, _P, _L, _P, _P, _I, _P, _L, _P, _P, _L, _I, _P],
+    "octic_colsum_bf16": [_P, _L, _L, _I, _P, _P],
+    "octic_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "octic_attention_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "octic_power_spectrum_fwd": [_P, _L, _P, _L, _L, _I, _P],
+    "octic_power_spectrum_bwd": [_P, _L, _I, _P, _L, _P, _L, _L, _I, _P],
+    "octic_bridge_permute": [_P, _L, _P, _L, _L, _I, _P],
+    "octic_im2col_patches": [_P, _I, _I, _I, _I, _I, _P, _L, _P],
+    "octic_cast_f32_to_bf16": [_P, _L, _P, _L, _L, _I, _P],
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once; fail loudly if it has not been built (python __graft_entry__.py / build.sh)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise OcticError(
+            f"{LIB_PATH} not found: build it with ./build.sh (nvcc, sm_100a). There is no CPU or PyTorch fallback.")
+    lib = C.CDLL(os.fspath(LIB_PATH))
+    lib.octic_strerror.restype = C.c_char_p
+    lib.octic_strerror.argtypes = [C.c_int]
+    lib.octic_version.restype = C.c_int
+    lib.octic_device_ok.restype = C.c_int
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().octic_strerror(rc).decode()
+        raise OcticError(f"{what} failed: {msg} (code {rc})")
+
+
+def call(name: str, *args) -> None:
+    check(getattr(load(), name)(*args), name)

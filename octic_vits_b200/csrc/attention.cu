@@ -1,0 +1,643 @@
+// Octic / dense multi-head attention, forward and backward, for short sequences (N = 197..261 tokens).
+//
+// Reference: AttentionD8.forward (octic_vits/d8_layers.py:623-656) builds q,k,v [B,H,N,hd] by concatenating, per
+// head, slices of the five irrep tensors -- [A1(c_h) | A2 | B1 | B2 | E row0 (2c_h) | E row1 (2c_h)] -- calls
+// F.scaled_dot_product_attention, and scatters the result back into the 5-tuple.  Here the gather happens while
+// K/V (or Q/dO) are staged into shared memory and the scatter happens in the output stores, straight from/to the
+// packed [T, 3D] / [T, D] rows, so the cat/permute/contiguous copies of the reference do not exist.  The dense
+// layout (deit/vit.py:36-50) is the same kernel with a trivial column map.
+//
+// One CTA per (batch, head): the whole K and V (<= 272 x 80 bf16 each) sit in shared memory; each warp owns 16 query
+// rows and runs an online-softmax loop over 64-key chunks with mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
+// Backward is two passes without atomics: pass A (warps own key rows) -> dK, dV; pass B (warps own query rows) -> dQ.
+// TODO(round 2): move QK^T / PV onto tcgen05 with S/P in TMEM.
+#include "octic_capi_internal.h"
+
+namespace octic {
+
+struct HeadMap {
+  int octic;   // 1: packed LinearD8 layout, 0: dense [3][H][hd]
+  int D;       // embed dim
+  int C;       // D / 8
+  int ch;      // hd / 8 = C / H
+  int hd;
+};
+
+// column of element j (even) of the head vector of (s, h) inside a qkv row, split as base + s * smul
+__device__ __forceinline__ void qkv_col(const HeadMap& m, int h, int j, int& base, int& smul) {
+  if (!m.octic) { base = h * m.hd + j; smul = m.D; return; }
+  if (j < 4 * m.ch) {
+    const int g = j / m.ch, jj = j - g * m.ch;
+    base = g * 3 * m.C + h * m.ch + jj; smul = m.C;
+  } else {
+    const int j2 = j - 4 * m.ch, r = j2 / (2 * m.ch), jj = j2 - r * 2 * m.ch;
+    base = 12 * m.C + r * 6 * m.C + h * 2 * m.ch + jj; smul = 2 * m.C;
+  }
+}
+// column of element j of head h inside an attention-output row (packed 5-tuple order, d8_layers.py:650-656)
+__device__ __forceinline__ int o_col(const HeadMap& m, int h, int j) {
+  if (!m.octic) return h * m.hd + j;
+  if (j < 4 * m.ch) {
+    const int g = j / m.ch, jj = j - g * m.ch;
+    return g * m.C + h * m.ch + jj;
+  }
+  const int j2 = j - 4 * m.ch, r = j2 / (2 * m.ch), jj = j2 - r * 2 * m.ch;
+  return 4 * m.C + r * 2 * m.C + h * 2 * m.ch + jj;
+}
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  const uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(p));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&b);
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+}
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+
+// B fragments of two adjacent 8-wide n-tiles for  C[m, n] += A[m, k] * M[n, k]   (M row-major [n][k] in smem):
+// b[0],b[1] -> n-tile n0, b[2],b[3] -> n-tile n0 + 8, k-step k0 (16 wide)
+template <int STR>
+__device__ __forceinline__ void load_b_nk(uint32_t (&b)[4], const __nv_bfloat16* M, int n0, int k0, int lane) {
+  const int mat = lane >> 3, row = lane & 7;
+  ldsm_x4(b, M + (n0 + (mat >> 1) * 8 + row) * STR + k0 + (mat & 1) * 8);
+}
+// B fragments for  C[m, n] += A[m, k] * M[k, n]   (M row-major [k][n] in smem): n-tiles n0 and n0 + 8, k-step k0
+template <int STR>
+__device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], const __nv_bfloat16* M, int k0, int n0, int lane) {
+  const int mat = lane >> 3, row = lane & 7;
+  ldsm_x4_t(b, M + (k0 + (mat & 1) * 8 + row) * STR + n0 + (mat >> 1) * 8);
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Stage rows [0, Npad) of tensor s of (b, h) into smem (zero rows >= N).
+template <int HD>
+__device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src_rows, long ld, int s, int N,
+                                           int Npad, const int* cb, const int* sm) {
+  constexpr int STR = HD + 8;
+  for (int idx = threadIdx.x; idx < Npad * (HD / 2); idx += blockDim.x) {
+    const int row = idx / (HD / 2), jp = idx - row * (HD / 2);
+    uint32_t v = 0;
+    if (row < N) v = *reinterpret_cast<const uint32_t*>(src_rows + row * ld + cb[jp] + s * sm[jp]);
+    *reinterpret_cast<uint32_t*>(dst + row * STR + jp * 2) = v;
+  }
+}
+
+// A fragments (16 rows x HD) of tensor s for rows r_lo = row0 + lane/4 and r_lo + 8, read straight from global.
+template <int HD>
+__device__ __forceinline__ void load_a_rows(uint32_t (&a)[HD / 16][4], const __nv_bfloat16* src_rows, long ld, int s,
+                                            int row0, int N, const int* cb, const int* sm, int lane) {
+  const int r_lo = row0 + (lane >> 2), r_hi = r_lo + 8;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    const int jp0 = ks * 8 + (lane & 3), jp1 = jp0 + 4;
+    const int c0 = cb[jp0] + s * sm[jp0], c1 = cb[jp1] + s * sm[jp1];
+    a[ks][0] = r_lo < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_lo * ld + c0) : 0u;
+    a[ks][1] = r_hi < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_hi * ld + c0) : 0u;
+    a[ks][2] = r_lo < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_lo * ld + c1) : 0u;
+    a[ks][3] = r_hi < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_hi * ld + c1) : 0u;
+  }
+}
+
+// ------------------------------------------------------ forward ------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(384) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
+                                                       float* __restrict__ lse, int N, int H, HeadMap m, float scale_log2) {
+  constexpr int STR = HD + 8, KS = HD / 16, DT = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int Npad = (N + 15) & ~15;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* Vs = Ks + Npad * STR;
+  int* cb = reinterpret_cast<int*>(Vs + Npad * STR);
+  int* sm = cb + HD / 2;
+  int* ocb = sm + HD / 2;
+
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const long ld3 = 3L * m.D;
+  const __nv_bfloat16* rows = qkv + static_cast<long>(b) * N * ld3;
+
+  if (threadIdx.x < HD / 2) {
+    int base, smul;
+    qkv_col(m, h, threadIdx.x * 2, base, smul);
+    cb[threadIdx.x] = base; sm[threadIdx.x] = smul;
+    ocb[threadIdx.x] = o_col(m, h, threadIdx.x * 2);
+  }
+  __syncthreads();
+  stage_rows<HD>(Ks, rows, ld3, 1, N, Npad, cb, sm);
+  stage_rows<HD>(Vs, rows, ld3, 2, N, Npad, cb, sm);
+  __syncthreads();
+
+  const int ntiles = Npad / 16;
+  for (int qt = warp; qt < ntiles; qt += nwarps) {
+    const int q0 = qt * 16;
+    uint32_t qa[KS][4];
+    load_a_rows<HD>(qa, rows, ld3, 0, q0, N, cb, sm, lane);
+    float oacc[DT][4];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
+    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+
+    for (int kv0 = 0; kv0 < Npad; kv0 += 64) {
+      const int nts = min(8, (Npad - kv0) >> 3);   // even
+      float s[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (2 * np < nts) {
+            uint32_t bf[4];
+            load_b_nk<STR>(bf, Ks, kv0 + np * 16, ks * 16, lane);
+            mma16816(s[2 * np], qa[ks], bf[0], bf[1]);
+            mma16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
+          }
+        }
+      }
+      float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = kv0 + nt * 8 + (lane & 3) * 2;
+        if (nt >= nts || col >= N) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+        if (nt >= nts || col + 1 >= N) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+        mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+        mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+      }
+      mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);
+      const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
+      const float corr_lo = exp2f((m_lo - mn_lo) * scale_log2), corr_hi = exp2f((m_hi - mn_hi) * scale_log2);
+      m_lo = mn_lo; m_hi = mn_hi;
+      const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
+      float rs_lo = 0.f, rs_hi = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] * scale_log2 - off_lo);
+        s[nt][1] = exp2f(s[nt][1] * scale_log2 - off_lo);
+        s[nt][2] = exp2f(s[nt][2] * scale_log2 - off_hi);
+        s[nt][3] = exp2f(s[nt][3] * scale_log2 - off_hi);
+        rs_lo += s[nt][0] + s[nt][1];
+        rs_hi += s[nt][2] + s[nt][3];
+      }
+      l_lo = l_lo * corr_lo + rs_lo;
+      l_hi = l_hi * corr_hi + rs_hi;
+#pragma unroll
+      for (int i = 0; i < DT; ++i) {
+        oacc[i][0] *= corr_lo; oacc[i][1] *= corr_lo; oacc[i][2] *= corr_hi; oacc[i][3] *= corr_hi;
+      }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (2 * kk < nts) {
+          uint32_t pa[4];
+          pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+          pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+          pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+          pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+          for (int dp = 0; dp < DT / 2; ++dp) {
+            uint32_t bf[4];
+            load_b_kn<STR>(bf, Vs, kv0 + kk * 16, dp * 16, lane);
+            mma16816(oacc[2 * dp], pa, bf[0], bf[1]);
+            mma16816(oacc[2 * dp + 1], pa, bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
+    const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+    const int r_lo = q0 + (lane >> 2), r_hi = r_lo + 8;
+    __nv_bfloat16* orow_lo = o + (static_cast<long>(b) * N + r_lo) * m.D;
+    __nv_bfloat16* orow_hi = o + (static_cast<long>(b) * N + r_hi) * m.D;
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      const int oc = ocb[dt * 4 + (lane & 3)];
+      if (r_lo < N) *reinterpret_cast<uint32_t*>(orow_lo + oc) = pack_bf16(oacc[dt][0] * inv_lo, oacc[dt][1] * inv_lo);
+      if (r_hi < N) *reinterpret_cast<uint32_t*>(orow_hi + oc) = pack_bf16(oacc[dt][2] * inv_hi, oacc[dt][3] * inv_hi);
+    }
+    if (lse != nullptr && (lane & 3) == 0) {
+      float* l = lse + (static_cast<long>(b) * H + h) * N;
+      if (r_lo < N) l[r_lo] = (m_lo * scale_log2 + log2f(l_lo)) * kLn2;
+      if (r_hi < N) l[r_hi] = (m_hi * scale_log2 + log2f(l_hi)) * kLn2;
+    }
+  }
+}
+
+// ------------------------------------------- backward: delta = rowsum(dO * O) -------------------------------------------
+__global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
+                                                         int B, int N, int H, HeadMap m) {
+  // one thread per (b, n, h); delta laid out [B, H, N]
+  const long total = static_cast<long>(B) * N * H;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int h = static_cast<int>(idx % H);
+    const long t = idx / H;
+    const int b = static_cast<int>(t / N), n = static_cast<int>(t - static_cast<long>(b) * N);
+    const __nv_bfloat16* orow = o + t * m.D;
+    const __nv_bfloat16* drow = d_o + t * m.D;
+    float acc = 0.f;
+    for (int j = 0; j < m.hd; j += 2) {
+      const int c = o_col(m, h, j);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(orow + c));
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(drow + c));
+      acc += a.x * g.x + a.y * g.y;
+    }
+    delta[(static_cast<long>(b) * H + h) * N + n] = acc;
+  }
+}
+
+// stage rows of an attention-output-shaped tensor (dO) for head h
+template <int HD>
+__device__ __forceinline__ void stage_o_rows(__nv_bfloat16* dst, const __nv_bfloat16* src_rows, long ld, int N, int Npad,
+                                             const int* ocb) {
+  constexpr int STR = HD + 8;
+  for (int idx = threadIdx.x; idx < Npad * (HD / 2); idx += blockDim.x) {
+    const int row = idx / (HD / 2), jp = idx - row * (HD / 2);
+    uint32_t v = 0;
+    if (row < N) v = *reinterpret_cast<const uint32_t*>(src_rows + row * ld + ocb[jp]);
+    *reinterpret_cast<uint32_t*>(dst + row * STR + jp * 2) = v;
+  }
+}
+template <int HD>
+__device__ __forceinline__ void load_a_o_rows(uint32_t (&a)[HD / 16][4], const __nv_bfloat16* src_rows, long ld, int row0,
+                                              int N, const int* ocb, int lane) {
+  const int r_lo = row0 + (lane >> 2), r_hi = r_lo + 8;
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+    const int c0 = ocb[ks * 8 + (lane & 3)], c1 = ocb[ks * 8 + 4 + (lane & 3)];
+    a[ks][0] = r_lo < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_lo * ld + c0) : 0u;
+    a[ks][1] = r_hi < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_hi * ld + c0) : 0u;
+    a[ks][2] = r_lo < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_lo * ld + c1) : 0u;
+    a[ks][3] = r_hi < N ? *reinterpret_cast<const uint32_t*>(src_rows + r_hi * ld + c1) : 0u;
+  }
+}
+
+// ------------------------------------------- backward pass A: dK, dV -------------------------------------------
+// Warps own 16 key rows.  S^T = K Q^T, P^T = exp(S^T*scale - lse[q]), dV += P^T dO, dP^T = V dO^T,
+// dS^T = P^T (dP^T - delta[q]), dK += scale * dS^T Q.
+template <int HD>
+__global__ void __launch_bounds__(384) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                          const __nv_bfloat16* __restrict__ d_o,
+                                                          const float* __restrict__ lse, const float* __restrict__ delta,
+                                                          __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
+                                                          float scale, float scale_log2) {
+  constexpr int STR = HD + 8, KS = HD / 16, DT = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int Npad = (N + 15) & ~15;
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* dOs = Qs + Npad * STR;
+  float* lse_s = reinterpret_cast<float*>(dOs + Npad * STR);
+  float* del_s = lse_s + Npad;
+  int* cb = reinterpret_cast<int*>(del_s + Npad);
+  int* sm = cb + HD / 2;
+  int* ocb = sm + HD / 2;
+
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const long ld3 = 3L * m.D;
+  const __nv_bfloat16* rows = qkv + static_cast<long>(b) * N * ld3;
+  const __nv_bfloat16* dorows = d_o + static_cast<long>(b) * N * m.D;
+  __nv_bfloat16* drows = dqkv + static_cast<long>(b) * N * ld3;
+
+  if (threadIdx.x < HD / 2) {
+    int base, smul;
+    qkv_col(m, h, threadIdx.x * 2, base, smul);
+    cb[threadIdx.x] = base; sm[threadIdx.x] = smul;
+    ocb[threadIdx.x] = o_col(m, h, threadIdx.x * 2);
+  }
+  for (int i = threadIdx.x; i < Npad; i += blockDim.x) {
+    const long off = (static_cast<long>(b) * H + h) * N + i;
+    lse_s[i] = i < N ? lse[off] * kLog2e : INFINITY;   // +inf -> P = 0 for padded queries
+    del_s[i] = i < N ? delta[off] : 0.f;
+  }
+  __syncthreads();
+  stage_rows<HD>(Qs, rows, ld3, 0, N, Npad, cb, sm);
+  stage_o_rows<HD>(dOs, dorows, m.D, N, Npad, ocb);
+  __syncthreads();
+
+  const int ntiles = Npad / 16;
+  for (int kt = warp; kt < ntiles; kt += nwarps) {
+    const int k0 = kt * 16;
+    uint32_t ka[KS][4], va[KS][4];
+    load_a_rows<HD>(ka, rows, ld3, 1, k0, N, cb, sm, lane);
+    load_a_rows<HD>(va, rows, ld3, 2, k0, N, cb, sm, lane);
+    float dk[DT][4], dv[DT][4];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) {
+      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
+    }
+    for (int q0 = 0; q0 < Npad; q0 += 32) {
+      const int nts = min(4, (Npad - q0) >> 3);   // 2 or 4
+      float st[4][4], dp[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          if (2 * np < nts) {
+            uint32_t bf[4];
+            load_b_nk<STR>(bf, Qs, q0 + np * 16, ks * 16, lane);
+            mma16816(st[2 * np], ka[ks], bf[0], bf[1]);
+            mma16816(st[2 * np + 1], ka[ks], bf[2], bf[3]);
+            load_b_nk<STR>(bf, dOs, q0 + np * 16, ks * 16, lane);
+            mma16816(dp[2 * np], va[ks], bf[0], bf[1]);
+            mma16816(dp[2 * np + 1], va[ks], bf[2], bf[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        if (nt < nts) {
+          const int col = q0 + nt * 8 + (lane & 3) * 2;
+          const float l0 = lse_s[col], l1 = lse_s[col + 1], d0 = del_s[col], d1 = del_s[col + 1];
+          const float p0 = exp2f(st[nt][0] * scale_log2 - l0), p1 = exp2f(st[nt][1] * scale_log2 - l1);
+          const float p2 = exp2f(st[nt][2] * scale_log2 - l0), p3 = exp2f(st[nt][3] * scale_log2 - l1);
+          st[nt][0] = p0; st[nt][1] = p1; st[nt][2] = p2; st[nt][3] = p3;
+          dp[nt][0] = p0 * (dp[nt][0] - d0); dp[nt][1] = p1 * (dp[nt][1] - d1);
+          dp[nt][2] = p2 * (dp[nt][2] - d0); dp[nt][3] = p3 * (dp[nt][3] - d1);
+        } else {
+          st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
+          dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        if (2 * kk < nts) {
+          uint32_t pa[4], da[4];
+          pa[0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);
+          pa[1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
+          pa[2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]);
+          pa[3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
+          da[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+          da[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+          da[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+          da[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+          for (int dpi = 0; dpi < DT / 2; ++dpi) {
+            uint32_t bf[4];
+            load_b_kn<STR>(bf, dOs, q0 + kk * 16, dpi * 16, lane);
+            mma16816(dv[2 * dpi], pa, bf[0], bf[1]);
+            mma16816(dv[2 * dpi + 1], pa, bf[2], bf[3]);
+            load_b_kn<STR>(bf, Qs, q0 + kk * 16, dpi * 16, lane);
+            mma16816(dk[2 * dpi], da, bf[0], bf[1]);
+            mma16816(dk[2 * dpi + 1], da, bf[2], bf[3]);
+          }
+        }
+      }
+    }
+    const int r_lo = k0 + (lane >> 2), r_hi = r_lo + 8;
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      const int jp = dt * 4 + (lane & 3);
+      const int ck = cb[jp] + sm[jp], cv = cb[jp] + 2 * sm[jp];
+      if (r_lo < N) {
+        *reinterpret_cast<uint32_t*>(drows + r_lo * ld3 + ck) = pack_bf16(dk[dt][0] * scale, dk[dt][1] * scale);
+        *reinterpret_cast<uint32_t*>(drows + r_lo * ld3 + cv) = pack_bf16(dv[dt][0], dv[dt][1]);
+      }
+      if (r_hi < N) {
+        *reinterpret_cast<uint32_t*>(drows + r_hi * ld3 + ck) = pack_bf16(dk[dt][2] * scale, dk[dt][3] * scale);
+        *reinterpret_cast<uint32_t*>(drows + r_hi * ld3 + cv) = pack_bf16(dv[dt][2], dv[dt][3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------- backward pass B: dQ -------------------------------------------
+// Warps own 16 query rows.  S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P (dP - delta), dQ = scale * dS K.
+template <int HD>
+__global__ void __launch_bounds__(384) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                         const __nv_bfloat16* __restrict__ d_o,
+                                                         const float* __restrict__ lse, const float* __restrict__ delta,
+                                                         __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
+                                                         float scale, float scale_log2) {
+  constexpr int STR = HD + 8, KS = HD / 16, DT = HD / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int Npad = (N + 15) & ~15;
+  __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(smem);
+  __nv_bfloat16* Vs = Ks + Npad * STR;
+  int* cb = reinterpret_cast<int*>(Vs + Npad * STR);
+  int* sm = cb + HD / 2;
+  int* ocb = sm + HD / 2;
+
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const long ld3 = 3L * m.D;
+  const __nv_bfloat16* rows = qkv + static_cast<long>(b) * N * ld3;
+  const __nv_bfloat16* dorows = d_o + static_cast<long>(b) * N * m.D;
+  __nv_bfloat16* drows = dqkv + static_cast<long>(b) * N * ld3;
+
+  if (threadIdx.x < HD / 2) {
+    int base, smul;
+    qkv_col(m, h, threadIdx.x * 2, base, smul);
+    cb[threadIdx.x] = base; sm[threadIdx.x] = smul;
+    ocb[threadIdx.x] = o_col(m, h, threadIdx.x * 2);
+  }
+  __syncthreads();
+  stage_rows<HD>(Ks, rows, ld3, 1, N, Npad, cb, sm);
+  stage_rows<HD>(Vs, rows, ld3, 2, N, Npad, cb, sm);
+  __syncthreads();
+
+  const int ntiles = Npad / 16;
+  for (int qt = warp; qt < ntiles; qt += nwarps) {
+    const int q0 = qt * 16;
+    uint32_t qa[KS][4], doa[KS][4];
+    load_a_rows<HD>(qa, rows, ld3, 0, q0, N, cb, sm, lane);
+    load_a_o_rows<HD>(doa, dorows, m.D, q0, N, ocb, lane);
+    const int r_lo = q0 + (lane >> 2), r_hi = r_lo + 8;
+    const long soff = (static_cast<long>(b) * H + h) * N;
+    const float lse_lo = r_lo < N ? lse[soff + r_lo] * kLog2e : INFINITY;
+    const float lse_hi = r_hi < N ? lse[soff + r_hi] * kLog2e : INFINITY;
+    const float del_lo = r_lo < N ? delta[soff + r_lo] : 0.f;
+    const float del_hi = r_hi < N ? delta[soff + r_hi] : 0.f;
+    float dq[DT][4];
+#pragma unroll
+    for (int i = 0; i < DT; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+
+    for (int kv0 = 0; kv0 < Npad; kv0 += 32) {
+      const int nts = min(4, (Npad - kv0) >> 3);
+      float s[4][4], dp[4][4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          if (2 * np < nts) {
+            uint32_t bf[4];
+            load_b_nk<STR>(bf, Ks, kv0 + np * 16, ks * 16, lane);
+            mma16816(s[2 * np], qa[ks], bf[0], bf[1]);
+            mma16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
+            load_b_nk<STR>(bf, Vs, kv0 + np * 16, ks * 16, lane);
+            mma16816(dp[2 * np], doa[ks], bf[0], bf[1]);
+            mma16816(dp[2 * np + 1], doa[ks], bf[2], bf[3]);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int col = kv0 + nt * 8 + (lane & 3) * 2;
+        const bool v0 = nt < nts && col < N, v1 = nt < nts && col + 1 < N;
+        const float p0 = v0 ? exp2f(s[nt][0] * scale_log2 - lse_lo) : 0.f;
+        const float p1 = v1 ? exp2f(s[nt][1] * scale_log2 - lse_lo) : 0.f;
+        const float p2 = v0 ? exp2f(s[nt][2] * scale_log2 - lse_hi) : 0.f;
+        const float p3 = v1 ? exp2f(s[nt][3] * scale_log2 - lse_hi) : 0.f;
+        dp[nt][0] = p0 * (dp[nt][0] - del_lo); dp[nt][1] = p1 * (dp[nt][1] - del_lo);
+        dp[nt][2] = p2 * (dp[nt][2] - del_hi); dp[nt][3] = p3 * (dp[nt][3] - del_hi);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        if (2 * kk < nts) {
+          uint32_t da[4];
+          da[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
+          da[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
+          da[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
+          da[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
+#pragma unroll
+          for (int dpi = 0; dpi < DT / 2; ++dpi) {
+            uint32_t bf[4];
+            load_b_kn<STR>(bf, Ks, kv0 + kk * 16, dpi * 16, lane);
+            mma16816(dq[2 * dpi], da, bf[0], bf[1]);
+            mma16816(dq[2 * dpi + 1], da, bf[2], bf[3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      const int cq = cb[dt * 4 + (lane & 3)];
+      if (r_lo < N) *reinterpret_cast<uint32_t*>(drows + r_lo * ld3 + cq) = pack_bf16(dq[dt][0] * scale, dq[dt][1] * scale);
+      if (r_hi < N) *reinterpret_cast<uint32_t*>(drows + r_hi * ld3 + cq) = pack_bf16(dq[dt][2] * scale, dq[dt][3] * scale);
+    }
+  }
+}
+
+// ------------------------------------------------------ host ------------------------------------------------------
+static int attn_warps(int N) {
+  const int ntiles = (N + 15) / 16;
+  const int rounds = (ntiles + 11) / 12;
+  return (ntiles + rounds - 1) / rounds;
+}
+static int make_head_map(HeadMap* m, int H, int hd, int octic) {
+  if (H <= 0 || hd <= 0 || (hd % 16) != 0) return OCTIC_ERR_ARG;
+  m->octic = octic; m->hd = hd; m->D = H * hd; m->C = m->D / 8; m->ch = hd / 8;
+  return OCTIC_OK;
+}
+
+template <int HD>
+static int launch_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, const HeadMap& m, cudaStream_t s) {
+  const int Npad = (N + 15) & ~15;
+  const int smem = 2 * Npad * (HD + 8) * 2 + 3 * (HD / 2) * 4;
+  static bool done = false;
+  if (!done) {
+    if (cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return OCTIC_ERR_CUDA;
+    done = true;
+  }
+  if (smem > 227 * 1024) return OCTIC_ERR_ARG;
+  const float scale_log2 = kLog2e / sqrtf(static_cast<float>(HD));
+  attn_fwd_kernel<HD><<<B * H, attn_warps(N) * 32, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                              static_cast<__nv_bfloat16*>(o), lse, N, H, m, scale_log2);
+  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+}
+
+template <int HD>
+static int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, void* dqkv, int B,
+                      int N, int H, const HeadMap& m, cudaStream_t s) {
+  const int Npad = (N + 15) & ~15;
+  const int smem_kv = 2 * Npad * (HD + 8) * 2 + 2 * Npad * 4 + 3 * (HD / 2) * 4;
+  const int smem_q = 2 * Npad * (HD + 8) * 2 + 3 * (HD / 2) * 4;
+  static bool done = false;
+  if (!done) {
+    if (cudaFuncSetAttribute(attn_bwd_kv_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(attn_bwd_q_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return OCTIC_ERR_CUDA;
+    done = true;
+  }
+  if (smem_kv > 227 * 1024) return OCTIC_ERR_ARG;
+  const float scale = 1.0f / sqrtf(static_cast<float>(HD));
+  const float scale_log2 = kLog2e * scale;
+  const long total = static_cast<long>(B) * N * H;
+  int dgrid = static_cast<int>((total + 255) / 256);
+  if (dgrid > 148 * 16) dgrid = 148 * 16;
+  attn_delta_kernel<<<dgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
+                                          delta, B, N, H, m);
+  const int threads = attn_warps(N) * 32;
+  attn_bwd_kv_kernel<HD><<<B * H, threads, smem_kv, s>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                         static_cast<const __nv_bfloat16*>(d_o), lse, delta,
+                                                         static_cast<__nv_bfloat16*>(dqkv), N, H, m, scale, scale_log2);
+  attn_bwd_q_kernel<HD><<<B * H, threads, smem_q, s>>>(static_cast<const __nv_bfloat16*>(qkv),
+                                                       static_cast<const __nv_bfloat16*>(d_o), lse, delta,
+                                                       static_cast<__nv_bfloat16*>(dqkv), N, H, m, scale, scale_log2);
+  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+}
+
+}  // namespace octic
+
+using namespace octic;
+
+extern "C" {
+
+int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int hd, int octic_layout,
+                        void* stream) {
+  if (!qkv || !o || B <= 0 || N <= 0) return OCTIC_ERR_ARG;
+  HeadMap m;
+  int rc = make_head_map(&m, H, hd, octic_layout);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (hd) {
+    case 32: return launch_fwd<32>(qkv, o, lse, B, N, H, m, s);
+    case 64: return launch_fwd<64>(qkv, o, lse, B, N, H, m, s);
+    case 80: return launch_fwd<80>(qkv, o, lse, B, N, H, m, s);
+    case 96: return launch_fwd<96>(qkv, o, lse, B, N, H, m, s);
+    case 128: return launch_fwd<128>(qkv, o, lse, B, N, H, m, s);
+    default: return OCTIC_ERR_ARG;
+  }
+}
+
+int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_ws,
+                           void* dqkv, int B, int N, int H, int hd, int octic_layout, void* stream) {
+  if (!qkv || !o || !d_o || !lse || !delta_ws || !dqkv || B <= 0 || N <= 0) return OCTIC_ERR_ARG;
+  HeadMap m;
+  int rc = make_head_map(&m, H, hd, octic_layout);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (hd) {
+    case 32: return launch_bwd<32>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+    case 64: return launch_bwd<64>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+    case 80: return launch_bwd<80>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+    case 96: return launch_bwd<96>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+    case 128: return launch_bwd<128>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+    default: return OCTIC_ERR_ARG;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// extern "C" entry points of liboctic_b200.so that are thin glue: error strings, device probe, the generic
+// grouped GEMM, and the LinearD8 / nn.Linear wrappers that turn reference-level arguments into GEMM groups.
+#include "octic_capi_internal.h"
+
+namespace octic {
+
+int pick_block_n(const int* ns, int count) {
+  int maxn = 0;
+  for (int i = 0; i < count; ++i) maxn = ns[i] > maxn ? ns[i] : maxn;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    bool ok = true;
+    for (int i = 0; i < count; ++i) ok = ok && (ns[i] % bn == 0);
+    if (ok && bn >= 32) return bn;
+  }
+  int bn = (maxn + 15) / 16 * 16;
+  return bn > 256 ? 256 : bn;
+}
+
+// fp32 [N, K] -> bf16 [N, ldp] (zero padded to ldp columns) and bf16 transpose [K, ldt] (zero padded).
+__global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, __nv_bfloat16* __restrict__ dst,
+                                   long ldp, int Kp, __nv_bfloat16* __restrict__ dst_t, long ldt, int Np) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, k = k0 + tx;
+    float v = (n < N && k < K) ? w[static_cast<long>(n) * K + k] : 0.f;
+    tile[i][tx] = v;
+    if (dst != nullptr && n < N && k < Kp) dst[static_cast<long>(n) * ldp + k] = __float2bfloat16(v);
+  }
+  __syncthreads();
+  if (dst_t != nullptr) {
+    for (int i = ty; i < 32; i += 8) {
+      const int k = k0 + i, n = n0 + tx;
+      if (k < K && n < Np) dst_t[static_cast<long>(k) * ldt + n] = __float2bfloat16(tile[tx][i]);
+    }
+  }
+}
+
+static int pack_one(const float* w, int N, int K, __nv_bfloat16* dst, long ldp, __nv_bfloat16* dst_t, long ldt,
+                    cudaStream_t s) {
+  const int Kp = roundup64(K), Np = roundup64(N);
+  dim3 grid((Kp + 31) / 32, (Np + 31) / 32), block(32, 8);
+  pack_weight_kernel<<<grid, block, 0, s>>>(w, N, K, dst, ldp, Kp, dst_t, ldt, Np);
+  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+}
+
+}  // namespace octic
+
+using namespace octic;
+
+extern "C" {
+
+const char* octic_strerror(int code) {
+  switch (code) {
+    case OCTIC_OK: return "ok";
+    case OCTIC_ERR_ARG: return "invalid argument (size, null pointer or unsupported shape)";
+    case OCTIC_ERR_ALIGN: return "pointer or leading dimension is not 16-byte aligned";
+    case OCTIC_ERR_DRIVER: return "cuTensorMapEncodeTiled driver entry point unavailable";
+    case OCTIC_ERR_TMAP: return "cuTensorMapEncodeTiled failed";
+    case OCTIC_ERR_CUDA: return "CUDA launch failed or no sm_100 device";
+    default: return "unknown octic error";
+  }
+}
+
+int octic_version(void) { return 100; }
+
+int octic_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int octic_gemm_bf16(const octic_gemm_desc* desc, void* stream) {
+  if (desc == nullptr || desc->a == nullptr || desc->b0 == nullptr) return OCTIC_ERR_ARG;
+  return launch_gemm_tn(desc, static_cast<cudaStream_t>(stream));
+}
+
+int octic_gemm_wgrad_bf16(const octic_wgrad_desc* desc, void* stream) {
+  if (desc == nullptr || desc->dy == nullptr || desc->x == nullptr) return OCTIC_ERR_ARG;
+  return launch_gemm_wgrad(desc, static_cast<cudaStream_t>(stream));
+}
+
+int octic_linear_d8_pack_weights(const float* wA1, const float* wA2, const float* wB1, const float* wB2,
+                                 const float* wE, int Din, int Dout, void* w1d, void* wE_packed, void* w1d_t,
+                                 void* wE_t, void* stream) {
+  if (Din % 8 || Dout % 8 || !wA1 || !wA2 || !wB1 || !wB2 || !wE) return OCTIC_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Ci = Din / 8, Co = Dout / 8;
+  const long ld1 = roundup64(Ci), ldE = roundup64(2 * Ci), ld1t = roundup64(Co), ldEt = roundup64(2 * Co);
+  const float* w[4] = {wA1, wA2, wB1, wB2};
+  for (int g = 0; g < 4; ++g) {
+    __nv_bfloat16* d = w1d ? static_cast<__nv_bfloat16*>(w1d) + static_cast<long>(g) * Co * ld1 : nullptr;
+    __nv_bfloat16* dt = w1d_t ? static_cast<__nv_bfloat16*>(w1d_t) + static_cast<long>(g) * Ci * ld1t : nullptr;
+    int rc = pack_one(w[g], Co, Ci, d, ld1, dt, ld1t, s);
+    if (rc) return rc;
+  }
+  return pack_one(wE, 2 * Co, 2 * Ci, static_cast<__nv_bfloat16*>(wE_packed), ldE,
+                  static_cast<__nv_bfloat16*>(wE_t), ldEt, s);
+}
+
+int octic_linear_pack_weights(const float* w, int N, int K, void* w_packed, void* w_t_packed, void* stream) {
+  if (!w || N <= 0 || K <= 0) return OCTIC_ERR_ARG;
+  return pack_one(w, N, K, static_cast<__nv_bfloat16*>(w_packed), roundup64(K),
+                  static_cast<__nv_bfloat16*>(w_t_packed), roundup64(N), static_cast<cudaStream_t>(stream));
+}
+
+// Six groups over the packed row: A1, A2, B1, B2 (K = Ci, N = Co) and the two E rows (K = 2Ci, N = 2Co, shared W_E).
+static void fill_d8_groups(octic_gemm_desc* d, int Ci, int Co, bool has_bias) {
+  d->num_groups = 6;
+  for (int g = 0; g < 4; ++g) {
+    octic_gemm_group& G = d->groups[g];
+    G.a_col = g * Ci; G.k = Ci; G.b_map = 0; G.b_row = g * Co; G.n = Co; G.c_col = g * Co;
+    G.bias_off = (g == 0 && has_bias) ? 0 : -1;
+  }
+  for (int r = 0; r < 2; ++r) {
+    octic_gemm_group& G = d->groups[4 + r];
+    G.a_col = 4 * Ci + r * 2 * Ci; G.k = 2 * Ci; G.b_map = 1; G.b_row = 0; G.n = 2 * Co;
+    G.c_col = 4 * Co + r * 2 * Co; G.bias_off = -1;
+  }
+}
+
+int octic_linear_d8_fwd(const void* x, int T, int Din, int Dout, const void* w1d, const void* wE_packed,
+                        const float* bias, const octic_gemm_desc* epi, void* stream) {
+  if (!x || !w1d || !wE_packed || !epi || Din % 8 || Dout % 8) return OCTIC_ERR_ARG;
+  const int Ci = Din / 8, Co = Dout / 8;
+  octic_gemm_desc d = *epi;
+  d.a = x; d.lda = Din; d.a_cols = Din; d.M = T;
+  d.b0 = w1d; d.b0_rows = 4L * Co; d.b0_cols = roundup64(Ci); d.b0_ld = roundup64(Ci);
+  d.b1 = wE_packed; d.b1_rows = 2L * Co; d.b1_cols = roundup64(2 * Ci); d.b1_ld = roundup64(2 * Ci);
+  d.bias = bias;
+  fill_d8_groups(&d, Ci, Co, bias != nullptr);
+  const int ns[2] = {Co, 2 * Co};
+  d.block_n = pick_block_n(ns, 2);
+  return launch_gemm_tn(&d, static_cast<cudaStream_t>(stream));
+}
+
+int octic_linear_d8_dgrad(const void* dy, int T, int Din, int Dout, const void* w1d_t, const void* wE_t, void* dx,
+                          void* stream) {
+  if (!dy || !w1d_t || !wE_t || !dx || Din % 8 || Dout % 8) return OCTIC_ERR_ARG;
+  const int Ci = Din / 8, Co = Dout / 8;
+  octic_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = dy; d.lda = Dout; d.a_cols = Dout; d.M = T;
+  d.b0 = w1d_t; d.b0_rows = 4L * Ci; d.b0_cols = roundup64(Co); d.b0_ld = roundup64(Co);
+  d.b1 = wE_t; d.b1_rows = 2L * Ci; d.b1_cols = roundup64(2 * Co); d.b1_ld = roundup64(2 * Co);
+  // roles of (Ci, Co) swap: contraction over the output features, result has Din columns
+  fill_d8_groups(&d, Co, Ci, false);
+  const int ns[2] = {Ci, 2 * Ci};
+  d.block_n = pick_block_n(ns, 2);
+  d.mode = OCTIC_EPI_BF16;
+  d.out = dx; d.ldo = Din;
+  return launch_gemm_tn(&d, static_cast<cudaStream_t>(stream));
+}
+
+int octic_linear_d8_wgrad(const void* dy, const void* x, int T, int Din, int Dout, float* dwA1, float* dwA2,
+                          float* dwB1, float* dwB2, float* dwE, void* stream) {
+  if (!dy || !x || !dwA1 || !dwA2 || !dwB1 || !dwB2 || !dwE || Din % 8 || Dout % 8) return OCTIC_ERR_ARG;
+  const int Ci = Din / 8, Co = Dout / 8;
+  octic_wgrad_desc d;
+  memset(&d, 0, sizeof(d));
+  d.dy = dy; d.ld_dy = Dout; d.dy_cols = Dout;
+  d.x = x; d.ld_x = Din; d.x_cols = Din;
+  d.T = T;
+  d.num_groups = 6;
+  float* dw[4] = {dwA1, dwA2, dwB1, dwB2};
+  for (int g = 0; g < 4; ++g) {
+    octic_wgrad_group& G = d.groups[g];
+    G.dy_col = g * Co; G.x_col = g * Ci; G.n_out = Co; G.k_in = Ci; G.dw = dw[g]; G.ldw = Ci;
+  }
+  for (int r = 0; r < 2; ++r) {   // both E rows accumulate into the same dW_E
+    octic_wgrad_group& G = d.groups[4 + r];
+    G.dy_col = 4 * Co + r * 2 * Co; G.x_col = 4 * Ci + r * 2 * Ci; G.n_out = 2 * Co; G.k_in = 2 * Ci;
+    G.dw = dwE; G.ldw = 2 * Ci;
+  }
+  int bn = roundup64(Ci);
+  d.block_n = bn > 256 ? 256 : bn;
+  d.splits = 0;
+  return launch_gemm_wgrad(&d, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

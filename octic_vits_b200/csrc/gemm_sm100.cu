@@ -1,0 +1,615 @@
+// Grouped bf16 GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma (fp32 accumulators in TMEM)
+// -> fused epilogue.  One persistent CTA per SM, warp-specialised:
+//   warp 0     TMA producer (one lane)
+//   warp 1     MMA issuer (one lane) + TMEM allocation (whole warp)
+//   warps 2-5  epilogue: tcgen05.ld -> registers -> per-warp smem transpose -> coalesced global I/O
+//
+// Two kernels live here:
+//   gemm_tn_kernel     C[m, n] = sum_k A[m, k] * B[n, k]   (both operands K-major).  A "problem" is a list of
+//                      up to 8 groups that share the token (M) dimension but have their own K-range inside
+//                      the packed activation row, their own weight rows, and their own output columns.  This
+//                      is exactly the irrep-block-diagonal LinearD8 of the reference
+//                      (octic_vits/d8_layers.py:104-127): 4 groups for A1/A2/B1/B2 and 2 groups (the two rows
+//                      of the 2-D irrep E) that share W_E.  groups = 1 is the dense nn.Linear of the
+//                      non-octic half (deit/vit.py:29-33).  dgrad reuses it with transposed weights.
+//   gemm_wgrad_kernel  dW[n_out, k_in] += sum_t dY[t, n_out] * X[t, k_in]   (both operands MN-major, the
+//                      contraction runs over tokens), split over token ranges, reduced with red.add.f32.
+#include "octic_capi_internal.h"
+#include "sm100_ptx.cuh"
+
+namespace octic {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
+constexpr int kStagingWords = 32 * 33;                // per epilogue warp: 32 rows x (32+1) words
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;                       // columns between the two accumulator stages
+
+struct SmemLayout {
+  uint32_t a_off, b_off, stg_off, bar_off, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int stages, int b_stage_bytes) {
+  SmemLayout L;
+  L.a_off = 0;
+  L.b_off = stages * kAStageBytes;
+  L.stg_off = L.b_off + stages * b_stage_bytes;
+  L.bar_off = L.stg_off + 4 * kStagingWords * 4;
+  L.total = L.bar_off + (2 * kMaxStages + 4) * 8 + 16;
+  return L;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------------------------------------------------
+//  TN kernel
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic smem base is only guaranteed 16.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.num_stages;
+  const int b_stage_bytes = p.block_n * kBlockK * 2;
+  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB0);
+    tma_prefetch_desc(&tmB1);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_tiles = p.num_m_blocks * p.tiles_per_m;
+
+  auto decode = [&](int tile, int& m_blk, int& g, int& n_blk) {
+    m_blk = tile / p.tiles_per_m;
+    int j = tile - m_blk * p.tiles_per_m;
+    g = 0;
+#pragma unroll 1
+    for (int i = 1; i < p.num_groups; ++i)
+      if (j >= p.g[i].tile_begin) g = i;
+    n_blk = j - p.g[g].tile_begin;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------ TMA producer ------------------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_blk, g, n_blk;
+        decode(tile, m_blk, g, n_blk);
+        const GemmGroup& G = p.g[g];
+        const CUtensorMap* tmB = G.b_map ? &tmB1 : &tmB0;
+        for (int kb = 0; kb < G.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes + b_stage_bytes);
+          tma_load_2d(smem + L.a_off + stage * kAStageBytes, &tmA, &full_bar[stage], G.a_col + kb * kBlockK,
+                      m_blk * kBlockM);
+          tma_load_2d(smem + L.b_off + stage * b_stage_bytes, tmB, &full_bar[stage], kb * kBlockK,
+                      G.b_row + n_blk * p.block_n);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------- MMA issuer --------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        int m_blk, g, n_blk;
+        decode(tile, m_blk, g, n_blk);
+        const int k_blocks = p.g[g].k_blocks;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          // K-major, SWIZZLE_128B: rows are 128 B, 8-row groups are 1024 B apart (SBO); LBO unused.
+          const uint64_t da = make_smem_desc(smem_u32(smem + L.a_off + stage * kAStageBytes), 0, 1024);
+          const uint64_t db = make_smem_desc(smem_u32(smem + L.b_off + stage * b_stage_bytes), 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing 16 bf16 (32 B) inside the swizzle atom = +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // --------------------------------------------- epilogue ---------------------------------------------
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    float* stg = reinterpret_cast<float*>(smem + L.stg_off) + (warp - 2) * kStagingWords;
+    const int mode = p.mode;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int m_blk, g, n_blk;
+      decode(tile, m_blk, g, n_blk);
+      const GemmGroup& G = p.g[g];
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int n0 = n_blk * p.block_n;                 // first column of the tile inside the group
+      const int n_valid = min(p.block_n, G.n - n0);     // columns of this tile that exist
+      const int row0 = m_blk * kBlockM + q * 32;        // first row handled by this warp
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+
+      for (int c0 = 0; c0 < n_valid; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        __syncwarp();
+
+        if (mode == EPI_BF16 || mode == EPI_GELU_BF16) {
+          // lane -> (row parity, column pair): each store instruction writes 2 rows x 64 B
+          const int cp = (lane & 15) * 2;
+          const int rsel = lane >> 4;
+          const int col = c0 + cp;                       // column inside the tile
+          const bool cv0 = col < n_valid, cv1 = col + 1 < n_valid;
+          float b0 = 0.f, b1 = 0.f;
+          if (p.bias != nullptr && G.bias_off >= 0) {
+            if (cv0) b0 = __ldg(p.bias + G.bias_off + n0 + col);
+            if (cv1) b1 = __ldg(p.bias + G.bias_off + n0 + col + 1);
+          }
+          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+          __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(p.branch_out);
+#pragma unroll 4
+          for (int rr = 0; rr < 16; ++rr) {
+            const int rl = rr * 2 + rsel;
+            const long m = row0 + rl;
+            if (m < p.M && cv0) {
+              float v0 = stg[rl * 33 + cp] + b0;
+              float v1 = stg[rl * 33 + cp + 1] + b1;
+              const long o = m * p.ldo + G.c_col + n0 + col;
+              if (mode == EPI_GELU_BF16) {
+                if (pre != nullptr) {
+                  if (cv1) *reinterpret_cast<__nv_bfloat162*>(pre + o) = __floats2bfloat162_rn(v0, v1);
+                  else pre[o] = __float2bfloat16(v0);
+                }
+                // the reference rounds the pre-activation to bf16 before nn.GELU under autocast
+                v0 = gelu_erf(__bfloat162float(__float2bfloat16(v0)));
+                v1 = gelu_erf(__bfloat162float(__float2bfloat16(v1)));
+              }
+              if (cv1) *reinterpret_cast<__nv_bfloat162*>(outp + o) = __floats2bfloat162_rn(v0, v1);
+              else outp[o] = __float2bfloat16(v0);
+            }
+          }
+        } else {
+          // lane -> column: 128 B of fp32 per row per instruction
+          const int col = c0 + lane;
+          const bool cv = col < n_valid;
+          float bv = 0.f, gv = 1.f;
+          if (cv) {
+            if (p.bias != nullptr && G.bias_off >= 0) bv = __ldg(p.bias + G.bias_off + n0 + col);
+            if (mode == EPI_RESID && p.gamma != nullptr) gv = __ldg(p.gamma + G.c_col + n0 + col);
+          }
+          const int rmax = min(32, p.M - row0);
+          for (int rr = 0; rr < rmax; ++rr) {
+            if (!cv) break;
+            const long m = row0 + rr;
+            float v = stg[rr * 33 + lane] + bv;
+            long mo = m;
+            if (p.remap_group > 0) mo = m + (m / p.remap_group) * p.remap_extra + p.remap_off;
+            if (mode == EPI_F32) {
+              reinterpret_cast<float*>(p.out)[mo * p.ldo + G.c_col + n0 + col] = v;
+            } else {  // EPI_RESID
+              if (p.branch_out != nullptr)
+                reinterpret_cast<__nv_bfloat16*>(p.branch_out)[mo * p.ldb + G.c_col + n0 + col] = __float2bfloat16(v);
+              // the reference's Linear emits bf16 under autocast; keep that rounding point
+              v = __bfloat162float(__float2bfloat16(v));
+              float s = gv;
+              if (p.row_scale != nullptr) s *= __ldg(p.row_scale + mo / p.rows_per_sample);
+              const long o = mo * p.ldr + G.c_col + n0 + col;
+              const float base = (p.resid_in != nullptr) ? p.resid_in[o] : 0.f;
+              p.resid_out[o] = base + s * v;
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  wgrad kernel (MN-major operands, contraction over tokens, split-K with fp32 red.add)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int stages = p.num_stages;
+  const int b_stage_bytes = p.block_n * kBlockK * 2;     // block_n is a multiple of 64 here
+  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // work item -> (group, m_tile, n_tile, split)
+  auto decode = [&](int item, int& g, int& m_t, int& n_t, int& split) {
+    split = item % p.splits;
+    int j = item / p.splits;
+    g = 0;
+#pragma unroll 1
+    for (int i = 1; i < p.num_groups; ++i)
+      if (j >= p.g[i].tile_begin) g = i;
+    j -= p.g[g].tile_begin;
+    m_t = j / p.g[g].n_tiles;
+    n_t = j - m_t * p.g[g].n_tiles;
+  };
+  const int total_items = p.total_tiles * p.splits;
+  const int kb_total = (p.T + kBlockK - 1) / kBlockK;
+  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
+  const int n_atoms = p.block_n / 64;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        int g, m_t, n_t, split;
+        decode(item, g, m_t, n_t, split);
+        const WgradGroup& G = p.g[g];
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes + b_stage_bytes);
+          uint8_t* a_dst = smem + L.a_off + stage * kAStageBytes;
+          uint8_t* b_dst = smem + L.b_off + stage * b_stage_bytes;
+          // each box: 64 features (128 B, swizzled) x 64 tokens = 8 KiB; consecutive boxes = consecutive MN atoms
+          for (int i = 0; i < 2; ++i)
+            tma_load_2d(a_dst + i * 8192, &tmDY, &full_bar[stage], G.dy_col + m_t * kBlockM + i * 64, kb * kBlockK);
+          for (int i = 0; i < n_atoms; ++i)
+            tma_load_2d(b_dst + i * 8192, &tmX, &full_bar[stage], G.x_col + n_t * p.block_n + i * 64, kb * kBlockK);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+        int g, m_t, n_t, split;
+        decode(item, g, m_t, n_t, split);
+        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          // MN-major, SWIZZLE_128B: an atom is 64 MN-elements (128 B) x 8 K-rows (1024 B).
+          // SBO = stride between 8-row groups along K (1024 B), LBO = stride between MN atoms (64 K-rows x 128 B).
+          const uint64_t da = make_smem_desc(smem_u32(smem + L.a_off + stage * kAStageBytes), 8192, 1024);
+          const uint64_t db = make_smem_desc(smem_u32(smem + L.b_off + stage * b_stage_bytes), 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // 16 K-rows x 128 B = 2048 B -> +128 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb > kb0) || (k != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0) {
+          // empty split (cannot happen with the host's choice of splits, but never leave the epilogue waiting)
+          umma_commit(&tfull_bar[as]);
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stg = reinterpret_cast<float*>(smem + L.stg_off) + (warp - 2) * kStagingWords;
+    int it = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+      int g, m_t, n_t, split;
+      decode(item, g, m_t, n_t, split);
+      const WgradGroup& G = p.g[g];
+      const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const int n0 = n_t * p.block_n;
+      const int n_valid = min(p.block_n, G.k_in - n0);
+      const int row0 = m_t * kBlockM + q * 32;            // out-feature row inside the group
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      if (kb1 > kb0) {
+        for (int c0 = 0; c0 < n_valid; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const int col = c0 + lane;
+          if (col < n_valid) {
+            const int rmax = min(32, G.n_out - row0);
+            for (int rr = 0; rr < rmax; ++rr) {
+              float* dst = G.dw + static_cast<long>(row0 + rr) * G.ldw + n0 + col;
+              atomicAdd(dst, stg[rr * 33 + lane]);   // compiles to RED.ADD.F32 (result unused)
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+//  host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] with row stride `ld` elements; box = (64 cols, box_rows), 128B swizzle.
+static int make_map_bf16(CUtensorMap* m, const void* base, long rows, long cols, long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (enc == nullptr) return OCTIC_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return OCTIC_ERR_ALIGN;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OCTIC_OK : OCTIC_ERR_TMAP;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+constexpr int kMaxDynSmem = 232448;   // 227 KiB
+
+int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
+  if (d->num_groups < 1 || d->num_groups > OCTIC_MAX_GROUPS) return OCTIC_ERR_ARG;
+  if (d->block_n < 16 || d->block_n > 256 || (d->block_n % 16) != 0) return OCTIC_ERR_ARG;
+  if (d->M <= 0) return OCTIC_OK;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = d->M;
+  p.num_groups = d->num_groups;
+  p.block_n = d->block_n;
+  p.num_m_blocks = (d->M + kBlockM - 1) / kBlockM;
+  int tiles = 0;
+  for (int i = 0; i < d->num_groups; ++i) {
+    const octic_gemm_group& s = d->groups[i];
+    GemmGroup& G = p.g[i];
+    if (s.k <= 0 || s.n <= 0) return OCTIC_ERR_ARG;
+    G.a_col = s.a_col;
+    G.k_blocks = (s.k + kBlockK - 1) / kBlockK;
+    G.b_map = s.b_map;
+    G.b_row = s.b_row;
+    G.n = s.n;
+    G.n_tiles = (s.n + d->block_n - 1) / d->block_n;
+    G.c_col = s.c_col;
+    G.bias_off = s.bias_off;
+    G.tile_begin = tiles;
+    tiles += G.n_tiles;
+  }
+  p.tiles_per_m = tiles;
+  const int b_stage_bytes = d->block_n * kBlockK * 2;
+  int stages = (kMaxDynSmem - 1024 - (4 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) return OCTIC_ERR_ARG;
+  p.num_stages = stages;
+  p.mode = d->mode;
+  p.out = d->out;
+  p.ldo = d->ldo;
+  p.bias = d->bias;
+  p.gamma = d->gamma;
+  p.resid_in = d->resid_in;
+  p.resid_out = d->resid_out;
+  p.ldr = d->ldr;
+  p.row_scale = d->row_scale;
+  p.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  p.branch_out = d->branch_out;
+  p.ldb = d->ldb;
+  p.remap_group = d->remap_group;
+  p.remap_extra = d->remap_extra;
+  p.remap_off = d->remap_off;
+  if (p.mode == EPI_RESID && p.resid_out == nullptr) return OCTIC_ERR_ARG;
+  if (p.mode != EPI_RESID && p.out == nullptr) return OCTIC_ERR_ARG;
+
+  CUtensorMap tmA, tmB0, tmB1;
+  int rc = make_map_bf16(&tmA, d->a, d->M, d->a_cols, d->lda, kBlockM);
+  if (rc) return rc;
+  rc = make_map_bf16(&tmB0, d->b0, d->b0_rows, d->b0_cols, d->b0_ld, d->block_n);
+  if (rc) return rc;
+  if (d->b1 != nullptr) {
+    rc = make_map_bf16(&tmB1, d->b1, d->b1_rows, d->b1_cols, d->b1_ld, d->block_n);
+    if (rc) return rc;
+  } else {
+    tmB1 = tmB0;
+  }
+  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+  const int smem_bytes = L.total + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (e != cudaSuccess) return OCTIC_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total_tiles = p.num_m_blocks * p.tiles_per_m;
+  int grid = num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  gemm_tn_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p);
+  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+}
+
+int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
+  if (d->num_groups < 1 || d->num_groups > OCTIC_MAX_GROUPS) return OCTIC_ERR_ARG;
+  if (d->block_n < 64 || d->block_n > 256 || (d->block_n % 64) != 0) return OCTIC_ERR_ARG;
+  if (d->T <= 0) return OCTIC_OK;
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = d->T;
+  p.num_groups = d->num_groups;
+  p.block_n = d->block_n;
+  int tiles = 0;
+  for (int i = 0; i < d->num_groups; ++i) {
+    const octic_wgrad_group& s = d->groups[i];
+    WgradGroup& G = p.g[i];
+    if (s.n_out <= 0 || s.k_in <= 0 || s.dw == nullptr) return OCTIC_ERR_ARG;
+    G.dy_col = s.dy_col;
+    G.x_col = s.x_col;
+    G.n_out = s.n_out;
+    G.k_in = s.k_in;
+    G.dw = s.dw;
+    G.ldw = s.ldw;
+    G.n_tiles = (s.k_in + d->block_n - 1) / d->block_n;
+    G.m_tiles = (s.n_out + kBlockM - 1) / kBlockM;
+    G.tile_begin = tiles;
+    tiles += G.n_tiles * G.m_tiles;
+  }
+  p.total_tiles = tiles;
+  const int kb_total = (d->T + kBlockK - 1) / kBlockK;
+  int splits = d->splits;
+  if (splits <= 0) {
+    // enough items for ~2 waves, but at least 8 k-blocks per item
+    splits = (2 * num_sms() + tiles - 1) / tiles;
+    int max_splits = kb_total / 8;
+    if (max_splits < 1) max_splits = 1;
+    if (splits > max_splits) splits = max_splits;
+  }
+  if (splits > kb_total) splits = kb_total;
+  // make sure no split is empty
+  while (splits > 1 && (splits - 1) * ((kb_total + splits - 1) / splits) >= kb_total) --splits;
+  p.splits = splits;
+  const int b_stage_bytes = d->block_n * kBlockK * 2;
+  int stages = (kMaxDynSmem - 1024 - (4 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.num_stages = stages;
+
+  CUtensorMap tmDY, tmX;
+  int rc = make_map_bf16(&tmDY, d->dy, d->T, d->dy_cols, d->ld_dy, kBlockK);
+  if (rc) return rc;
+  rc = make_map_bf16(&tmX, d->x, d->T, d->x_cols, d->ld_x, kBlockK);
+  if (rc) return rc;
+  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+  const int smem_bytes = L.total + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+    if (e != cudaSuccess) return OCTIC_ERR_CUDA;
+    attr_set = true;
+  }
+  const int total_items = tiles * splits;
+  int grid = num_sms();
+  if (grid > total_items) grid = total_items;
+  gemm_wgrad_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(tmDY, tmX, p);
+  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+}
+
+}  // namespace octic

@@ -1,0 +1,886 @@
+// HBM-bound kernels of the octic block: D8 GELU, LayerNormD8 / LayerNorm, layer-scale backward, column sums,
+// power-spectrum invariant, hybrid bridge, im2col and casts.  All of them stream packed [T, D] rows with
+// 16-byte accesses; per-token reductions are warp-shuffle, column (parameter-gradient) reductions are
+// register accumulators + one red.add per column per CTA.
+#include "octic_capi_internal.h"
+
+namespace octic {
+
+constexpr float kSqrt2Over4 = 0.35355339059327376f;
+constexpr float kInvSqrt2 = 0.70710678118654752f;
+constexpr float kInvSqrt2Pi = 0.39894228040143268f;
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * kInvSqrt2)); }
+// d/dx gelu(x) = Phi(x) + x * phi(x)      (reference octic_vits/d8_gelu.py:16-26)
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * kInvSqrt2));
+  const float pdf = kInvSqrt2Pi * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+// Isotypic -> regular (inverse D8 Fourier transform), reference octic_vits/d8_utils.py:276-303.
+__device__ __forceinline__ void i2r(const float (&x)[8], float (&y)[8]) {
+  const float a = x[0] + x[1], b = x[0] - x[1], c = x[2] + x[3], d = x[2] - x[3];
+  const float e = x[4] + x[5], f = x[4] - x[5], g = x[6] + x[7], h = x[6] - x[7];
+  const float apc = a + c, amc = a - c, bpd = b + d, bmd = b - d;
+  const float eph = e + h, emh = e - h, fpg = f + g, fmg = f - g;
+  y[0] = kSqrt2Over4 * (apc + eph);
+  y[1] = kSqrt2Over4 * (amc + fmg);
+  y[2] = kSqrt2Over4 * (apc - eph);
+  y[3] = kSqrt2Over4 * (amc - fmg);
+  y[4] = kSqrt2Over4 * (bpd - fpg);
+  y[5] = kSqrt2Over4 * (bmd - emh);
+  y[6] = kSqrt2Over4 * (bpd + fpg);
+  y[7] = kSqrt2Over4 * (bmd + emh);
+}
+// Regular -> isotypic (forward D8 Fourier transform), reference octic_vits/d8_utils.py:317-344.
+__device__ __forceinline__ void r2i(const float (&x)[8], float (&y)[8]) {
+  const float a = x[0] + x[1], b = x[0] - x[1], c = x[2] + x[3], d = x[2] - x[3];
+  const float e = x[4] + x[5], f = x[4] - x[5], g = x[6] + x[7], h = x[6] - x[7];
+  const float apc = a + c, cma = c - a, bpd = b + d, bmd = b - d;
+  const float epg = e + g, gme = g - e, fph = f + h, fmh = f - h;
+  y[0] = kSqrt2Over4 * (apc + epg);
+  y[1] = kSqrt2Over4 * (apc - epg);
+  y[2] = kSqrt2Over4 * (bpd + fph);
+  y[3] = kSqrt2Over4 * (bpd - fph);
+  y[4] = kSqrt2Over4 * (gme - cma);
+  y[5] = kSqrt2Over4 * (bmd + fmh);
+  y[6] = kSqrt2Over4 * (bmd - fmh);
+  y[7] = kSqrt2Over4 * (gme + cma);
+}
+
+// ----------------------------------------------- vector I/O -----------------------------------------------
+template <typename T, int V> struct Vec;
+template <> struct Vec<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+template <> struct Vec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      const float2 f = __bfloat1622float2(b);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 b = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&b);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <> struct Vec<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
+    const __nv_bfloat162 b0 = __floats2bfloat162_rn(v[0], v[1]);
+    const __nv_bfloat162 b1 = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t;
+    t.x = *reinterpret_cast<const uint32_t*>(&b0);
+    t.y = *reinterpret_cast<const uint32_t*>(&b1);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+template <> struct Vec<__nv_bfloat16, 1> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[1]) { v[0] = __bfloat162float(*p); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[1]) { *p = __float2bfloat16(v[0]); }
+};
+
+// column offset (in units of C) of 8-tuple component k inside the packed row
+// (x4 = E[0,:C], x5 = E[1,:C], x6 = E[0,C:], x7 = E[1,C:]; reference octic_vits/d8_utils.py:370-385)
+__device__ __constant__ int kCompOff[8] = {0, 1, 2, 3, 4, 6, 5, 7};
+
+// ------------------------------------------------- D8 GELU -------------------------------------------------
+template <typename T, int V>
+__global__ void __launch_bounds__(256) gelu_d8_fwd_kernel(const T* __restrict__ x, long ldx, T* __restrict__ y, long ldy,
+                                                          long T_rows, int C) {
+  const int nv = C / V;
+  const long total = T_rows * nv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long t = idx / nv;
+    const int c = static_cast<int>(idx - t * nv) * V;
+    float in[8][V];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) Vec<T, V>::load(x + t * ldx + kCompOff[k] * C + c, in[k]);
+    float out[8][V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float a[8], r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = in[k][v];
+      i2r(a, r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = gelu_f(r[k]);
+      r2i(r, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k][v] = a[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) Vec<T, V>::store(y + t * ldy + kCompOff[k] * C + c, out[k]);
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) gelu_d8_bwd_kernel(const T* __restrict__ g, long ldg, const T* __restrict__ x,
+                                                          long ldx, T* __restrict__ gin, long ldgin, long T_rows, int C) {
+  const int nv = C / V;
+  const long total = T_rows * nv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long t = idx / nv;
+    const int c = static_cast<int>(idx - t * nv) * V;
+    float xin[8][V], gg[8][V];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      Vec<T, V>::load(x + t * ldx + kCompOff[k] * C + c, xin[k]);
+      Vec<T, V>::load(g + t * ldg + kCompOff[k] * C + c, gg[k]);
+    }
+    float out[8][V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float a[8], u[8], b[8], gu[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { a[k] = xin[k][v]; b[k] = gg[k][v]; }
+      i2r(a, u);
+      i2r(b, gu);   // R2I = I2R^T, so the cotangent is pulled back with I2R (octic_vits/d8_gelu.py:283-321)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = gelu_grad_f(u[k]) * gu[k];
+      r2i(u, a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k][v] = a[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) Vec<T, V>::store(gin + t * ldgin + kCompOff[k] * C + c, out[k]);
+  }
+}
+
+// plain GELU backward (dense half): gin = g * gelu'(x), bf16
+__global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __restrict__ g,
+                                                       const __nv_bfloat16* __restrict__ x,
+                                                       __nv_bfloat16* __restrict__ gin, long n8) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n8;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float a[8], b[8], o[8];
+    Vec<__nv_bfloat16, 8>::load(g + i * 8, a);
+    Vec<__nv_bfloat16, 8>::load(x + i * 8, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = a[k] * gelu_grad_f(b[k]);
+    Vec<__nv_bfloat16, 8>::store(gin + i * 8, o);
+  }
+}
+
+// ------------------------------------------------ column sums ------------------------------------------------
+// out[c] += sum_t x[t, c];  block = 32 x 8 threads, each thread owns 2 columns and strides rows.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ldx, long T_rows,
+                                                          int n_cols, float* __restrict__ out, int rows_per_block) {
+  __shared__ float red[8][64];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 2;
+  const long r0 = static_cast<long>(blockIdx.y) * rows_per_block;
+  const long r1 = min(T_rows, r0 + rows_per_block);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < n_cols) {
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * ldx + c));
+      s0 += f.x; s1 += f.y;
+    }
+  }
+  red[threadIdx.y][threadIdx.x * 2] = s0;
+  red[threadIdx.y][threadIdx.x * 2 + 1] = s1;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < n_cols) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { s0 += red[i][threadIdx.x * 2]; s1 += red[i][threadIdx.x * 2 + 1]; }
+    atomicAdd(out + c, s0);
+    if (c + 1 < n_cols) atomicAdd(out + c + 1, s1);
+  }
+}
+
+// ------------------------------------------------ LayerNorm(D8) ------------------------------------------------
+// One warp per token; the whole row lives in registers (NCH float4 chunks per lane, D <= 128 * NCH).
+// D8 = true : six mean/variance groups {A1,A2,B1,B2,E0,E1}, one shared std (d8_layers.py:166-186)
+// D8 = false: ordinary LayerNorm.
+template <bool D8>
+__device__ __forceinline__ int seg_of(int col, int C) {
+  if (!D8) return 0;
+  return col < 4 * C ? col / C : 4 + (col - 4 * C) / (2 * C);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename TY, bool D8, int NCH>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restrict__ x, long ldx,
+                                                            const float* __restrict__ alpha,
+                                                            const float* __restrict__ beta, float eps,
+                                                            TY* __restrict__ y, long ldy, float* __restrict__ stats,
+                                                            long T_rows, int D) {
+  constexpr int NSEG = D8 ? 6 : 1;
+  const int lane = threadIdx.x & 31;
+  const int C = D / 8;
+  const int nchunks = D / 4;
+  const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  for (long t = warp_global; t < T_rows; t += nwarps) {
+    float v[NCH][4];
+    int seg[NCH];
+    float sum[NSEG];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) sum[s] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int ch = lane + 32 * j;
+      seg[j] = -1;
+      if (ch < nchunks) {
+        Vec<float, 4>::load(x + t * ldx + ch * 4, v[j]);
+        seg[j] = seg_of<D8>(ch * 4, C);
+        const float s4 = (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) sum[s] += (seg[j] == s) ? s4 : 0.f;
+      }
+    }
+    float mean[NSEG], var[NSEG];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+      const float n = D8 ? (s < 4 ? C : 2 * C) : D;
+      mean[s] = warp_sum(sum[s]) / n;
+      var[s] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (seg[j] >= 0) {
+        float mu = 0.f;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) mu = (seg[j] == s) ? mean[s] : mu;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[j][i] -= mu; q += v[j][i] * v[j][i]; }
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) var[s] += (seg[j] == s) ? q : 0.f;
+      }
+    }
+    float S = 0.f;
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+      const float n = D8 ? (s < 4 ? C : 2 * C) : D;
+      const float w = D8 ? (s < 4 ? 1.0f : 0.5f) : 1.0f;
+      S += w * (warp_sum(var[s]) / n);
+    }
+    // D8: std = (sqrt2/4) * sqrt(S + eps)  ->  rstd = sqrt(8 / (S + eps));   plain: rstd = 1/sqrt(var + eps)
+    const float rstd = D8 ? sqrtf(8.0f / (S + eps)) : rsqrtf(S + eps);
+    if (stats != nullptr && lane == 0) {
+      if (D8) {
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) stats[t * 8 + s] = mean[s];
+        stats[t * 8 + 6] = rstd;
+      } else {
+        stats[t * 2] = mean[0];
+        stats[t * 2 + 1] = rstd;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (seg[j] >= 0) {
+        const int col = (lane + 32 * j) * 4;
+        float a[4], o[4];
+        Vec<float, 4>::load(alpha + col, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = v[j][i] * rstd * a[i];
+        if (beta != nullptr && (!D8 || col < C)) {
+          float b[4];
+          Vec<float, 4>::load(beta + col, b);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] += b[i];
+        }
+        Vec<TY, 4>::store(y + t * ldy + col, o);
+      }
+    }
+  }
+}
+
+// Backward.  With yhat = (x - mu_g) * r, dyh = alpha * dout, Q = sum(dyh * yhat), m_g = mean_g(dyh):
+//   dx = r * (dyh - m_g - coef_g * yhat * Q),  coef_g = w_g / (8 n_g)  (D8)  or 1/D (plain)   [SURVEY A.7]
+// Parameter gradients: each lane owns fixed columns for every token it sees, so dalpha/dbeta accumulate in
+// registers and are flushed once per CTA (smem reduce over the 8 warps, then red.add).
+template <typename TDY, bool D8, int NCH>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restrict__ dy, long lddy,
+                                                            const float* __restrict__ x, long ldx,
+                                                            const float* __restrict__ stats,
+                                                            const float* __restrict__ alpha,
+                                                            const float* __restrict__ dx_in, float* __restrict__ dx_out,
+                                                            long lddx, float* __restrict__ dalpha,
+                                                            float* __restrict__ dbeta, long T_rows, int D) {
+  constexpr int NSEG = D8 ? 6 : 1;
+  extern __shared__ float red[];   // [D] dalpha + [D] dbeta
+  const int lane = threadIdx.x & 31;
+  const int C = D / 8;
+  const int nchunks = D / 4;
+  const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+
+  float acc_a[NCH][4], acc_b[NCH][4];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc_a[j][i] = 0.f; acc_b[j][i] = 0.f; }
+  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+
+  for (long t = warp_global; t < T_rows; t += nwarps) {
+    float yh[NCH][4], dyh[NCH][4];
+    int seg[NCH];
+    float mean[NSEG], msum[NSEG];
+    float rstd;
+    if (D8) {
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) mean[s] = stats[t * 8 + s];
+      rstd = stats[t * 8 + 6];
+    } else {
+      mean[0] = stats[t * 2];
+      rstd = stats[t * 2 + 1];
+    }
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) msum[s] = 0.f;
+    float Q = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int ch = lane + 32 * j;
+      seg[j] = -1;
+      if (ch < nchunks) {
+        const int col = ch * 4;
+        seg[j] = seg_of<D8>(col, C);
+        float mu = 0.f;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) mu = (seg[j] == s) ? mean[s] : mu;
+        float xv[4], a[4], d[4];
+        Vec<float, 4>::load(x + t * ldx + col, xv);
+        Vec<float, 4>::load(alpha + col, a);
+        Vec<TDY, 4>::load(dy + t * lddy + col, d);
+        float s4 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          yh[j][i] = (xv[i] - mu) * rstd;
+          dyh[j][i] = a[i] * d[i];
+          acc_a[j][i] += d[i] * yh[j][i];
+          acc_b[j][i] += d[i];
+          Q += dyh[j][i] * yh[j][i];
+          s4 += dyh[j][i];
+        }
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) msum[s] += (seg[j] == s) ? s4 : 0.f;
+      }
+    }
+    Q = warp_sum(Q);
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+      const float n = D8 ? (s < 4 ? C : 2 * C) : D;
+      msum[s] = warp_sum(msum[s]) / n;
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (seg[j] >= 0) {
+        const int col = (lane + 32 * j) * 4;
+        float m = 0.f, coef = 0.f;
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) {
+          const float cs = D8 ? (s < 4 ? 1.0f / (8.0f * C) : 0.5f / (16.0f * C)) : 1.0f / D;
+          m = (seg[j] == s) ? msum[s] : m;
+          coef = (seg[j] == s) ? cs : coef;
+        }
+        float o[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = rstd * (dyh[j][i] - m - coef * yh[j][i] * Q);
+        if (dx_in != nullptr) {
+          float b[4];
+          Vec<float, 4>::load(dx_in + t * lddx + col, b);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] += b[i];
+        }
+        Vec<float, 4>::store(dx_out + t * lddx + col, o);
+      }
+    }
+  }
+  // flush parameter gradients
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int ch = lane + 32 * j;
+    if (ch < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        atomicAdd(&red[ch * 4 + i], acc_a[j][i]);
+        atomicAdd(&red[D + ch * 4 + i], acc_b[j][i]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    if (dalpha != nullptr) atomicAdd(dalpha + i, red[i]);
+    if (dbeta != nullptr && (!D8 || i < C)) atomicAdd(dbeta + i, red[D + i]);
+  }
+}
+
+// --------------------------------------------- layer-scale backward ---------------------------------------------
+// Threads own float4 column groups, CTAs own row ranges: dy = gamma * s * dres (bf16), dgamma += dres * s * branch,
+// colsum += dy.
+template <int NV>   // float4 groups per thread (D/4 <= 256 * NV)
+__global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __restrict__ dres, long lddres,
+                                                             const __nv_bfloat16* __restrict__ branch, long ldbr,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ row_scale, int rows_per_sample,
+                                                             __nv_bfloat16* __restrict__ dy, long lddy,
+                                                             float* __restrict__ dgamma, float* __restrict__ colsum,
+                                                             long T_rows, int D, int rows_per_block) {
+  const int nchunks = D / 4;
+  const long r0 = static_cast<long>(blockIdx.x) * rows_per_block;
+  const long r1 = min(T_rows, r0 + rows_per_block);
+  float g[NV][4], ag[NV][4], as[NV][4];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int ch = threadIdx.x + 256 * j;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { ag[j][i] = 0.f; as[j][i] = 0.f; g[j][i] = 0.f; }
+    if (ch < nchunks) {
+      if (gamma != nullptr) Vec<float, 4>::load(gamma + ch * 4, g[j]);
+      else { g[j][0] = g[j][1] = g[j][2] = g[j][3] = 1.f; }
+    }
+  }
+  for (long r = r0; r < r1; ++r) {
+    const float s = row_scale != nullptr ? __ldg(row_scale + r / rows_per_sample) : 1.0f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int ch = threadIdx.x + 256 * j;
+      if (ch < nchunks) {
+        float d[4], o[4];
+        Vec<float, 4>::load(dres + r * lddres + ch * 4, d);
+        if (branch != nullptr) {
+          float b[4];
+          Vec<__nv_bfloat16, 4>::load(branch + r * ldbr + ch * 4, b);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ag[j][i] += d[i] * s * b[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[i] = g[j][i] * s * d[i];
+          // what the bias gradient sees is the bf16-rounded dy that also feeds dgrad/wgrad
+          as[j][i] += __bfloat162float(__float2bfloat16(o[i]));
+        }
+        Vec<__nv_bfloat16, 4>::store(dy + r * lddy + ch * 4, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int ch = threadIdx.x + 256 * j;
+    if (ch < nchunks) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (dgamma != nullptr) atomicAdd(dgamma + ch * 4 + i, ag[j][i]);
+        if (colsum != nullptr) atomicAdd(colsum + ch * 4 + i, as[j][i]);
+      }
+    }
+  }
+}
+
+// --------------------------------------------- invariant / bridge ---------------------------------------------
+__global__ void __launch_bounds__(256) power_spectrum_fwd_kernel(const float* __restrict__ x, long ldx,
+                                                                 __nv_bfloat16* __restrict__ y, long ldy, long T_rows,
+                                                                 int C) {
+  const int nv = 6 * C / 4;
+  const long total = T_rows * nv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long t = idx / nv;
+    const int col = static_cast<int>(idx - t * nv) * 4;   // output column
+    float a[4], o[4];
+    Vec<float, 4>::load(x + t * ldx + col, a);
+    if (col < C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = a[i];
+    } else if (col < 4 * C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = fabsf(a[i]);
+    } else {
+      float b[4];
+      Vec<float, 4>::load(x + t * ldx + col + 2 * C, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = sqrtf(a[i] * a[i] + b[i] * b[i]);
+    }
+    Vec<__nv_bfloat16, 4>::store(y + t * ldy + col, o);
+  }
+}
+
+template <typename TDY>
+__global__ void __launch_bounds__(256) power_spectrum_bwd_kernel(const TDY* __restrict__ dy, long lddy,
+                                                                 const float* __restrict__ x, long ldx,
+                                                                 float* __restrict__ dx, long lddx, long T_rows, int C) {
+  const int nv = 6 * C / 4;
+  const long total = T_rows * nv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long t = idx / nv;
+    const int col = static_cast<int>(idx - t * nv) * 4;
+    float a[4], g[4], o[4];
+    Vec<float, 4>::load(x + t * ldx + col, a);
+    Vec<TDY, 4>::load(dy + t * lddy + col, g);
+    if (col < C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = g[i];
+      Vec<float, 4>::store(dx + t * lddx + col, o);
+    } else if (col < 4 * C) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = a[i] > 0.f ? g[i] : (a[i] < 0.f ? -g[i] : 0.f);
+      Vec<float, 4>::store(dx + t * lddx + col, o);
+    } else {
+      float b[4], o2[4];
+      Vec<float, 4>::load(x + t * ldx + col + 2 * C, b);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float n = sqrtf(a[i] * a[i] + b[i] * b[i]);
+        const float inv = n > 0.f ? g[i] / n : 0.f;   // torch.norm backward: 0 at the origin
+        o[i] = a[i] * inv;
+        o2[i] = b[i] * inv;
+      }
+      Vec<float, 4>::store(dx + t * lddx + col, o);
+      Vec<float, 4>::store(dx + t * lddx + col + 2 * C, o2);
+    }
+  }
+}
+
+// packed row -> cat(convert_5tuple_to_8tuple(xs)) order: swap column blocks [5C,6C) <-> [6C,7C)
+__global__ void __launch_bounds__(256) bridge_permute_kernel(const float* __restrict__ x, long ldx, float* __restrict__ y,
+                                                             long ldy, long T_rows, int C) {
+  const int nv = 8 * C / 4;
+  const long total = T_rows * nv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long t = idx / nv;
+    const int col = static_cast<int>(idx - t * nv) * 4;
+    int src = col;
+    if (col >= 5 * C && col < 6 * C) src = col + C;
+    else if (col >= 6 * C && col < 7 * C) src = col - C;
+    float a[4];
+    Vec<float, 4>::load(x + t * ldx + src, a);
+    Vec<float, 4>::store(y + t * ldy + col, a);
+  }
+}
+
+// --------------------------------------------------- im2col ---------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ img, int B, int Cin, int Himg, int Wimg,
+                                                     int p, __nv_bfloat16* __restrict__ out, long ldo, int Kp) {
+  const int gh = Himg / p, gw = Wimg / p;
+  const long rows = static_cast<long>(B) * gh * gw;
+  const int K = Cin * p * p;
+  const long total = rows * Kp;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long row = idx / Kp;
+    const int k = static_cast<int>(idx - row * Kp);
+    float v = 0.f;
+    if (k < K) {
+      const int c = k / (p * p), ij = k - c * p * p, i = ij / p, j = ij - i * p;
+      const int b = static_cast<int>(row / (gh * gw));
+      const int pr = static_cast<int>(row - static_cast<long>(b) * gh * gw);
+      const int gy = pr / gw, gx = pr - gy * gw;
+      v = img[((static_cast<long>(b) * Cin + c) * Himg + gy * p + i) * Wimg + gx * p + j];
+    }
+    out[row * ldo + k] = __float2bfloat16(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ x, long ldx,
+                                                            __nv_bfloat16* __restrict__ y, long ldy, long rows, int cols) {
+  const int nv = cols / 4;
+  const long total = rows * nv;
+  for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = idx / nv;
+    const int c = static_cast<int>(idx - r * nv) * 4;
+    float a[4];
+    Vec<float, 4>::load(x + r * ldx + c, a);
+    Vec<__nv_bfloat16, 4>::store(y + r * ldy + c, a);
+  }
+}
+
+// ------------------------------------------------- host helpers -------------------------------------------------
+static inline int grid_for(long work_items, int block = 256, int max_blocks = 148 * 16) {
+  long b = (work_items + block - 1) / block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+static inline int last_err() { return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace octic
+
+using namespace octic;
+
+extern "C" {
+
+int octic_colsum_bf16(const void* x, long ldx, long T, int n_cols, float* out, void* stream) {
+  if (!x || !out || T < 0 || n_cols <= 0 || (n_cols & 1) || (ldx & 1)) return OCTIC_ERR_ARG;
+  if (T == 0) return OCTIC_OK;
+  const int rows_per_block = 512;
+  dim3 grid((n_cols + 63) / 64, static_cast<unsigned>((T + rows_per_block - 1) / rows_per_block)), block(32, 8);
+  colsum_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), ldx, T, n_cols, out, rows_per_block);
+  return last_err();
+}
+
+int octic_gelu_d8_fwd(const void* x, long ldx, void* y, long ldy, long T, int C, int dtype, void* stream) {
+  if (!x || !y || T < 0 || C <= 0) return OCTIC_ERR_ARG;
+  if (T == 0) return OCTIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == OCTIC_BF16) {
+    const bool v8 = (C % 8 == 0) && (ldx % 8 == 0) && (ldy % 8 == 0) && aligned16(x) && aligned16(y);
+    if (v8)
+      gelu_d8_fwd_kernel<__nv_bfloat16, 8><<<grid_for(T * (C / 8)), 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, T, C);
+    else
+      gelu_d8_fwd_kernel<__nv_bfloat16, 1><<<grid_for(T * C), 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(x), ldx, static_cast<__nv_bfloat16*>(y), ldy, T, C);
+  } else if (dtype == OCTIC_F32) {
+    const bool v4 = (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(x) && aligned16(y);
+    if (v4)
+      gelu_d8_fwd_kernel<float, 4><<<grid_for(T * (C / 4)), 256, 0, s>>>(static_cast<const float*>(x), ldx,
+                                                                         static_cast<float*>(y), ldy, T, C);
+    else
+      gelu_d8_fwd_kernel<float, 1><<<grid_for(T * C), 256, 0, s>>>(static_cast<const float*>(x), ldx,
+                                                                   static_cast<float*>(y), ldy, T, C);
+  } else {
+    return OCTIC_ERR_ARG;
+  }
+  return last_err();
+}
+
+int octic_gelu_d8_bwd(const void* g, long ldg, const void* x, long ldx, void* gin, long ldgin, long T, int C,
+                      int dtype, float* colsum, void* stream) {
+  if (!g || !x || !gin || T < 0 || C <= 0) return OCTIC_ERR_ARG;
+  if (T == 0) return OCTIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (dtype == OCTIC_BF16) {
+    const bool v8 = (C % 8 == 0) && (ldx % 8 == 0) && (ldg % 8 == 0) && (ldgin % 8 == 0) && aligned16(x) &&
+                    aligned16(g) && aligned16(gin);
+    if (v8)
+      gelu_d8_bwd_kernel<__nv_bfloat16, 8><<<grid_for(T * (C / 8)), 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(g), ldg, static_cast<const __nv_bfloat16*>(x), ldx,
+          static_cast<__nv_bfloat16*>(gin), ldgin, T, C);
+    else
+      gelu_d8_bwd_kernel<__nv_bfloat16, 1><<<grid_for(T * C), 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(g), ldg, static_cast<const __nv_bfloat16*>(x), ldx,
+          static_cast<__nv_bfloat16*>(gin), ldgin, T, C);
+    int rc = last_err();
+    if (rc) return rc;
+    // bias gradient of the preceding LinearD8 (A1 block only carries a bias, but the sum is cheap: C columns)
+    if (colsum != nullptr) return octic_colsum_bf16(gin, ldgin, T, C, colsum, stream);
+    return OCTIC_OK;
+  } else if (dtype == OCTIC_F32) {
+    if (colsum != nullptr) return OCTIC_ERR_ARG;
+    const bool v4 = (C % 4 == 0) && (ldx % 4 == 0) && (ldg % 4 == 0) && (ldgin % 4 == 0) && aligned16(x) &&
+                    aligned16(g) && aligned16(gin);
+    if (v4)
+      gelu_d8_bwd_kernel<float, 4><<<grid_for(T * (C / 4)), 256, 0, s>>>(
+          static_cast<const float*>(g), ldg, static_cast<const float*>(x), ldx, static_cast<float*>(gin), ldgin, T, C);
+    else
+      gelu_d8_bwd_kernel<float, 1><<<grid_for(T * C), 256, 0, s>>>(
+          static_cast<const float*>(g), ldg, static_cast<const float*>(x), ldx, static_cast<float*>(gin), ldgin, T, C);
+    return last_err();
+  }
+  return OCTIC_ERR_ARG;
+}
+
+int octic_gelu_bwd(const void* g, const void* x, void* gin, long n_rows, int n_cols, float* colsum, void* stream) {
+  if (!g || !x || !gin || n_rows < 0 || n_cols <= 0 || (n_cols % 8)) return OCTIC_ERR_ARG;
+  if (n_rows == 0) return OCTIC_OK;
+  const long n8 = n_rows * n_cols / 8;
+  gelu_bwd_kernel<<<grid_for(n8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(gin), n8);
+  int rc = last_err();
+  if (rc) return rc;
+  if (colsum != nullptr) return octic_colsum_bf16(gin, n_cols, n_rows, n_cols, colsum, stream);
+  return OCTIC_OK;
+}
+
+#define OCTIC_LN_DISPATCH(KERNEL, TY, D8FLAG, ...)                                          \
+  do {                                                                                      \
+    const int nch = (D / 4 + 31) / 32;                                                      \
+    if (nch <= 3) KERNEL<TY, D8FLAG, 3><<<grid, 256, smem, s>>>(__VA_ARGS__);               \
+    else if (nch <= 6) KERNEL<TY, D8FLAG, 6><<<grid, 256, smem, s>>>(__VA_ARGS__);          \
+    else if (nch <= 8) KERNEL<TY, D8FLAG, 8><<<grid, 256, smem, s>>>(__VA_ARGS__);          \
+    else if (nch <= 10) KERNEL<TY, D8FLAG, 10><<<grid, 256, smem, s>>>(__VA_ARGS__);        \
+    else if (nch <= 16) KERNEL<TY, D8FLAG, 16><<<grid, 256, smem, s>>>(__VA_ARGS__);        \
+    else return OCTIC_ERR_ARG;                                                              \
+  } while (0)
+
+static int ln_fwd_common(bool d8, const float* x, long ldx, const float* alpha, const float* beta, float eps, void* y,
+                         long ldy, int y_dtype, float* stats, long T, int D, void* stream) {
+  if (!x || !alpha || !y || T < 0 || D <= 0) return OCTIC_ERR_ARG;
+  if (d8 ? (D % 32 != 0) : (D % 4 != 0)) return OCTIC_ERR_ARG;   // C = D/8 must be a multiple of 4
+  if ((ldx % 4) || (ldy % 4) || !aligned16(x) || !aligned16(y) || !aligned16(alpha) || (beta && !aligned16(beta)))
+    return OCTIC_ERR_ALIGN;
+  if (T == 0) return OCTIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(T * 32, 256, 148 * 8);
+  const int smem = 0;
+  if (y_dtype == OCTIC_BF16) {
+    __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
+    if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, __nv_bfloat16, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+    else OCTIC_LN_DISPATCH(layernorm_fwd_kernel, __nv_bfloat16, false, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+  } else if (y_dtype == OCTIC_F32) {
+    float* yy = static_cast<float*>(y);
+    if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, float, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+    else OCTIC_LN_DISPATCH(layernorm_fwd_kernel, float, false, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+  } else {
+    return OCTIC_ERR_ARG;
+  }
+  return last_err();
+}
+
+static int ln_bwd_common(bool d8, const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
+                         const float* alpha, const float* dx_in, float* dx_out, long lddx, float* dalpha, float* dbeta,
+                         long T, int D, void* stream) {
+  if (!dy || !x || !stats || !alpha || !dx_out || T < 0 || D <= 0) return OCTIC_ERR_ARG;
+  if (d8 ? (D % 32 != 0) : (D % 4 != 0)) return OCTIC_ERR_ARG;
+  if ((ldx % 4) || (lddy % 4) || (lddx % 4) || !aligned16(x) || !aligned16(dy) || !aligned16(dx_out) ||
+      !aligned16(alpha) || (dx_in && !aligned16(dx_in)))
+    return OCTIC_ERR_ALIGN;
+  if (T == 0) return OCTIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(T * 32, 256, 148 * 4);
+  const int smem = 2 * D * static_cast<int>(sizeof(float));
+  if (dy_dtype == OCTIC_BF16) {
+    const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dy);
+    if (d8) OCTIC_LN_DISPATCH(layernorm_bwd_kernel, __nv_bfloat16, true, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
+    else OCTIC_LN_DISPATCH(layernorm_bwd_kernel, __nv_bfloat16, false, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
+  } else if (dy_dtype == OCTIC_F32) {
+    const float* d = static_cast<const float*>(dy);
+    if (d8) OCTIC_LN_DISPATCH(layernorm_bwd_kernel, float, true, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
+    else OCTIC_LN_DISPATCH(layernorm_bwd_kernel, float, false, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
+  } else {
+    return OCTIC_ERR_ARG;
+  }
+  return last_err();
+}
+
+int octic_layernorm_d8_fwd(const float* x, long ldx, const float* alpha, const float* beta, float eps, void* y,
+                           long ldy, int y_dtype, float* stats, long T, int D, void* stream) {
+  return ln_fwd_common(true, x, ldx, alpha, beta, eps, y, ldy, y_dtype, stats, T, D, stream);
+}
+int octic_layernorm_d8_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
+                           const float* alpha, const float* dx_in, float* dx_out, long lddx, float* dalpha,
+                           float* dbeta, long T, int D, void* stream) {
+  return ln_bwd_common(true, dy, lddy, dy_dtype, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, stream);
+}
+int octic_layernorm_fwd(const float* x, long ldx, const float* w, const float* b, float eps, void* y, long ldy,
+                        int y_dtype, float* stats, long T, int D, void* stream) {
+  return ln_fwd_common(false, x, ldx, w, b, eps, y, ldy, y_dtype, stats, T, D, stream);
+}
+int octic_layernorm_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
+                        const float* w, const float* dx_in, float* dx_out, long lddx, float* dw, float* db, long T,
+                        int D, void* stream) {
+  return ln_bwd_common(false, dy, lddy, dy_dtype, x, ldx, stats, w, dx_in, dx_out, lddx, dw, db, T, D, stream);
+}
+
+int octic_layerscale_bwd(const float* dres, long lddres, const void* branch, long ldbr, const float* gamma,
+                         const float* row_scale, int rows_per_sample, void* dy, long lddy, float* dgamma,
+                         float* colsum, long T, int D, void* stream) {
+  if (!dres || !dy || T < 0 || D <= 0 || (D % 4)) return OCTIC_ERR_ARG;
+  if ((lddres % 4) || (lddy % 4) || (branch && (ldbr % 4)) || !aligned16(dres) || !aligned16(dy) ||
+      (gamma && !aligned16(gamma)))
+    return OCTIC_ERR_ALIGN;
+  if (T == 0) return OCTIC_OK;
+  if (rows_per_sample <= 0) rows_per_sample = 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int rows_per_block = 64;
+  const int grid = static_cast<int>((T + rows_per_block - 1) / rows_per_block);
+  const int nchunks = D / 4;
+  const __nv_bfloat16* br = static_cast<const __nv_bfloat16*>(branch);
+  __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dy);
+  if (nchunks <= 256)
+    layerscale_bwd_kernel<1><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale, rows_per_sample, d, lddy, dgamma, colsum, T, D, rows_per_block);
+  else if (nchunks <= 512)
+    layerscale_bwd_kernel<2><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale, rows_per_sample, d, lddy, dgamma, colsum, T, D, rows_per_block);
+  else if (nchunks <= 1024)
+    layerscale_bwd_kernel<4><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale, rows_per_sample, d, lddy, dgamma, colsum, T, D, rows_per_block);
+  else
+    return OCTIC_ERR_ARG;
+  return last_err();
+}
+
+int octic_power_spectrum_fwd(const float* x, long ldx, void* y, long ldy, long T, int C, void* stream) {
+  if (!x || !y || T < 0 || C <= 0 || (C % 4)) return OCTIC_ERR_ARG;
+  if ((ldx % 4) || (ldy % 4) || !aligned16(x) || !aligned16(y)) return OCTIC_ERR_ALIGN;
+  if (T == 0) return OCTIC_OK;
+  power_spectrum_fwd_kernel<<<grid_for(T * (6 * C / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, static_cast<__nv_bfloat16*>(y), ldy, T, C);
+  return last_err();
+}
+
+int octic_power_spectrum_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, float* dx,
+                             long lddx, long T, int C, void* stream) {
+  if (!dy || !x || !dx || T < 0 || C <= 0 || (C % 4)) return OCTIC_ERR_ARG;
+  if ((ldx % 4) || (lddy % 4) || (lddx % 4) || !aligned16(x) || !aligned16(dy) || !aligned16(dx)) return OCTIC_ERR_ALIGN;
+  if (T == 0) return OCTIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(T * (6 * C / 4));
+  if (dy_dtype == OCTIC_BF16)
+    power_spectrum_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy), lddy, x, ldx, dx, lddx, T, C);
+  else if (dy_dtype == OCTIC_F32)
+    power_spectrum_bwd_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(dy), lddy, x, ldx, dx, lddx, T, C);
+  else
+    return OCTIC_ERR_ARG;
+  return last_err();
+}
+
+int octic_bridge_permute(const float* x, long ldx, float* y, long ldy, long T, int C, void* stream) {
+  if (!x || !y || x == y || T < 0 || C <= 0 || (C % 4)) return OCTIC_ERR_ARG;
+  if ((ldx % 4) || (ldy % 4) || !aligned16(x) || !aligned16(y)) return OCTIC_ERR_ALIGN;
+  if (T == 0) return OCTIC_OK;
+  bridge_permute_kernel<<<grid_for(T * (8 * C / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ldx, y, ldy, T, C);
+  return last_err();
+}
+
+int octic_im2col_patches(const float* img, int B, int Cin, int Himg, int Wimg, int p, void* out, long ldo,
+                         void* stream) {
+  if (!img || !out || B <= 0 || Cin <= 0 || p <= 0 || Himg % p || Wimg % p) return OCTIC_ERR_ARG;
+  const int Kp = roundup64(Cin * p * p);
+  if (ldo < Kp) return OCTIC_ERR_ARG;
+  const long rows = static_cast<long>(B) * (Himg / p) * (Wimg / p);
+  im2col_kernel<<<grid_for(rows * Kp), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, B, Cin, Himg, Wimg, p, static_cast<__nv_bfloat16*>(out), ldo, Kp);
+  return last_err();
+}
+
+int octic_cast_f32_to_bf16(const float* x, long ldx, void* y, long ldy, long rows, int cols, void* stream) {
+  if (!x || !y || rows < 0 || cols <= 0 || (cols % 4)) return OCTIC_ERR_ARG;
+  if ((ldx % 4) || (ldy % 4) || !aligned16(x) || (reinterpret_cast<uintptr_t>(y) & 7)) return OCTIC_ERR_ALIGN;
+  if (rows == 0) return OCTIC_OK;
+  cast_f32_bf16_kernel<<<grid_for(rows * (cols / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, static_cast<__nv_bfloat16*>(y), ldy, rows, cols);
+  return last_err();
+}
+
+}  // extern "C"
