@@ -74,14 +74,14 @@ _I2R_SIGNS = torch.tensor([
 
 
 def isotypic_to_regular(xs8: Sequence[Tensor]) -> List[Tensor]:
-    m = _I2R_SIGNS.to(xs8[0].dtype) * RT2_4
+    m = _I2R_SIGNS.to(dtype=xs8[0].dtype, device=xs8[0].device) * RT2_4
     x = torch.stack(list(xs8), dim=-1)
     y = x @ m.T
     return list(y.unbind(-1))
 
 
 def regular_to_isotypic(xs8: Sequence[Tensor]) -> List[Tensor]:
-    m = _I2R_SIGNS.to(xs8[0].dtype) * RT2_4
+    m = _I2R_SIGNS.to(dtype=xs8[0].dtype, device=xs8[0].device) * RT2_4
     x = torch.stack(list(xs8), dim=-1)
     y = x @ m
     return list(y.unbind(-1))
