@@ -1,0 +1,334 @@
+"""Differentiable ops on packed octic rows (torch.autograd.Function wrappers over ops.py).
+
+Dtype policy = what the reference does under torch.autocast(bfloat16): the residual stream and
+LayerNorm statistics are fp32, every linear / attention / GELU consumes and produces bf16, accumulation is fp32.
+All activations here are 2-D [T, D] (T = B*N tokens) packed rows; parameters are the reference's own fp32 tensors.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+from ._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID, OcticError
+
+# ----------------------------------------------------------------------------------------------------------------
+# packing cache: fp32 parameters -> bf16 GEMM operands, re-packed only when a parameter's version changes
+# (optimizer steps bump ._version; load_state_dict copies in place and bumps it too)
+# ----------------------------------------------------------------------------------------------------------------
+_pack_cache: dict = {}
+
+
+def _cached(tensors, build):
+    """Cache only for nn.Parameters (stable identity); derived weights (e.g. the expanded patch-embed filters) are
+    packed on every call.  An entry is valid while the same objects still hold the same storage at the same version."""
+    if not all(isinstance(t, torch.nn.Parameter) for t in tensors):
+        with torch.no_grad():
+            return build()
+    ident = tuple(id(t) for t in tensors)
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    hit = _pack_cache.get(ident)
+    if hit is not None and hit[0] == key and all(r() is t for r, t in zip(hit[2], tensors)):
+        return hit[1]
+    with torch.no_grad():
+        pk = build()
+    _pack_cache[ident] = (key, pk, tuple(weakref.ref(t) for t in tensors))
+    return pk
+
+
+def packed_d8(weights: Tuple[torch.Tensor, ...]) -> ops.PackedD8:
+    return _cached(weights, lambda: ops.pack_linear_d8(*[w.detach() for w in weights]))
+
+
+def packed_dense(weight: torch.Tensor) -> ops.PackedDense:
+    return _cached((weight,), lambda: ops.pack_linear(weight.detach().contiguous()))
+
+
+def clear_pack_cache() -> None:
+    _pack_cache.clear()
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# LinearD8  (reference octic_vits/d8_layers.py:104-127)
+# ----------------------------------------------------------------------------------------------------------------
+class LinearD8Fn(torch.autograd.Function):
+    """y_bf16[T, Dout] = LinearD8(x_bf16[T, Din])."""
+
+    @staticmethod
+    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias):
+        x = _c(x)
+        pk = packed_d8((wA1, wA2, wB1, wB2, wE))
+        y = torch.empty(x.shape[0], pk.dout, dtype=torch.bfloat16, device=x.device)
+        ops.linear_d8(x, pk, bias, EPI_BF16, out=y)
+        ctx.save_for_backward(x)
+        ctx.pk = pk
+        ctx.has_bias = bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        pk = ctx.pk
+        dy = _c(dy)
+        dx = ops.linear_d8_dgrad(dy, pk) if ctx.needs_input_grad[0] else None
+        dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
+        db = ops.colsum_bf16(dy, pk.dout // 8) if (ctx.has_bias and ctx.needs_input_grad[6]) else None
+        return (dx, *dws, db)
+
+
+class LinearD8ResidualFn(torch.autograd.Function):
+    """resid_out_f32 = resid_f32 + row_scale * gamma * bf16(LinearD8(x_bf16))  -- the proj / fc2 GEMM with the
+    LayerScaleD8 / AffineD8(bias=False), DropPathD8 and residual add of the block fused into its epilogue
+    (reference d8_layers.py:698-707, 759-776, 205-212, 249-282)."""
+
+    @staticmethod
+    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, gamma, resid, row_scale, rows_per_sample):
+        x = _c(x)
+        pk = packed_d8((wA1, wA2, wB1, wB2, wE))
+        need_branch = gamma is not None and gamma.requires_grad and torch.is_grad_enabled()
+        out = torch.empty_like(resid)
+        branch = torch.empty(x.shape[0], pk.dout, dtype=torch.bfloat16, device=x.device) if need_branch else None
+        ops.linear_d8(x, pk, bias, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out, row_scale=row_scale,
+                      rows_per_sample=rows_per_sample, branch_out=branch)
+        ctx.save_for_backward(x, branch, gamma, row_scale)
+        ctx.pk = pk
+        ctx.rows_per_sample = rows_per_sample
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, branch, gamma, row_scale = ctx.saved_tensors
+        pk = ctx.pk
+        dout = _c(dout)
+        dy, dgamma, colsum = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
+                                                want_colsum=ctx.has_bias)
+        dx = ops.linear_d8_dgrad(dy, pk) if ctx.needs_input_grad[0] else None
+        dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
+        db = colsum[: pk.dout // 8] if ctx.has_bias else None
+        return (dx, *dws, db, dgamma, dout, None, None)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# dense nn.Linear  (deit/vit.py:29-33, timm Mlp)
+# ----------------------------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x_bf16 @ W^T + b, bf16 out (or fp32 when out_f32); optional fused exact GELU (saves the pre-activation)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gelu: bool, out_f32: bool):
+        x = _c(x)
+        pk = packed_dense(weight)
+        n, k = pk.n, pk.k
+        y = torch.empty(x.shape[0], n, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
+        pre = None
+        if gelu:
+            pre = torch.empty(x.shape[0], n, dtype=torch.bfloat16, device=x.device) if torch.is_grad_enabled() else None
+            ops.linear_dense(x, pk.w, n, k, bias, EPI_GELU_BF16, out=y, branch_out=pre)
+        else:
+            ops.linear_dense(x, pk.w, n, k, bias, EPI_F32 if out_f32 else EPI_BF16, out=y)
+        ctx.save_for_backward(x, pre)
+        ctx.pk, ctx.gelu, ctx.has_bias = pk, gelu, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre = ctx.saved_tensors
+        pk = ctx.pk
+        n, k = pk.n, pk.k
+        dy = _c(dy)
+        if dy.dtype != torch.bfloat16:
+            dy = ops.cast_bf16(dy) if dy.shape[1] % 4 == 0 else dy.to(torch.bfloat16)
+        if n % 8:   # TMA needs 16-byte row strides: pad tiny heads (e.g. 10 classes) with zero columns
+            dy = torch.nn.functional.pad(dy, (0, 8 - n % 8))
+        db = None
+        if ctx.gelu:
+            colsum = torch.zeros(n, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            dy = ops.gelu_bwd(dy, pre, colsum)
+            db = colsum
+        elif ctx.has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum_bf16(dy)[:n]
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape[0], k, dtype=torch.bfloat16, device=x.device)
+            ops.linear_dense(dy, pk.w_t, k, n, None, EPI_BF16, out=dx)
+        dw = ops.linear_dense_wgrad(dy, x, n, k) if ctx.needs_input_grad[1] else None
+        return dx, dw, db, None, None
+
+
+class LinearResidualFn(torch.autograd.Function):
+    """resid_out = resid + row_scale * gamma * bf16(x @ W^T + b): dense proj / fc2 with layer scale, DropPath and the
+    residual add fused (deit/vit.py:131-134).  `remap` scatters GEMM rows into a larger token matrix (patch embed)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, gamma, resid, row_scale, rows_per_sample, remap):
+        x = _c(x)
+        pk = packed_dense(weight)
+        need_branch = gamma is not None and gamma.requires_grad and torch.is_grad_enabled()
+        out = torch.empty_like(resid)
+        if remap != (0, 0, 0):
+            out.copy_(resid)        # rows the GEMM does not touch (cls tokens) must carry over
+        branch = torch.empty(resid.shape[0], pk.n, dtype=torch.bfloat16, device=x.device) if need_branch else None
+        ops.linear_dense(x, pk.w, pk.n, pk.k, bias, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out,
+                         row_scale=row_scale, rows_per_sample=rows_per_sample, branch_out=branch, remap=remap)
+        ctx.save_for_backward(x, branch, gamma, row_scale)
+        ctx.pk, ctx.rows_per_sample, ctx.has_bias, ctx.remap = pk, rows_per_sample, bias is not None, remap
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, branch, gamma, row_scale = ctx.saved_tensors
+        pk = ctx.pk
+        dout = _c(dout)
+        if ctx.remap != (0, 0, 0):
+            grp, extra, off = ctx.remap
+            # gather the rows the GEMM wrote: [M/grp, grp + extra, D] -> rows off..off+grp of every group
+            d3 = dout.view(-1, grp + extra, dout.shape[1])[:, off:off + grp, :]
+            dy = d3.to(torch.bfloat16).reshape(-1, dout.shape[1])
+            dgamma = None
+            colsum = dy.float().sum(0) if ctx.has_bias else None
+        else:
+            dy, dgamma, colsum = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
+                                                    want_colsum=ctx.has_bias)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape[0], pk.k, dtype=torch.bfloat16, device=x.device)
+            ops.linear_dense(dy, pk.w_t, pk.k, pk.n, None, EPI_BF16, out=dx)
+        dw = ops.linear_dense_wgrad(dy, x, pk.n, pk.k) if ctx.needs_input_grad[1] else None
+        return dx, dw, colsum, dgamma, dout, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# normalisation
+# ----------------------------------------------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """LayerNormD8 + AffineD8 (d8=True, reference d8_layers.py:161-186, 132-158; alpha is the packed [D] vector with
+    alpha_E repeated for both E rows) or nn.LayerNorm (d8=False).  fp32 in, bf16 or fp32 out."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, beta, eps: float, d8: bool, out_bf16: bool):
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        y, stats = ops.layernorm_fwd(x, alpha, beta, eps, d8, torch.bfloat16 if out_bf16 else torch.float32,
+                                     want_stats=torch.is_grad_enabled())
+        ctx.save_for_backward(x, stats, alpha)
+        ctx.d8, ctx.has_beta = d8, beta is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, alpha = ctx.saved_tensors
+        dy = _c(dy)
+        dx, dalpha, dbeta = ops.layernorm_bwd(dy, x, stats, alpha, ctx.d8)
+        return dx, dalpha, (dbeta if ctx.has_beta else None), None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# D8 GELU  (reference octic_vits/d8_gelu.py:456-482)
+# ----------------------------------------------------------------------------------------------------------------
+class GeluD8Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return ops.gelu_d8_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_d8_bwd(_c(g), x)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention core  (reference d8_layers.py:632-656 + F.scaled_dot_product_attention; deit/vit.py:36-50)
+# ----------------------------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, B: int, N: int, H: int, hd: int, octic: bool):
+        qkv = _c(qkv)
+        o, lse = ops.attention_fwd(qkv, B, N, H, hd, octic, want_lse=torch.is_grad_enabled())
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.cfg = (B, N, H, hd, octic)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        B, N, H, hd, octic = ctx.cfg
+        return ops.attention_bwd(qkv, o, _c(d_o), lse, B, N, H, hd, octic), None, None, None, None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# invariantisation / bridge  (reference d8_invariantization.py:49-64, model.py:196-200)
+# ----------------------------------------------------------------------------------------------------------------
+class PowerSpectrumFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        return ops.power_spectrum_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.power_spectrum_bwd(_c(dy), x)
+
+
+class BridgeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.bridge_permute(_c(x))
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.bridge_permute(_c(dy))
+
+
+class Im2ColFn(torch.autograd.Function):
+    """Patches of an image as GEMM rows (no gradient w.r.t. the image: it is the network input)."""
+
+    @staticmethod
+    def forward(ctx, img, p: int):
+        return ops.im2col_patches(_c(img), p)
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# 5-tuple <-> packed rows
+# ----------------------------------------------------------------------------------------------------------------
+def pack_five(xs) -> torch.Tensor:
+    """(A1, A2, B1, B2, E) -> [B, N, 8C].  If the five tensors already are the views handed out by `unpack_five`
+    of one packed tensor, that tensor is returned without a copy."""
+    if len(xs) != 5:
+        raise AssertionError("Input should be a 5-tuple")
+    a1 = xs[0]
+    base = getattr(a1, "_base", None)
+    C = a1.shape[-1]
+    if (base is not None and base.dim() == 3 and base.shape[-1] == 8 * C and base.is_contiguous()
+            and all(getattr(t, "_base", None) is base for t in xs)
+            and all(xs[i].storage_offset() == base.storage_offset() + i * C for i in range(4))
+            and xs[4].storage_offset() == base.storage_offset() + 4 * C and xs[4].shape[-2:] == (2, 2 * C)):
+        return base
+    e = xs[4]
+    return torch.cat((xs[0], xs[1], xs[2], xs[3], e[..., 0, :], e[..., 1, :]), dim=-1)
+
+
+def unpack_five(x: torch.Tensor):
+    """[B, N, 8C] -> strided views (A1, A2, B1, B2, E[B, N, 2, 2C]) of the same storage."""
+    C = x.shape[-1] // 8
+    return (x[..., 0:C], x[..., C:2 * C], x[..., 2 * C:3 * C], x[..., 3 * C:4 * C],
+            x[..., 4 * C:].unflatten(-1, (2, 2 * C)))
+
+
+def require_cuda(t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise OcticError("octic_vits_b200 runs on sm_100 GPUs only: got a CPU tensor (no CPU fallback exists)")
