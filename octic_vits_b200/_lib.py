@@ -117,5 +117,47 @@ def check(rc: int, what: str) -> None:
         raise OcticError(f"{what} failed: {msg} (code {rc})")
 
 
-def call(name: str, *args) -> None:
-    check(getattr(load(), name)(*args), name)
+# kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_attention_bwd": 3}
+
+
+class _Stats:
+    """Launch counter + optional CUDA-event timing of selected entry points (used by bench.py only)."""
+
+    def __init__(self):
+        self.profile_prefixes = ()
+        self.reset()
+
+    def reset(self):
+        self.kernel_launches = 0
+        self.calls = {}
+        self._events = []
+
+    def collect(self):
+        """(total ms, total algorithmic FLOPs, number of timed calls) of the profiled entry points; synchronises."""
+        import torch
+        torch.cuda.synchronize()
+        ms = sum(a.elapsed_time(b) for a, b, _ in self._events)
+        flops = sum(f for _, _, f in self._events)
+        n = len(self._events)
+        self._events = []
+        return ms, flops, n
+
+
+STATS = _Stats()
+
+
+def call(name: str, *args, flops: float = 0.0, extra_kernels: int = 0) -> None:
+    fn = getattr(load(), name)
+    STATS.kernel_launches += KERNELS_PER_CALL.get(name, 1) + extra_kernels
+    STATS.calls[name] = STATS.calls.get(name, 0) + 1
+    if STATS.profile_prefixes and name in STATS.profile_prefixes:
+        import torch
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rc = fn(*args)
+        b.record()
+        STATS._events.append((a, b, flops))
+    else:
+        rc = fn(*args)
+    check(rc, name)

@@ -91,7 +91,7 @@ class LinearD8ResidualFn(torch.autograd.Function):
     def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, gamma, resid, row_scale, rows_per_sample):
         x = _c(x)
         pk = packed_d8((wA1, wA2, wB1, wB2, wE))
-        need_branch = gamma is not None and gamma.requires_grad and torch.is_grad_enabled()
+        need_branch = gamma is not None and ctx.needs_input_grad[7]
         out = torch.empty_like(resid)
         branch = torch.empty(x.shape[0], pk.dout, dtype=torch.bfloat16, device=x.device) if need_branch else None
         ops.linear_d8(x, pk, bias, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out, row_scale=row_scale,
@@ -129,7 +129,7 @@ class LinearFn(torch.autograd.Function):
         y = torch.empty(x.shape[0], n, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
         pre = None
         if gelu:
-            pre = torch.empty(x.shape[0], n, dtype=torch.bfloat16, device=x.device) if torch.is_grad_enabled() else None
+            pre = torch.empty(x.shape[0], n, dtype=torch.bfloat16, device=x.device) if any(ctx.needs_input_grad) else None
             ops.linear_dense(x, pk.w, n, k, bias, EPI_GELU_BF16, out=y, branch_out=pre)
         else:
             ops.linear_dense(x, pk.w, n, k, bias, EPI_F32 if out_f32 else EPI_BF16, out=y)
@@ -170,7 +170,7 @@ class LinearResidualFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, resid, row_scale, rows_per_sample, remap):
         x = _c(x)
         pk = packed_dense(weight)
-        need_branch = gamma is not None and gamma.requires_grad and torch.is_grad_enabled()
+        need_branch = gamma is not None and ctx.needs_input_grad[3]
         out = torch.empty_like(resid)
         if remap != (0, 0, 0):
             out.copy_(resid)        # rows the GEMM does not touch (cls tokens) must carry over
@@ -216,7 +216,7 @@ class LayerNormFn(torch.autograd.Function):
         if x.stride(-1) != 1:
             x = x.contiguous()
         y, stats = ops.layernorm_fwd(x, alpha, beta, eps, d8, torch.bfloat16 if out_bf16 else torch.float32,
-                                     want_stats=torch.is_grad_enabled())
+                                     want_stats=any(ctx.needs_input_grad))
         ctx.save_for_backward(x, stats, alpha)
         ctx.d8, ctx.has_beta = d8, beta is not None
         return y
@@ -252,7 +252,7 @@ class AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, B: int, N: int, H: int, hd: int, octic: bool):
         qkv = _c(qkv)
-        o, lse = ops.attention_fwd(qkv, B, N, H, hd, octic, want_lse=torch.is_grad_enabled())
+        o, lse = ops.attention_fwd(qkv, B, N, H, hd, octic, want_lse=any(ctx.needs_input_grad))
         ctx.save_for_backward(qkv, o, lse)
         ctx.cfg = (B, N, H, hd, octic)
         return o

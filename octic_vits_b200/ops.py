@@ -140,7 +140,7 @@ def linear_d8(x: torch.Tensor, pk: PackedD8, bias: Optional[torch.Tensor], mode:
         _req(bias, torch.float32, "bias", ndim=1)
     d = _epilogue_desc(mode, **epi)
     call("octic_linear_d8_fwd", x.data_ptr(), x.shape[0], pk.din, pk.dout, pk.w1d.data_ptr(), pk.wE.data_ptr(),
-         _ptr(bias), C.byref(d), _stream())
+         _ptr(bias), C.byref(d), _stream(), flops=2.0 * x.shape[0] * pk.din * pk.dout * 3 / 16)
 
 
 def linear_d8_dgrad(dy: torch.Tensor, pk: PackedD8) -> torch.Tensor:
@@ -149,7 +149,7 @@ def linear_d8_dgrad(dy: torch.Tensor, pk: PackedD8) -> torch.Tensor:
         raise _lib.OcticError("dy must be a dense [T, Dout] bf16 matrix")
     dx = torch.empty(dy.shape[0], pk.din, dtype=torch.bfloat16, device=dy.device)
     call("octic_linear_d8_dgrad", dy.data_ptr(), dy.shape[0], pk.din, pk.dout, pk.w1d_t.data_ptr(),
-         pk.wE_t.data_ptr(), dx.data_ptr(), _stream())
+         pk.wE_t.data_ptr(), dx.data_ptr(), _stream(), flops=2.0 * dy.shape[0] * pk.din * pk.dout * 3 / 16)
     return dx
 
 
@@ -160,7 +160,8 @@ def linear_d8_wgrad(dy: torch.Tensor, x: torch.Tensor, din: int, dout: int):
     dws = [torch.zeros(co, ci, dtype=torch.float32, device=x.device) for _ in range(4)]
     dwE = torch.zeros(2 * co, 2 * ci, dtype=torch.float32, device=x.device)
     call("octic_linear_d8_wgrad", dy.data_ptr(), x.data_ptr(), x.shape[0], din, dout, dws[0].data_ptr(),
-         dws[1].data_ptr(), dws[2].data_ptr(), dws[3].data_ptr(), dwE.data_ptr(), _stream())
+         dws[1].data_ptr(), dws[2].data_ptr(), dws[3].data_ptr(), dwE.data_ptr(), _stream(),
+         flops=2.0 * x.shape[0] * din * dout * 3 / 16)
     return (*dws, dwE)
 
 
@@ -179,7 +180,7 @@ def linear_dense(x: torch.Tensor, w: torch.Tensor, n: int, k: int, bias: Optiona
     g.bias_off = 0 if bias is not None else -1
     d.bias = _ptr(bias)
     d.block_n = _pick_block_n([n])
-    call("octic_gemm_bf16", C.byref(d), _stream())
+    call("octic_gemm_bf16", C.byref(d), _stream(), flops=2.0 * x.shape[0] * n * k)
 
 
 def linear_dense_wgrad(dy: torch.Tensor, x: torch.Tensor, n: int, k: int, dw: Optional[torch.Tensor] = None,
@@ -198,7 +199,7 @@ def linear_dense_wgrad(dy: torch.Tensor, x: torch.Tensor, n: int, k: int, dw: Op
     g.dy_col, g.x_col, g.n_out, g.k_in, g.dw, g.ldw = 0, 0, n, k, dw.data_ptr(), dw.stride(0)
     d.block_n = min(256, roundup64(k))
     d.splits = splits
-    call("octic_gemm_wgrad_bf16", C.byref(d), _stream())
+    call("octic_gemm_wgrad_bf16", C.byref(d), _stream(), flops=2.0 * x.shape[0] * n * k)
     return dw
 
 
@@ -218,7 +219,7 @@ def gelu_d8_bwd(g: torch.Tensor, x: torch.Tensor, colsum: Optional[torch.Tensor]
     _req(g, x.dtype, "g")
     gin = torch.empty_like(x)
     call("octic_gelu_d8_bwd", g.data_ptr(), g.stride(0), x.data_ptr(), x.stride(0), gin.data_ptr(), gin.stride(0),
-         x.shape[0], x.shape[1] // 8, _dt(x), _ptr(colsum), _stream())
+         x.shape[0], x.shape[1] // 8, _dt(x), _ptr(colsum), _stream(), extra_kernels=int(colsum is not None))
     return gin
 
 
@@ -228,7 +229,8 @@ def gelu_bwd(g: torch.Tensor, x: torch.Tensor, colsum: Optional[torch.Tensor] = 
     if not (x.is_contiguous() and g.is_contiguous()):
         raise _lib.OcticError("gelu_bwd expects contiguous matrices")
     gin = torch.empty_like(x)
-    call("octic_gelu_bwd", g.data_ptr(), x.data_ptr(), gin.data_ptr(), x.shape[0], x.shape[1], _ptr(colsum), _stream())
+    call("octic_gelu_bwd", g.data_ptr(), x.data_ptr(), gin.data_ptr(), x.shape[0], x.shape[1], _ptr(colsum), _stream(),
+         extra_kernels=int(colsum is not None))
     return gin
 
 
