@@ -91,16 +91,25 @@ __device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], const __nv_bfloat16*
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-// Stage rows [0, Npad) of tensor s of (b, h) into smem (zero rows >= N).
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Stage rows [0, Npad) of tensor s of (b, h) into smem (zero rows >= N) with 4-byte cp.async: the gather of the
+// head vector from the packed row happens here.  Caller must cp_async_wait_all() + __syncthreads().
 template <int HD>
 __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src_rows, long ld, int s, int N,
                                            int Npad, const int* cb, const int* sm) {
   constexpr int STR = HD + 8;
   for (int idx = threadIdx.x; idx < Npad * (HD / 2); idx += blockDim.x) {
     const int row = idx / (HD / 2), jp = idx - row * (HD / 2);
-    uint32_t v = 0;
-    if (row < N) v = *reinterpret_cast<const uint32_t*>(src_rows + row * ld + cb[jp] + s * sm[jp]);
-    *reinterpret_cast<uint32_t*>(dst + row * STR + jp * 2) = v;
+    __nv_bfloat16* d = dst + row * STR + jp * 2;
+    if (row < N) cp_async4(d, src_rows + row * ld + cb[jp] + s * sm[jp]);
+    else *reinterpret_cast<uint32_t*>(d) = 0u;
   }
 }
 
@@ -122,7 +131,7 @@ __device__ __forceinline__ void load_a_rows(uint32_t (&a)[HD / 16][4], const __n
 
 // ------------------------------------------------------ forward ------------------------------------------------------
 template <int HD>
-__global__ void __launch_bounds__(384) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
+__global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
                                                        float* __restrict__ lse, int N, int H, HeadMap m, float scale_log2) {
   constexpr int STR = HD + 8, KS = HD / 16, DT = HD / 8;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(384) attn_fwd_kernel(const __nv_bfloat16* __re
   __syncthreads();
   stage_rows<HD>(Ks, rows, ld3, 1, N, Npad, cb, sm);
   stage_rows<HD>(Vs, rows, ld3, 2, N, Npad, cb, sm);
+  cp_async_wait_all();
   __syncthreads();
 
   const int ntiles = Npad / 16;
@@ -274,9 +284,9 @@ __device__ __forceinline__ void stage_o_rows(__nv_bfloat16* dst, const __nv_bflo
   constexpr int STR = HD + 8;
   for (int idx = threadIdx.x; idx < Npad * (HD / 2); idx += blockDim.x) {
     const int row = idx / (HD / 2), jp = idx - row * (HD / 2);
-    uint32_t v = 0;
-    if (row < N) v = *reinterpret_cast<const uint32_t*>(src_rows + row * ld + ocb[jp]);
-    *reinterpret_cast<uint32_t*>(dst + row * STR + jp * 2) = v;
+    __nv_bfloat16* d = dst + row * STR + jp * 2;
+    if (row < N) cp_async4(d, src_rows + row * ld + ocb[jp]);
+    else *reinterpret_cast<uint32_t*>(d) = 0u;
   }
 }
 template <int HD>
@@ -297,7 +307,7 @@ __device__ __forceinline__ void load_a_o_rows(uint32_t (&a)[HD / 16][4], const _
 // Warps own 16 key rows.  S^T = K Q^T, P^T = exp(S^T*scale - lse[q]), dV += P^T dO, dP^T = V dO^T,
 // dS^T = P^T (dP^T - delta[q]), dK += scale * dS^T Q.
 template <int HD>
-__global__ void __launch_bounds__(384) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(288) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                           const __nv_bfloat16* __restrict__ d_o,
                                                           const float* __restrict__ lse, const float* __restrict__ delta,
                                                           __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
@@ -334,6 +344,7 @@ __global__ void __launch_bounds__(384) attn_bwd_kv_kernel(const __nv_bfloat16* _
   __syncthreads();
   stage_rows<HD>(Qs, rows, ld3, 0, N, Npad, cb, sm);
   stage_o_rows<HD>(dOs, dorows, m.D, N, Npad, ocb);
+  cp_async_wait_all();
   __syncthreads();
 
   const int ntiles = Npad / 16;
@@ -431,7 +442,7 @@ __global__ void __launch_bounds__(384) attn_bwd_kv_kernel(const __nv_bfloat16* _
 // ------------------------------------------- backward pass B: dQ -------------------------------------------
 // Warps own 16 query rows.  S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P (dP - delta), dQ = scale * dS K.
 template <int HD>
-__global__ void __launch_bounds__(384) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                          const __nv_bfloat16* __restrict__ d_o,
                                                          const float* __restrict__ lse, const float* __restrict__ delta,
                                                          __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
@@ -461,6 +472,7 @@ __global__ void __launch_bounds__(384) attn_bwd_q_kernel(const __nv_bfloat16* __
   __syncthreads();
   stage_rows<HD>(Ks, rows, ld3, 1, N, Npad, cb, sm);
   stage_rows<HD>(Vs, rows, ld3, 2, N, Npad, cb, sm);
+  cp_async_wait_all();
   __syncthreads();
 
   const int ntiles = Npad / 16;
@@ -543,7 +555,7 @@ __global__ void __launch_bounds__(384) attn_bwd_q_kernel(const __nv_bfloat16* __
 // ------------------------------------------------------ host ------------------------------------------------------
 static int attn_warps(int N) {
   const int ntiles = (N + 15) / 16;
-  const int rounds = (ntiles + 11) / 12;
+  const int rounds = (ntiles + 8) / 9;   // at most 9 warps (288 threads) per CTA
   return (ntiles + rounds - 1) / rounds;
 }
 static int make_head_map(HeadMap* m, int H, int hd, int octic) {

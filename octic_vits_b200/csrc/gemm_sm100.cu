@@ -22,7 +22,8 @@ namespace octic {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;          // TN kernel: 2 + 8 epilogue warps
+constexpr int kWgradThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
 constexpr int kStagingWords = 32 * 33;                // per epilogue warp: 32 rows x (32+1) words
@@ -37,16 +38,36 @@ __host__ __device__ inline SmemLayout smem_layout(int stages, int b_stage_bytes)
   L.a_off = 0;
   L.b_off = stages * kAStageBytes;
   L.stg_off = L.b_off + stages * b_stage_bytes;
-  L.bar_off = L.stg_off + 4 * kStagingWords * 4;
+  L.bar_off = L.stg_off + 8 * kStagingWords * 4;
   L.total = L.bar_off + (2 * kMaxStages + 4) * 8 + 16;
   return L;
 }
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one MUFU.RCP + one MUFU.EX2 + 6 FMA instead of erff's ~30
+__device__ __forceinline__ float erf_fast(float x) {
+  const float z = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);
+  return copysignf(e, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 // ------------------------------------------------------------------------------------------------------------
 //  TN kernel
 // ------------------------------------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ GemmParams p) {
@@ -76,7 +97,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], 8);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -154,9 +175,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // --------------------------------------------- epilogue ---------------------------------------------
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    float* stg = reinterpret_cast<float*>(smem + L.stg_off) + (warp - 2) * kStagingWords;
-    const int mode = p.mode;
+    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter alternate 32-column chunks.
+    // A chunk goes TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced global I/O (lane = column).
+    const int ew = warp - 2;
+    const int q = warp & 3;
+    const int half = ew >> 2;
+    const uint32_t stg = smem_u32(smem + L.stg_off) + ew * kStagingWords * 4;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int m_blk, g, n_blk;
@@ -169,48 +193,65 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = n_blk * p.block_n;                 // first column of the tile inside the group
       const int n_valid = min(p.block_n, G.n - n0);     // columns of this tile that exist
       const int row0 = m_blk * kBlockM + q * 32;        // first row handled by this warp
+      const int rmax = min(32, p.M - row0);
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      const bool has_bias = p.bias != nullptr && G.bias_off >= 0;
 
-      for (int c0 = 0; c0 < n_valid; c0 += 32) {
+      for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
         uint32_t r[32];
         tmem_ld_32x32(t_addr + c0, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) sts_u32(stg + (lane * 33 + j) * 4, r[j]);
         __syncwarp();
+        const bool full = (rmax == 32) && (c0 + 32 <= n_valid);
 
-        if (mode == EPI_BF16 || mode == EPI_GELU_BF16) {
+        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
           // lane -> (row parity, column pair): each store instruction writes 2 rows x 64 B
           const int cp = (lane & 15) * 2;
           const int rsel = lane >> 4;
           const int col = c0 + cp;                       // column inside the tile
           const bool cv0 = col < n_valid, cv1 = col + 1 < n_valid;
           float b0 = 0.f, b1 = 0.f;
-          if (p.bias != nullptr && G.bias_off >= 0) {
+          if (has_bias) {
             if (cv0) b0 = __ldg(p.bias + G.bias_off + n0 + col);
             if (cv1) b1 = __ldg(p.bias + G.bias_off + n0 + col + 1);
           }
-          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-          __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(p.branch_out);
-#pragma unroll 4
-          for (int rr = 0; rr < 16; ++rr) {
-            const int rl = rr * 2 + rsel;
-            const long m = row0 + rl;
-            if (m < p.M && cv0) {
-              float v0 = stg[rl * 33 + cp] + b0;
-              float v1 = stg[rl * 33 + cp + 1] + b1;
-              const long o = m * p.ldo + G.c_col + n0 + col;
-              if (mode == EPI_GELU_BF16) {
-                if (pre != nullptr) {
-                  if (cv1) *reinterpret_cast<__nv_bfloat162*>(pre + o) = __floats2bfloat162_rn(v0, v1);
-                  else pre[o] = __float2bfloat16(v0);
-                }
+          const uint32_t rd = stg + (rsel * 33 + cp) * 4;
+          const long o0 = static_cast<long>(row0 + rsel) * p.ldo + G.c_col + n0 + col;
+          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
+          __nv_bfloat16* pre = (MODE == EPI_GELU_BF16 && p.branch_out != nullptr)
+                                   ? reinterpret_cast<__nv_bfloat16*>(p.branch_out) + o0 : nullptr;
+          const long step = 2 * p.ldo;
+          if (full) {
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              float v0 = lds_f32(rd + rr * 264) + b0;
+              float v1 = lds_f32(rd + rr * 264 + 4) + b1;
+              if (MODE == EPI_GELU_BF16) {
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(v0, v1);
+                if (pre != nullptr) *reinterpret_cast<__nv_bfloat162*>(pre + rr * step) = hb;
                 // the reference rounds the pre-activation to bf16 before nn.GELU under autocast
-                v0 = gelu_erf(__bfloat162float(__float2bfloat16(v0)));
-                v1 = gelu_erf(__bfloat162float(__float2bfloat16(v1)));
+                const float2 hf = __bfloat1622float2(hb);
+                v0 = gelu_fast(hf.x);
+                v1 = gelu_fast(hf.y);
               }
-              if (cv1) *reinterpret_cast<__nv_bfloat162*>(outp + o) = __floats2bfloat162_rn(v0, v1);
-              else outp[o] = __float2bfloat16(v0);
+              *reinterpret_cast<__nv_bfloat162*>(outp + rr * step) = __floats2bfloat162_rn(v0, v1);
+            }
+          } else if (cv0) {
+            for (int rr = 0; rr < 16; ++rr) {
+              if (rr * 2 + rsel < rmax) {
+                float v0 = lds_f32(rd + rr * 264) + b0;
+                float v1 = lds_f32(rd + rr * 264 + 4) + b1;
+                if (MODE == EPI_GELU_BF16) {
+                  const __nv_bfloat16 h0 = __float2bfloat16(v0), h1 = __float2bfloat16(v1);
+                  if (pre != nullptr) { pre[rr * step] = h0; if (cv1) pre[rr * step + 1] = h1; }
+                  v0 = gelu_fast(__bfloat162float(h0));
+                  v1 = gelu_fast(__bfloat162float(h1));
+                }
+                outp[rr * step] = __float2bfloat16(v0);
+                if (cv1) outp[rr * step + 1] = __float2bfloat16(v1);
+              }
             }
           }
         } else {
@@ -219,28 +260,76 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const bool cv = col < n_valid;
           float bv = 0.f, gv = 1.f;
           if (cv) {
-            if (p.bias != nullptr && G.bias_off >= 0) bv = __ldg(p.bias + G.bias_off + n0 + col);
-            if (mode == EPI_RESID && p.gamma != nullptr) gv = __ldg(p.gamma + G.c_col + n0 + col);
+            if (has_bias) bv = __ldg(p.bias + G.bias_off + n0 + col);
+            if (MODE == EPI_RESID && p.gamma != nullptr) gv = __ldg(p.gamma + G.c_col + n0 + col);
           }
-          const int rmax = min(32, p.M - row0);
-          for (int rr = 0; rr < rmax; ++rr) {
-            if (!cv) break;
-            const long m = row0 + rr;
-            float v = stg[rr * 33 + lane] + bv;
-            long mo = m;
-            if (p.remap_group > 0) mo = m + (m / p.remap_group) * p.remap_extra + p.remap_off;
-            if (mode == EPI_F32) {
-              reinterpret_cast<float*>(p.out)[mo * p.ldo + G.c_col + n0 + col] = v;
-            } else {  // EPI_RESID
-              if (p.branch_out != nullptr)
-                reinterpret_cast<__nv_bfloat16*>(p.branch_out)[mo * p.ldb + G.c_col + n0 + col] = __float2bfloat16(v);
-              // the reference's Linear emits bf16 under autocast; keep that rounding point
-              v = __bfloat162float(__float2bfloat16(v));
-              float s = gv;
-              if (p.row_scale != nullptr) s *= __ldg(p.row_scale + mo / p.rows_per_sample);
-              const long o = mo * p.ldr + G.c_col + n0 + col;
-              const float base = (p.resid_in != nullptr) ? p.resid_in[o] : 0.f;
-              p.resid_out[o] = base + s * v;
+          const long ocol = G.c_col + n0 + col;
+          const uint32_t rd = stg + lane * 4;
+          const bool fast = full && p.remap_group == 0 && (p.row_scale == nullptr || p.rows_per_sample >= 32);
+          if (fast) {
+            if (MODE == EPI_F32) {
+              float* outp = reinterpret_cast<float*>(p.out) + static_cast<long>(row0) * p.ldo + ocol;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) outp[rr * p.ldo] = lds_f32(rd + rr * 132) + bv;
+            } else {
+              // DropPath factor: a 32-row block spans at most two samples when rows_per_sample >= 32
+              float s_a = 1.f, s_b = 1.f;
+              int boundary = 32;
+              if (p.row_scale != nullptr) {
+                const int smp = row0 / p.rows_per_sample;
+                boundary = (smp + 1) * p.rows_per_sample - row0;
+                s_a = __ldg(p.row_scale + smp);
+                s_b = boundary < 32 ? __ldg(p.row_scale + smp + 1) : s_a;
+              }
+              const float* rin = p.resid_in != nullptr ? p.resid_in + static_cast<long>(row0) * p.ldr + ocol : nullptr;
+              float* rout = p.resid_out + static_cast<long>(row0) * p.ldr + ocol;
+              __nv_bfloat16* br = p.branch_out != nullptr
+                                      ? reinterpret_cast<__nv_bfloat16*>(p.branch_out) + static_cast<long>(row0) * p.ldb + ocol
+                                      : nullptr;
+#pragma unroll
+              for (int r8 = 0; r8 < 32; r8 += 8) {
+                float base[8];
+                // all loads of a batch before its stores (resid_in may alias resid_out)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int rr = r8 + i;
+                  float v = lds_f32(rd + rr * 132) + bv;
+                  const __nv_bfloat16 vb = __float2bfloat16(v);
+                  if (br != nullptr) br[rr * p.ldb] = vb;
+                  // the reference's Linear emits bf16 under autocast; keep that rounding point
+                  rout[rr * p.ldr] = base[i] + (rr < boundary ? s_a : s_b) * gv * __bfloat162float(vb);
+                }
+              }
+            }
+          } else if (cv) {
+#pragma unroll 1
+            for (int r8 = 0; r8 < rmax; r8 += 8) {
+              long mo[8];
+              float base[8], sc[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const long m = row0 + r8 + i;
+                mo[i] = (p.remap_group > 0) ? m + (m / p.remap_group) * p.remap_extra + p.remap_off : m;
+                const bool rv = r8 + i < rmax;
+                base[i] = (MODE == EPI_RESID && rv && p.resid_in != nullptr) ? p.resid_in[mo[i] * p.ldr + ocol] : 0.f;
+                sc[i] = (MODE == EPI_RESID && rv && p.row_scale != nullptr) ? __ldg(p.row_scale + mo[i] / p.rows_per_sample) : 1.f;
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (r8 + i < rmax) {
+                  float v = lds_f32(rd + (r8 + i) * 132) + bv;
+                  if (MODE == EPI_F32) {
+                    reinterpret_cast<float*>(p.out)[mo[i] * p.ldo + ocol] = v;
+                  } else {
+                    if (p.branch_out != nullptr)
+                      reinterpret_cast<__nv_bfloat16*>(p.branch_out)[mo[i] * p.ldb + ocol] = __float2bfloat16(v);
+                    v = __bfloat162float(__float2bfloat16(v));
+                    p.resid_out[mo[i] * p.ldr + ocol] = base[i] + sc[i] * gv * v;
+                  }
+                }
+              }
             }
           }
         }
@@ -263,7 +352,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------------------
 //  wgrad kernel (MN-major operands, contraction over tokens, split-K with fp32 red.add)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const __grid_constant__ WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -500,7 +589,7 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   }
   p.tiles_per_m = tiles;
   const int b_stage_bytes = d->block_n * kBlockK * 2;
-  int stages = (kMaxDynSmem - 1024 - (4 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
+  int stages = (kMaxDynSmem - 1024 - (8 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return OCTIC_ERR_ARG;
   p.num_stages = stages;
@@ -535,16 +624,25 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   }
   const SmemLayout L = smem_layout(stages, b_stage_bytes);
   const int smem_bytes = L.total + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    if (e != cudaSuccess) return OCTIC_ERR_CUDA;
-    attr_set = true;
-  }
   const int total_tiles = p.num_m_blocks * p.tiles_per_m;
   int grid = num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  gemm_tn_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tn_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tn_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tn_kernel<EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
+      return OCTIC_ERR_CUDA;
+    attr_set = true;
+  }
+  switch (p.mode) {
+    case EPI_BF16: gemm_tn_kernel<EPI_BF16><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
+    case EPI_RESID: gemm_tn_kernel<EPI_RESID><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
+    case EPI_F32: gemm_tn_kernel<EPI_F32><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
+    case EPI_GELU_BF16: gemm_tn_kernel<EPI_GELU_BF16><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
+    default: return OCTIC_ERR_ARG;
+  }
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
@@ -588,7 +686,7 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
   while (splits > 1 && (splits - 1) * ((kb_total + splits - 1) / splits) >= kb_total) --splits;
   p.splits = splits;
   const int b_stage_bytes = d->block_n * kBlockK * 2;
-  int stages = (kMaxDynSmem - 1024 - (4 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
+  int stages = (kMaxDynSmem - 1024 - (8 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
 
@@ -608,7 +706,7 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
   const int total_items = tiles * splits;
   int grid = num_sms();
   if (grid > total_items) grid = total_items;
-  gemm_wgrad_kernel<<<grid, kGemmThreads, smem_bytes, stream>>>(tmDY, tmX, p);
+  gemm_wgrad_kernel<<<grid, kWgradThreads, smem_bytes, stream>>>(tmDY, tmX, p);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 

@@ -467,27 +467,40 @@ __global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __rest
       else { g[j][0] = g[j][1] = g[j][2] = g[j][3] = 1.f; }
     }
   }
-  for (long r = r0; r < r1; ++r) {
-    const float s = row_scale != nullptr ? __ldg(row_scale + r / rows_per_sample) : 1.0f;
+  constexpr int RU = 4;   // rows in flight per thread: loads of RU rows are issued before any store
+  for (long rb = r0; rb < r1; rb += RU) {
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int ch = threadIdx.x + 256 * j;
       if (ch < nchunks) {
-        float d[4], o[4];
-        Vec<float, 4>::load(dres + r * lddres + ch * 4, d);
-        if (branch != nullptr) {
-          float b[4];
-          Vec<__nv_bfloat16, 4>::load(branch + r * ldbr + ch * 4, b);
+        float d[RU][4], b[RU][4], s[RU];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ag[j][i] += d[i] * s * b[i];
+        for (int u = 0; u < RU; ++u) {
+          const long r = rb + u;
+          s[u] = 0.f;
+          d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
+          b[u][0] = b[u][1] = b[u][2] = b[u][3] = 0.f;
+          if (r < r1) {
+            s[u] = row_scale != nullptr ? __ldg(row_scale + r / rows_per_sample) : 1.0f;
+            Vec<float, 4>::load(dres + r * lddres + ch * 4, d[u]);
+            if (branch != nullptr) Vec<__nv_bfloat16, 4>::load(branch + r * ldbr + ch * 4, b[u]);
+          }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          o[i] = g[j][i] * s * d[i];
-          // what the bias gradient sees is the bf16-rounded dy that also feeds dgrad/wgrad
-          as[j][i] += __bfloat162float(__float2bfloat16(o[i]));
+        for (int u = 0; u < RU; ++u) {
+          const long r = rb + u;
+          if (r < r1) {
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              ag[j][i] += d[u][i] * s[u] * b[u][i];
+              o[i] = g[j][i] * s[u] * d[u][i];
+              // what the bias gradient sees is the bf16-rounded dy that also feeds dgrad/wgrad
+              as[j][i] += __bfloat162float(__float2bfloat16(o[i]));
+            }
+            Vec<__nv_bfloat16, 4>::store(dy + r * lddy + ch * 4, o);
+          }
         }
-        Vec<__nv_bfloat16, 4>::store(dy + r * lddy + ch * 4, o);
       }
     }
   }
@@ -814,7 +827,7 @@ int octic_layerscale_bwd(const float* dres, long lddres, const void* branch, lon
   if (T == 0) return OCTIC_OK;
   if (rows_per_sample <= 0) rows_per_sample = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int rows_per_block = 64;
+  const int rows_per_block = 32;
   const int grid = static_cast<int>((T + rows_per_block - 1) / rows_per_block);
   const int nchunks = D / 4;
   const __nv_bfloat16* br = static_cast<const __nv_bfloat16*>(branch);
