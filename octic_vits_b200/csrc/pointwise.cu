@@ -10,10 +10,21 @@ constexpr float kSqrt2Over4 = 0.35355339059327376f;
 constexpr float kInvSqrt2 = 0.70710678118654752f;
 constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * kInvSqrt2)); }
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. below fp32 GELU's own rounding for |x| < 4):
+// one MUFU.RCP + one MUFU.EX2 + 6 FMA instead of erff's ~30 instructions (the D8 GELU needs 8 erf per channel)
+__device__ __forceinline__ float erf_as(float x) {
+  const float z = fabsf(x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));   // MUFU.RCP
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  return copysignf(1.0f - poly * t * __expf(-z * z), x);
+}
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erf_as(x * kInvSqrt2)); }
 // d/dx gelu(x) = Phi(x) + x * phi(x)      (reference octic_vits/d8_gelu.py:16-26)
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * kInvSqrt2));
+  const float cdf = 0.5f * (1.0f + erf_as(x * kInvSqrt2));
   const float pdf = kInvSqrt2Pi * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
@@ -323,96 +334,108 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 
 // Backward.  With yhat = (x - mu_g) * r, dyh = alpha * dout, Q = sum(dyh * yhat), m_g = mean_g(dyh):
 //   dx = r * (dyh - m_g - coef_g * yhat * Q),  coef_g = w_g / (8 n_g)  (D8)  or 1/D (plain)   [SURVEY A.7]
-// Parameter gradients: each lane owns fixed columns for every token it sees, so dalpha/dbeta accumulate in
-// registers and are flushed once per CTA (smem reduce over the 8 warps, then red.add).
-template <typename TDY, bool D8, int NCH>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restrict__ dy, long lddy,
-                                                            const float* __restrict__ x, long ldx,
-                                                            const float* __restrict__ stats,
-                                                            const float* __restrict__ alpha,
-                                                            const float* __restrict__ dx_in, float* __restrict__ dx_out,
-                                                            long lddx, float* __restrict__ dalpha,
-                                                            float* __restrict__ dbeta, long T_rows, int D) {
+// One CTA owns a token range; thread i owns float4 column chunk i for every token (so dalpha / dbeta accumulate in
+// 8 registers and flush with one red.add per column per CTA).  Tokens are processed G at a time: each thread forms
+// its partial Q and partial segment sum, a warp-shuffle + smem reduction makes the 7 per-token scalars available to
+// all threads, then dx is written.  ~60 registers, so many CTAs are resident and the loads of G tokens are in
+// flight together.
+constexpr int kLnG = 4;   // tokens per reduction round
+template <typename TDY, bool D8>
+__global__ void __launch_bounds__(512) layernorm_bwd_kernel(const TDY* __restrict__ dy, long lddy,
+                                                             const float* __restrict__ x, long ldx,
+                                                             const float* __restrict__ stats,
+                                                             const float* __restrict__ alpha,
+                                                             const float* __restrict__ dx_in, float* __restrict__ dx_out,
+                                                             long lddx, float* __restrict__ dalpha,
+                                                             float* __restrict__ dbeta, long T_rows, int D,
+                                                             int tokens_per_block) {
   constexpr int NSEG = D8 ? 6 : 1;
-  extern __shared__ float red[];   // [D] dalpha + [D] dbeta
-  const int lane = threadIdx.x & 31;
+  constexpr int NRED = NSEG + 1;                     // Q + per-segment sums
+  __shared__ float part[16][kLnG * NRED];            // per-warp partials
+  __shared__ float tot[kLnG * NRED];
   const int C = D / 8;
   const int nchunks = D / 4;
-  const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
-  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  const int ch = threadIdx.x;
+  const bool active = ch < nchunks;
+  const int col = ch * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int seg = active ? seg_of<D8>(col, C) : -1;
+  const float nseg = D8 ? (seg < 4 ? C : 2 * C) : D;
+  const float coef = D8 ? (seg < 4 ? 1.0f / (8.0f * C) : 0.5f / (16.0f * C)) : 1.0f / D;
+  float a4[4] = {0.f, 0.f, 0.f, 0.f};
+  if (active) Vec<float, 4>::load(alpha + col, a4);
+  float acc_a[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
 
-  float acc_a[NCH][4], acc_b[NCH][4];
+  (void)tokens_per_block;
+  const long t1 = T_rows;
+  for (long tb = static_cast<long>(blockIdx.x) * kLnG; tb < t1; tb += static_cast<long>(gridDim.x) * kLnG) {
+    float yh[kLnG][4], dyh[kLnG][4], rstd[kLnG], q[kLnG], s4[kLnG];
 #pragma unroll
-  for (int j = 0; j < NCH; ++j)
+    for (int u = 0; u < kLnG; ++u) {
+      const long t = tb + u;
+      rstd[u] = 0.f; q[u] = 0.f; s4[u] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { acc_a[j][i] = 0.f; acc_b[j][i] = 0.f; }
-  for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) red[i] = 0.f;
-  __syncthreads();
-
-  for (long t = warp_global; t < T_rows; t += nwarps) {
-    float yh[NCH][4], dyh[NCH][4];
-    int seg[NCH];
-    float mean[NSEG], msum[NSEG];
-    float rstd;
-    if (D8) {
+      for (int i = 0; i < 4; ++i) { yh[u][i] = 0.f; dyh[u][i] = 0.f; }
+      {
+        // unconditional loads (indices clamped) so that the loads of all kLnG tokens are issued back to back
+        const long tc = min(t, t1 - 1);
+        const int colc = active ? col : 0;
+        const int segc = active ? seg : 0;
+        const float valid = (active && t < t1) ? 1.0f : 0.0f;
+        float xv[4], d[4];
+        Vec<float, 4>::load(x + tc * ldx + colc, xv);
+        Vec<TDY, 4>::load(dy + tc * lddy + colc, d);
+        const float mu = D8 ? __ldg(stats + tc * 8 + segc) : __ldg(stats + tc * 2);
+        rstd[u] = D8 ? __ldg(stats + tc * 8 + 6) : __ldg(stats + tc * 2 + 1);
 #pragma unroll
-      for (int s = 0; s < NSEG; ++s) mean[s] = stats[t * 8 + s];
-      rstd = stats[t * 8 + 6];
-    } else {
-      mean[0] = stats[t * 2];
-      rstd = stats[t * 2 + 1];
-    }
-#pragma unroll
-    for (int s = 0; s < NSEG; ++s) msum[s] = 0.f;
-    float Q = 0.f;
-#pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      const int ch = lane + 32 * j;
-      seg[j] = -1;
-      if (ch < nchunks) {
-        const int col = ch * 4;
-        seg[j] = seg_of<D8>(col, C);
-        float mu = 0.f;
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) mu = (seg[j] == s) ? mean[s] : mu;
-        float xv[4], a[4], d[4];
-        Vec<float, 4>::load(x + t * ldx + col, xv);
-        Vec<float, 4>::load(alpha + col, a);
-        Vec<TDY, 4>::load(dy + t * lddy + col, d);
-        float s4 = 0.f;
+        for (int i = 0; i < 4; ++i) d[i] *= valid;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          yh[j][i] = (xv[i] - mu) * rstd;
-          dyh[j][i] = a[i] * d[i];
-          acc_a[j][i] += d[i] * yh[j][i];
-          acc_b[j][i] += d[i];
-          Q += dyh[j][i] * yh[j][i];
-          s4 += dyh[j][i];
+          yh[u][i] = (xv[i] - mu) * rstd[u];
+          dyh[u][i] = a4[i] * d[i];
+          acc_a[i] += d[i] * yh[u][i];
+          acc_b[i] += d[i];
+          q[u] += dyh[u][i] * yh[u][i];
+          s4[u] += dyh[u][i];
         }
-#pragma unroll
-        for (int s = 0; s < NSEG; ++s) msum[s] += (seg[j] == s) ? s4 : 0.f;
       }
     }
-    Q = warp_sum(Q);
+    // block reduction of kLnG * NRED scalars; a warp only shuffles for the segments it actually touches
 #pragma unroll
-    for (int s = 0; s < NSEG; ++s) {
-      const float n = D8 ? (s < 4 ? C : 2 * C) : D;
-      msum[s] = warp_sum(msum[s]) / n;
+    for (int sg = 0; sg < NSEG; ++sg) {
+      const bool mine = (seg == sg);
+      if (__any_sync(0xffffffffu, mine)) {
+#pragma unroll
+        for (int u = 0; u < kLnG; ++u) {
+          const float v = warp_sum(mine ? s4[u] : 0.f);
+          if (lane == 0) part[warp][u * NRED + 1 + sg] = v;
+        }
+      } else if (lane == 0) {
+#pragma unroll
+        for (int u = 0; u < kLnG; ++u) part[warp][u * NRED + 1 + sg] = 0.f;
+      }
     }
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      if (seg[j] >= 0) {
-        const int col = (lane + 32 * j) * 4;
-        float m = 0.f, coef = 0.f;
+    for (int u = 0; u < kLnG; ++u) {
+      const float v = warp_sum(q[u]);
+      if (lane == 0) part[warp][u * NRED] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < kLnG * NRED) {
+      float v = 0.f;
+      for (int w = 0; w < nwarps; ++w) v += part[w][threadIdx.x];
+      tot[threadIdx.x] = v;
+    }
+    __syncthreads();
 #pragma unroll
-        for (int s = 0; s < NSEG; ++s) {
-          const float cs = D8 ? (s < 4 ? 1.0f / (8.0f * C) : 0.5f / (16.0f * C)) : 1.0f / D;
-          m = (seg[j] == s) ? msum[s] : m;
-          coef = (seg[j] == s) ? cs : coef;
-        }
+    for (int u = 0; u < kLnG; ++u) {
+      const long t = tb + u;
+      if (active && t < t1) {
+        const float Q = tot[u * NRED];
+        const float m = tot[u * NRED + 1 + (D8 ? seg : 0)] / nseg;
         float o[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) o[i] = rstd * (dyh[j][i] - m - coef * yh[j][i] * Q);
+        for (int i = 0; i < 4; ++i) o[i] = rstd[u] * (dyh[u][i] - m - coef * yh[u][i] * Q);
         if (dx_in != nullptr) {
           float b[4];
           Vec<float, 4>::load(dx_in + t * lddx + col, b);
@@ -423,29 +446,19 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
       }
     }
   }
-  // flush parameter gradients
+  if (active) {
 #pragma unroll
-  for (int j = 0; j < NCH; ++j) {
-    const int ch = lane + 32 * j;
-    if (ch < nchunks) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        atomicAdd(&red[ch * 4 + i], acc_a[j][i]);
-        atomicAdd(&red[D + ch * 4 + i], acc_b[j][i]);
-      }
+    for (int i = 0; i < 4; ++i) {
+      if (dalpha != nullptr) atomicAdd(dalpha + col + i, acc_a[i]);
+      if (dbeta != nullptr && (!D8 || col < C)) atomicAdd(dbeta + col + i, acc_b[i]);
     }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D; i += blockDim.x) {
-    if (dalpha != nullptr) atomicAdd(dalpha + i, red[i]);
-    if (dbeta != nullptr && (!D8 || i < C)) atomicAdd(dbeta + i, red[D + i]);
   }
 }
 
 // --------------------------------------------- layer-scale backward ---------------------------------------------
 // Threads own float4 column groups, CTAs own row ranges: dy = gamma * s * dres (bf16), dgamma += dres * s * branch,
 // colsum += dy.
-template <int NV>   // float4 groups per thread (D/4 <= 256 * NV)
+template <int NV, bool HAS_BRANCH>   // NV float4 groups per thread (D/4 <= 256 * NV)
 __global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __restrict__ dres, long lddres,
                                                              const __nv_bfloat16* __restrict__ branch, long ldbr,
                                                              const float* __restrict__ gamma,
@@ -454,65 +467,48 @@ __global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __rest
                                                              float* __restrict__ dgamma, float* __restrict__ colsum,
                                                              long T_rows, int D, int rows_per_block) {
   const int nchunks = D / 4;
-  const long r0 = static_cast<long>(blockIdx.x) * rows_per_block;
-  const long r1 = min(T_rows, r0 + rows_per_block);
-  float g[NV][4], ag[NV][4], as[NV][4];
+  constexpr int RU = 4;   // rows in flight per thread
+  // persistent CTAs: row groups are dealt round-robin, so the grid can be sized to exactly fill the machine and
+  // each CTA flushes its column sums once
+  const long r1 = T_rows;
+  const long rstride = static_cast<long>(gridDim.x) * RU;
+  (void)rows_per_block;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int ch = threadIdx.x + 256 * j;
+    if (ch >= nchunks) continue;
+    const int col = ch * 4;
+    float g[4] = {1.f, 1.f, 1.f, 1.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+    if (gamma != nullptr) Vec<float, 4>::load(gamma + col, g);
+    for (long rb = static_cast<long>(blockIdx.x) * RU; rb < r1; rb += rstride) {
+      float d[RU][4], b[RU][4], sc[RU];
+      // loads are unconditional (row index clamped) so the compiler can issue all of them before the first use
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { ag[j][i] = 0.f; as[j][i] = 0.f; g[j][i] = 0.f; }
-    if (ch < nchunks) {
-      if (gamma != nullptr) Vec<float, 4>::load(gamma + ch * 4, g[j]);
-      else { g[j][0] = g[j][1] = g[j][2] = g[j][3] = 1.f; }
-    }
-  }
-  constexpr int RU = 4;   // rows in flight per thread: loads of RU rows are issued before any store
-  for (long rb = r0; rb < r1; rb += RU) {
+      for (int u = 0; u < RU; ++u) {
+        const long r = min(rb + u, r1 - 1);
+        Vec<float, 4>::load(dres + r * lddres + col, d[u]);
+        if (HAS_BRANCH) Vec<__nv_bfloat16, 4>::load(branch + r * ldbr + col, b[u]);
+        sc[u] = row_scale != nullptr ? __ldg(row_scale + r / rows_per_sample) : 1.0f;
+      }
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int ch = threadIdx.x + 256 * j;
-      if (ch < nchunks) {
-        float d[RU][4], b[RU][4], s[RU];
+      for (int u = 0; u < RU; ++u) {
+        if (rb + u < r1) {
+          float o[4];
 #pragma unroll
-        for (int u = 0; u < RU; ++u) {
-          const long r = rb + u;
-          s[u] = 0.f;
-          d[u][0] = d[u][1] = d[u][2] = d[u][3] = 0.f;
-          b[u][0] = b[u][1] = b[u][2] = b[u][3] = 0.f;
-          if (r < r1) {
-            s[u] = row_scale != nullptr ? __ldg(row_scale + r / rows_per_sample) : 1.0f;
-            Vec<float, 4>::load(dres + r * lddres + ch * 4, d[u]);
-            if (branch != nullptr) Vec<__nv_bfloat16, 4>::load(branch + r * ldbr + ch * 4, b[u]);
+          for (int i = 0; i < 4; ++i) {
+            if (HAS_BRANCH) ag[i] += d[u][i] * sc[u] * b[u][i];
+            o[i] = g[i] * sc[u] * d[u][i];
+            // what the bias gradient sees is the bf16-rounded dy that also feeds dgrad/wgrad
+            as[i] += __bfloat162float(__float2bfloat16(o[i]));
           }
-        }
-#pragma unroll
-        for (int u = 0; u < RU; ++u) {
-          const long r = rb + u;
-          if (r < r1) {
-            float o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              ag[j][i] += d[u][i] * s[u] * b[u][i];
-              o[i] = g[j][i] * s[u] * d[u][i];
-              // what the bias gradient sees is the bf16-rounded dy that also feeds dgrad/wgrad
-              as[j][i] += __bfloat162float(__float2bfloat16(o[i]));
-            }
-            Vec<__nv_bfloat16, 4>::store(dy + r * lddy + ch * 4, o);
-          }
+          Vec<__nv_bfloat16, 4>::store(dy + (rb + u) * lddy + col, o);
         }
       }
     }
-  }
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int ch = threadIdx.x + 256 * j;
-    if (ch < nchunks) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (dgamma != nullptr) atomicAdd(dgamma + ch * 4 + i, ag[j][i]);
-        if (colsum != nullptr) atomicAdd(colsum + ch * 4 + i, as[j][i]);
-      }
+    for (int i = 0; i < 4; ++i) {
+      if (HAS_BRANCH && dgamma != nullptr) atomicAdd(dgamma + col + i, ag[i]);
+      if (colsum != nullptr) atomicAdd(colsum + col + i, as[i]);
     }
   }
 }
@@ -782,16 +778,20 @@ static int ln_bwd_common(bool d8, const void* dy, long lddy, int dy_dtype, const
     return OCTIC_ERR_ALIGN;
   if (T == 0) return OCTIC_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int grid = grid_for(T * 32, 256, 148 * 4);
-  const int smem = 2 * D * static_cast<int>(sizeof(float));
+  const int nthreads = ((D / 4) + 31) / 32 * 32;
+  if (nthreads > 512) return OCTIC_ERR_ARG;   // D <= 2048
+  const int tokens_per_block = kLnG;
+  const long groups = (T + kLnG - 1) / kLnG;
+  const int per_sm = nthreads <= 128 ? 8 : (nthreads <= 256 ? 4 : 2);
+  const int grid = static_cast<int>(groups < 148L * per_sm ? groups : 148L * per_sm);
   if (dy_dtype == OCTIC_BF16) {
     const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dy);
-    if (d8) OCTIC_LN_DISPATCH(layernorm_bwd_kernel, __nv_bfloat16, true, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
-    else OCTIC_LN_DISPATCH(layernorm_bwd_kernel, __nv_bfloat16, false, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
+    if (d8) layernorm_bwd_kernel<__nv_bfloat16, true><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
+    else layernorm_bwd_kernel<__nv_bfloat16, false><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
   } else if (dy_dtype == OCTIC_F32) {
     const float* d = static_cast<const float*>(dy);
-    if (d8) OCTIC_LN_DISPATCH(layernorm_bwd_kernel, float, true, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
-    else OCTIC_LN_DISPATCH(layernorm_bwd_kernel, float, false, d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D);
+    if (d8) layernorm_bwd_kernel<float, true><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
+    else layernorm_bwd_kernel<float, false><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
   } else {
     return OCTIC_ERR_ARG;
   }
@@ -827,19 +827,27 @@ int octic_layerscale_bwd(const float* dres, long lddres, const void* branch, lon
   if (T == 0) return OCTIC_OK;
   if (rows_per_sample <= 0) rows_per_sample = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int rows_per_block = 32;
-  const int grid = static_cast<int>((T + rows_per_block - 1) / rows_per_block);
+  const int rows_per_block = 4;
+  long want = (T + rows_per_block - 1) / rows_per_block;
+  const int grid = static_cast<int>(want < 148 * 3 ? want : 148 * 3);   // 3 CTAs of 256 threads per SM
   const int nchunks = D / 4;
   const __nv_bfloat16* br = static_cast<const __nv_bfloat16*>(branch);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dy);
-  if (nchunks <= 256)
-    layerscale_bwd_kernel<1><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale, rows_per_sample, d, lddy, dgamma, colsum, T, D, rows_per_block);
-  else if (nchunks <= 512)
-    layerscale_bwd_kernel<2><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale, rows_per_sample, d, lddy, dgamma, colsum, T, D, rows_per_block);
-  else if (nchunks <= 1024)
-    layerscale_bwd_kernel<4><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale, rows_per_sample, d, lddy, dgamma, colsum, T, D, rows_per_block);
-  else
-    return OCTIC_ERR_ARG;
+#define OCTIC_LS_LAUNCH(NVV)                                                                                        \
+  do {                                                                                                            \
+    if (br != nullptr)                                                                                            \
+      layerscale_bwd_kernel<NVV, true><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale,             \
+                                                            rows_per_sample, d, lddy, dgamma, colsum, T, D,        \
+                                                            rows_per_block);                                       \
+    else                                                                                                          \
+      layerscale_bwd_kernel<NVV, false><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale,            \
+                                                             rows_per_sample, d, lddy, dgamma, colsum, T, D,       \
+                                                             rows_per_block);                                      \
+  } while (0)
+  if (nchunks <= 256) OCTIC_LS_LAUNCH(1);
+  else if (nchunks <= 512) OCTIC_LS_LAUNCH(2);
+  else if (nchunks <= 1024) OCTIC_LS_LAUNCH(4);
+  else return OCTIC_ERR_ARG;
   return last_err();
 }
 

@@ -209,24 +209,34 @@ class LinearResidualFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------------------------
 class LayerNormFn(torch.autograd.Function):
     """LayerNormD8 + AffineD8 (d8=True, reference d8_layers.py:161-186, 132-158; alpha is the packed [D] vector with
-    alpha_E repeated for both E rows) or nn.LayerNorm (d8=False).  fp32 in, bf16 or fp32 out."""
+    alpha_E repeated for both E rows) or nn.LayerNorm (d8=False).  fp32 in, bf16 or fp32 out.
+
+    With passthrough=True the input is returned as a second output: a pre-LN residual block then takes its skip
+    connection from that output, so autograd hands both cotangents of x to this backward and the kernel emits
+    dx = d_skip + LN^T(dy) in one pass (no separate gradient-accumulation kernel)."""
 
     @staticmethod
-    def forward(ctx, x, alpha, beta, eps: float, d8: bool, out_bf16: bool):
+    def forward(ctx, x, alpha, beta, eps: float, d8: bool, out_bf16: bool, passthrough: bool = False):
         if x.stride(-1) != 1:
             x = x.contiguous()
         y, stats = ops.layernorm_fwd(x, alpha, beta, eps, d8, torch.bfloat16 if out_bf16 else torch.float32,
                                      want_stats=any(ctx.needs_input_grad))
         ctx.save_for_backward(x, stats, alpha)
-        ctx.d8, ctx.has_beta = d8, beta is not None
+        ctx.d8, ctx.has_beta, ctx.passthrough = d8, beta is not None, passthrough
+        if passthrough:
+            return y, x.view_as(x)
         return y
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         x, stats, alpha = ctx.saved_tensors
+        if dy is None:     # only the skip connection was used downstream
+            return dskip, None, None, None, None, None, None
         dy = _c(dy)
-        dx, dalpha, dbeta = ops.layernorm_bwd(dy, x, stats, alpha, ctx.d8)
-        return dx, dalpha, (dbeta if ctx.has_beta else None), None, None, None
+        if dskip is not None:
+            dskip = _c(dskip)
+        dx, dalpha, dbeta = ops.layernorm_bwd(dy, x, stats, alpha, ctx.d8, dx_in=dskip)
+        return dx, dalpha, (dbeta if ctx.has_beta else None), None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------

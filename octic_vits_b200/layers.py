@@ -175,8 +175,11 @@ class LayerNormD8(nn.Module):
         OF.require_cuda(x)
         return OF.unpack_five(self.forward_packed(_as_f32(x), out_bf16=False))
 
-    def forward_packed(self, x: Tensor, out_bf16: bool = True) -> Tensor:
+    def forward_packed(self, x: Tensor, out_bf16: bool = True, passthrough: bool = False):
         alpha, beta = self._affine(x)
+        if passthrough:
+            y, skip = OF.LayerNormFn.apply(_rows(x), alpha, beta, self.eps, True, out_bf16, True)
+            return y.view(x.shape), skip.view(x.shape)
         return OF.LayerNormFn.apply(_rows(x), alpha, beta, self.eps, True, out_bf16).view(x.shape)
 
 
@@ -322,9 +325,11 @@ class _OcticBlockBase(nn.Module):
         ls2 = None if isinstance(self._ls(2), nn.Identity) else self._ls(2)
         s1 = self._dp(1).sample(B, x.device) if isinstance(self._dp(1), DropPathD8) else None
         s2 = self._dp(2).sample(B, x.device) if isinstance(self._dp(2), DropPathD8) else None
-        a = self.attn.core_packed(self.norm1.forward_packed(x))
+        xn, x = self.norm1.forward_packed(x, passthrough=True)
+        a = self.attn.core_packed(xn)
         x = _branch_residual(self.attn.proj, a, ls1, x, s1)
-        h = self.mlp.fc1.forward_packed(self.norm2.forward_packed(x))
+        xn, x = self.norm2.forward_packed(x, passthrough=True)
+        h = self.mlp.fc1.forward_packed(xn)
         h = self.mlp.act.forward_packed(h)
         return _branch_residual(self.mlp.fc2, h, ls2, x, s2)
 
@@ -669,11 +674,11 @@ class _DenseBlockBase(nn.Module):
         B, N, D = x.shape
         s1 = self._dp(1).sample(B, x.device) if isinstance(self._dp(1), DropPathD8) else None
         s2 = self._dp(2).sample(B, x.device) if isinstance(self._dp(2), DropPathD8) else None
-        xn = OF.LayerNormFn.apply(_rows(x), self.norm1.weight, self.norm1.bias, self.norm1.eps, False, True)
+        xn, xs = OF.LayerNormFn.apply(_rows(x), self.norm1.weight, self.norm1.bias, self.norm1.eps, False, True, True)
         a = self.attn.core_packed(xn.view(B, N, D))
-        x2 = OF.LinearResidualFn.apply(_rows(a), self.attn.proj.weight, self.attn.proj.bias, self._gamma(1), _rows(x),
+        x2 = OF.LinearResidualFn.apply(_rows(a), self.attn.proj.weight, self.attn.proj.bias, self._gamma(1), xs,
                                        s1, N, (0, 0, 0))
-        xn = OF.LayerNormFn.apply(x2, self.norm2.weight, self.norm2.bias, self.norm2.eps, False, True)
+        xn, x2 = OF.LayerNormFn.apply(x2, self.norm2.weight, self.norm2.bias, self.norm2.eps, False, True, True)
         h = self.mlp.hidden_packed(xn)
         out = OF.LinearResidualFn.apply(h, self.mlp.fc2.weight, self.mlp.fc2.bias, self._gamma(2), x2, s2, N, (0, 0, 0))
         return out.view(B, N, D)

@@ -157,8 +157,9 @@ def linear_d8_wgrad(dy: torch.Tensor, x: torch.Tensor, din: int, dout: int):
     _req(dy, torch.bfloat16, "dy")
     _req(x, torch.bfloat16, "x")
     ci, co = din // 8, dout // 8
-    dws = [torch.zeros(co, ci, dtype=torch.float32, device=x.device) for _ in range(4)]
-    dwE = torch.zeros(2 * co, 2 * ci, dtype=torch.float32, device=x.device)
+    flat = torch.zeros(8 * co * ci, dtype=torch.float32, device=x.device)      # one fill for all five gradients
+    dws = [flat[i * co * ci:(i + 1) * co * ci].view(co, ci) for i in range(4)]
+    dwE = flat[4 * co * ci:].view(2 * co, 2 * ci)
     call("octic_linear_d8_wgrad", dy.data_ptr(), x.data_ptr(), x.shape[0], din, dout, dws[0].data_ptr(),
          dws[1].data_ptr(), dws[2].data_ptr(), dws[3].data_ptr(), dwE.data_ptr(), _stream(),
          flops=2.0 * x.shape[0] * din * dout * 3 / 16)
@@ -250,8 +251,9 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, alpha:
     """returns (dx [= dx_in + LN^T dy], dalpha [D], dbeta [C or D])"""
     T, D = x.shape
     dx = torch.empty(T, D, dtype=torch.float32, device=x.device)
-    dalpha = torch.zeros(D, dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros(D // 8 if d8 else D, dtype=torch.float32, device=x.device)
+    nb = D // 8 if d8 else D
+    flat = torch.zeros(D + nb, dtype=torch.float32, device=x.device)
+    dalpha, dbeta = flat[:D], flat[D:]
     call("octic_layernorm_d8_bwd" if d8 else "octic_layernorm_bwd", dy.data_ptr(), dy.stride(0), _dt(dy),
          x.data_ptr(), x.stride(0), stats.data_ptr(), alpha.data_ptr(), _ptr(dx_in), dx.data_ptr(), dx.stride(0),
          dalpha.data_ptr(), dbeta.data_ptr(), T, D, _stream())
@@ -264,8 +266,9 @@ def layerscale_bwd(dres: torch.Tensor, branch: Optional[torch.Tensor], gamma: Op
     _req(dres, torch.float32, "dres")
     T, D = dres.shape
     dy = torch.empty(T, D, dtype=torch.bfloat16, device=dres.device)
-    dgamma = torch.zeros(D, dtype=torch.float32, device=dres.device) if branch is not None else None
-    colsum = torch.zeros(D, dtype=torch.float32, device=dres.device) if want_colsum else None
+    flat = torch.zeros(2 * D, dtype=torch.float32, device=dres.device)
+    dgamma = flat[:D] if branch is not None else None
+    colsum = flat[D:] if want_colsum else None
     call("octic_layerscale_bwd", dres.data_ptr(), dres.stride(0), _ptr(branch),
          branch.stride(0) if branch is not None else 0, _ptr(gamma), _ptr(row_scale), rows_per_sample,
          dy.data_ptr(), dy.stride(0), _ptr(dgamma), _ptr(colsum), T, D, _stream())

@@ -1,0 +1,195 @@
+"""CPU-only tests: the C-ABI library loads and exports every prototype of include/octic_b200.h, the host-side mirror
+keeps the reference's constructor / state-dict / error contract, the product path refuses to run without a GPU, and
+the batch-shard + flat-gradient all-reduce logic works at world_size 2 (gloo)."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from octic_vits_b200 import _lib
+    if not _lib.LIB_PATH.exists():
+        subprocess.run(["bash", str(ROOT / "build.sh")], check=True, cwd=ROOT)
+    return _lib.load()
+
+
+def header_prototypes():
+    hdr = (ROOT / "include" / "octic_b200.h").read_text()
+    return re.findall(r"^(?:int|const char\*)\s+(octic_\w+)\s*\(", hdr, flags=re.M)
+
+
+def test_library_exports_every_header_symbol(lib):
+    from octic_vits_b200 import _lib
+    names = header_prototypes()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/octic_b200.h but not exported"
+    bound = set(_lib.SIGNATURES) | {"octic_strerror", "octic_version", "octic_device_ok"}
+    assert set(names) == bound, set(names) ^ bound
+    assert lib.octic_version() >= 100
+    assert lib.octic_strerror(-2).decode().startswith("pointer or leading dimension")
+
+
+def test_no_cpu_fallback(lib):
+    from octic_vits_b200 import layers as L
+    from octic_vits_b200._lib import OcticError
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.octic_device_ok() == 0
+    xs = tuple(torch.randn(1, 3, 8) for _ in range(4)) + (torch.randn(1, 3, 2, 16),)
+    for mod in (L.LinearD8(64, 64), L.LayerNormD8(64), L.TritonGeluD8(), L.AttentionD8(64, 2), L.MlpD8(64),
+                L.Layer_scale_init_BlockD8(64, 2), L.BlockD8(64, 2), L.PowerSpectrumInvariant(64)):
+        with pytest.raises(OcticError):
+            mod(xs)
+
+
+def test_constructor_contract_matches_reference():
+    from octic_vits_b200 import layers as L
+    for bad in (lambda: L.LinearD8(60, 64), lambda: L.LinearD8(64, 60), lambda: L.AffineD8(12),
+                lambda: L.LayerScaleD8(12), lambda: L.LiftD8(3, 60, 8, 8, True), lambda: L.PatchEmbedD8(embed_dim=60)):
+        with pytest.raises(ValueError):
+            bad()
+    with pytest.raises(NotImplementedError):
+        L.AttentionD8(64, 2, rope=object())
+    with pytest.raises(AssertionError):
+        L.AttentionD8(60, 7)
+    with pytest.raises(ValueError):
+        L.LiftIrrepD8Conv2d(3, 8, 8, 8, bias=True, irrep="A2")
+    with pytest.raises(ValueError):
+        L.LiftIrrepD8Conv2d(3, 8, 2, 2, bias=False, irrep="B1")
+    with pytest.raises(NotImplementedError):
+        L.LiftIrrepD8Conv2d(3, 8, 7, 7, bias=False)
+    blk = L.Layer_scale_init_BlockD8(64, 2, init_values=0.25)
+    assert float(blk.gamma_1.alpha_E[0]) == 0.25 and blk.gamma_1.beta is None
+    assert isinstance(L.BlockD8(64, 2).ls1, torch.nn.Identity)
+    assert isinstance(L.BlockD8(64, 2, init_values=1e-5).ls1, L.LayerScaleD8)
+
+
+@pytest.mark.parametrize("name", ["model_hybrid", "model_invariant", "model_timm_default"])
+def test_reference_state_dict_loads_key_for_key(golden, name):
+    from octic_vits_b200 import layers as L
+    from octic_vits_b200.model import OcticVisionTransformer
+    fx = golden(name)
+    cfg = fx["cfg"]
+    kw = dict(img_size=cfg["img_size"], patch_size=cfg["patch"], embed_dim=cfg["embed_dim"], depth=cfg["depth"],
+              num_heads=cfg["num_heads"], num_classes=cfg["num_classes"])
+    if name == "model_timm_default":
+        model = OcticVisionTransformer(init_scale=0.7, **kw)
+    else:
+        model = OcticVisionTransformer(qkv_bias=True, invariant=cfg["invariant"],
+                                       standard_block_layers=L.Layer_scale_init_Block,
+                                       octic_block_layers=L.Layer_scale_init_BlockD8, **kw)
+    assert list(model.state_dict().keys()) == list(fx["sd"].keys())
+    for k, v in model.state_dict().items():
+        assert v.shape == fx["sd"][k].shape, k
+    model.load_state_dict(fx["sd"], strict=True)
+    frozen = [n for n, p in model.named_parameters() if not p.requires_grad]
+    assert frozen == [f"cls_token.{i}" for i in range(1, 5)]
+    assert "cls_token.0" in model.no_weight_decay() and "pos_embed.5" in model.no_weight_decay()
+
+
+def test_factories_and_param_counts():
+    from octic_vits_b200.deit_models import create_model, list_models
+    assert {"hybrid_deit_large_patch16", "hybrid_deit_huge_patch14", "d8_inv_early_deit_huge_patch14",
+            "d8_inv_early_deit_large_patch16"} <= set(list_models())
+    with pytest.raises(RuntimeError):
+        create_model("no_such_model")
+    m = create_model("hybrid_deit_small_patch16", num_classes=1000, drop_rate=0.0, drop_path_rate=0.1, drop_block_rate=None)
+    assert sum(p.numel() for p in m.parameters()) == 12_439_432 or abs(sum(p.numel() for p in m.parameters()) / 1e6 - 12.44) < 0.01
+
+
+def test_pos_embed_unfold_matches_oracle(golden):
+    from octic_vits_b200.model import unfold_pos_embed_packed
+    from oracle import octic_oracle as O
+    fx = golden("model_hybrid")
+    ps = [fx["sd"][f"pos_embed.{i}"] for i in range(6)]
+    want = O.pack_rows(tuple(t.flatten(0, 1) for t in O.unfold_pos_embed(ps)))
+    assert torch.equal(unfold_pos_embed_packed(ps), want)
+
+
+def test_lift_weight_expansion_matches_oracle(golden):
+    from octic_vits_b200 import layers as L
+    from oracle import octic_oracle as O
+    fx = golden("model_hybrid")
+    lift = L.LiftD8(3, 64, 16, 16, True)
+    lift.load_state_dict({k[len("patch_embed.lift8."):]: v for k, v in fx["sd"].items() if k.startswith("patch_embed.lift8.")})
+    for name in ("A1", "A2", "B1", "B2"):
+        got = getattr(lift, f"conv_{name}").expand_weight()
+        assert torch.allclose(got, O.expand_lift_weight(fx["sd"][f"patch_embed.lift8.conv_{name}.weight"], name), atol=1e-7)
+    assert torch.allclose(lift.conv_E_left.expand_weight(),
+                          O.expand_lift_weight(fx["sd"]["patch_embed.lift8.conv_E_left.weight"], "E"), atol=1e-7)
+    w, b = lift.packed_weight_and_bias()
+    assert w.shape == (64, 3 * 16 * 16) and b.shape == (64,) and torch.count_nonzero(b[8:]) == 0
+
+
+def test_pack_unpack_views_are_zero_copy():
+    from octic_vits_b200 import functional as OF
+    x = torch.randn(2, 5, 64)
+    xs = OF.unpack_five(x)
+    assert [tuple(t.shape) for t in xs] == [(2, 5, 8)] * 4 + [(2, 5, 2, 16)]
+    assert OF.pack_five(xs) is x                       # views of one packed tensor: no copy
+    ys = tuple(t.clone() for t in xs)
+    assert torch.equal(OF.pack_five(ys), x)            # foreign tensors: packed by concatenation
+    with pytest.raises(AssertionError):
+        OF.pack_five(xs[:4])
+
+
+def test_shard_batch_covers_everything():
+    from octic_vits_b200.parallel import shard_batch
+    for gb, world in [(256, 8), (10, 4), (7, 8), (2048, 2)]:
+        spans = [shard_batch(gb, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from octic_vits_b200.parallel import FlatGrads, shard_batch
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+torch.manual_seed(0)                                   # same replica on both ranks
+model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GELU(), torch.nn.Linear(5, 3))
+model[0].bias.requires_grad_(False)                    # a frozen parameter, like cls_token.1-4
+fg = FlatGrads(model.parameters())
+data = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+a, b = shard_batch(8, rank, 2)
+fg.zero()
+model(data[a:b]).square().sum().backward()
+fg.all_reduce()
+# reference: the whole batch on one replica; mean over ranks of per-shard sums = full sum / 2
+ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.GELU(), torch.nn.Linear(5, 3))
+ref.load_state_dict(model.state_dict())
+ref(data).square().sum().backward()
+for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+    if p.requires_grad:
+        assert torch.allclose(p.grad, q.grad / 2, atol=1e-5), n
+    else:
+        assert p.grad is None
+assert model[0].weight.grad.data_ptr() == fg.flat.data_ptr()
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_flat_grad_allreduce_world2_gloo(tmp_path):
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT), str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
