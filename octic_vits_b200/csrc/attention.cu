@@ -129,10 +129,119 @@ __device__ __forceinline__ void load_a_rows(uint32_t (&a)[HD / 16][4], const __n
   }
 }
 
+// ------------------------------------------------------ tiles ------------------------------------------------------
+// ldmatrix addressing: every lane keeps a constant byte offset inside a [rows][STR] bf16 tile, the rest of the address
+// is (row block, column block) arithmetic that is compile-time inside the unrolled loops.
+__device__ __forceinline__ void ldsm_x4_addr(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t_addr(uint32_t (&r)[4], uint32_t a) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+template <int STR>
+__device__ __forceinline__ uint32_t lane_off_nk(int lane) {   // operand stored [n][k], B fragment of A * M^T
+  const int mat = lane >> 3, row = lane & 7;
+  return static_cast<uint32_t>((((mat >> 1) * 8 + row) * STR + (mat & 1) * 8) * 2);
+}
+template <int STR>
+__device__ __forceinline__ uint32_t lane_off_kn(int lane) {   // operand stored [k][n], B fragment of A * M
+  const int mat = lane >> 3, row = lane & 7;
+  return static_cast<uint32_t>((((mat & 1) * 8 + row) * STR + (mat >> 1) * 8) * 2);
+}
+
+// acc[NT][4] += A(16 x HD, registers) * M[n0 .. n0 + 8 NT, :]^T       (M stored [n][HD] in smem; NT even)
+template <int HD, int NT>
+__device__ __forceinline__ void mma_a_mt(float (&acc)[NT][4], const uint32_t (&a)[HD / 16][4], uint32_t m_nk, int n0) {
+  constexpr int STR = HD + 8;
+  const uint32_t base = m_nk + static_cast<uint32_t>(n0) * (STR * 2);
+#pragma unroll
+  for (int ks = 0; ks < HD / 16; ++ks) {
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t bf[4];
+      ldsm_x4_addr(bf, base + (np * 16 * STR + ks * 16) * 2);
+      mma16816(acc[2 * np], a[ks], bf[0], bf[1]);
+      mma16816(acc[2 * np + 1], a[ks], bf[2], bf[3]);
+    }
+  }
+}
+// acc[HD/8][4] += P(16 x 8 NT, bf16 fragments built from p[NT][4]) * M[k0 .. k0 + 8 NT, :]   (M stored [k][HD])
+template <int HD, int NT>
+__device__ __forceinline__ void mma_p_m(float (&acc)[HD / 8][4], const float (&p)[NT][4], uint32_t m_kn, int k0) {
+  constexpr int STR = HD + 8;
+  const uint32_t base = m_kn + static_cast<uint32_t>(k0) * (STR * 2);
+#pragma unroll
+  for (int kk = 0; kk < NT / 2; ++kk) {
+    uint32_t pa[4];
+    pa[0] = pack_bf16(p[2 * kk][0], p[2 * kk][1]);
+    pa[1] = pack_bf16(p[2 * kk][2], p[2 * kk][3]);
+    pa[2] = pack_bf16(p[2 * kk + 1][0], p[2 * kk + 1][1]);
+    pa[3] = pack_bf16(p[2 * kk + 1][2], p[2 * kk + 1][3]);
+#pragma unroll
+    for (int dp = 0; dp < HD / 16; ++dp) {
+      uint32_t bf[4];
+      ldsm_x4_t_addr(bf, base + (kk * 16 * STR + dp * 16) * 2);
+      mma16816(acc[2 * dp], pa, bf[0], bf[1]);
+      mma16816(acc[2 * dp + 1], pa, bf[2], bf[3]);
+    }
+  }
+}
+template <int NT>
+__device__ __forceinline__ void zero_acc(float (&a)[NT][4]) {
+#pragma unroll
+  for (int i = 0; i < NT; ++i) a[i][0] = a[i][1] = a[i][2] = a[i][3] = 0.f;
+}
+
 // ------------------------------------------------------ forward ------------------------------------------------------
+struct SoftmaxState { float m_lo, m_hi, l_lo, l_hi; };
+
+// one KV chunk of 8*NT keys starting at kv0; MASK: the chunk may contain keys >= N
+template <int HD, int NT, bool MASK>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&qa)[HD / 16][4], float (&oacc)[HD / 8][4], SoftmaxState& st,
+                                          uint32_t k_nk, uint32_t v_kn, int kv0, int N, float scale_log2, int lane) {
+  float s[NT][4];
+  zero_acc<NT>(s);
+  mma_a_mt<HD, NT>(s, qa, k_nk, kv0);
+  float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    if (MASK) {
+      const int col = kv0 + nt * 8 + (lane & 3) * 2;
+      if (col >= N) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (col + 1 >= N) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+    }
+    mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+    mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+  }
+  mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);
+  const float mn_lo = fmaxf(st.m_lo, mx_lo), mn_hi = fmaxf(st.m_hi, mx_hi);
+  const float corr_lo = exp2f((st.m_lo - mn_lo) * scale_log2), corr_hi = exp2f((st.m_hi - mn_hi) * scale_log2);
+  st.m_lo = mn_lo; st.m_hi = mn_hi;
+  const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
+  float rs_lo = 0.f, rs_hi = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    s[nt][0] = exp2f(fmaf(s[nt][0], scale_log2, -off_lo));
+    s[nt][1] = exp2f(fmaf(s[nt][1], scale_log2, -off_lo));
+    s[nt][2] = exp2f(fmaf(s[nt][2], scale_log2, -off_hi));
+    s[nt][3] = exp2f(fmaf(s[nt][3], scale_log2, -off_hi));
+    rs_lo += s[nt][0] + s[nt][1];
+    rs_hi += s[nt][2] + s[nt][3];
+  }
+  st.l_lo = st.l_lo * corr_lo + rs_lo;
+  st.l_hi = st.l_hi * corr_hi + rs_hi;
+#pragma unroll
+  for (int i = 0; i < HD / 8; ++i) {
+    oacc[i][0] *= corr_lo; oacc[i][1] *= corr_lo; oacc[i][2] *= corr_hi; oacc[i][3] *= corr_hi;
+  }
+  mma_p_m<HD, NT>(oacc, s, v_kn, kv0);
+}
+
 template <int HD>
-__global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
-                                                       float* __restrict__ lse, int N, int H, HeadMap m, float scale_log2) {
+__global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
+                                                          float* __restrict__ lse, int N, int H, HeadMap m, float scale_log2) {
   constexpr int STR = HD + 8, KS = HD / 16, DT = HD / 8;
   extern __shared__ __align__(16) uint8_t smem[];
   const int Npad = (N + 15) & ~15;
@@ -159,82 +268,27 @@ __global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_fwd_kernel(const
   cp_async_wait_all();
   __syncthreads();
 
+  const uint32_t k_nk = static_cast<uint32_t>(__cvta_generic_to_shared(Ks)) + lane_off_nk<STR>(lane);
+  const uint32_t v_kn = static_cast<uint32_t>(__cvta_generic_to_shared(Vs)) + lane_off_kn<STR>(lane);
   const int ntiles = Npad / 16;
+  const int full_end = (N / 64) * 64;      // keys [0, full_end) need no masking
   for (int qt = warp; qt < ntiles; qt += nwarps) {
     const int q0 = qt * 16;
     uint32_t qa[KS][4];
     load_a_rows<HD>(qa, rows, ld3, 0, q0, N, cb, sm, lane);
     float oacc[DT][4];
-#pragma unroll
-    for (int i = 0; i < DT; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
-    float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
-
-    for (int kv0 = 0; kv0 < Npad; kv0 += 64) {
-      const int nts = min(8, (Npad - kv0) >> 3);   // even
-      float s[8][4];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          if (2 * np < nts) {
-            uint32_t bf[4];
-            load_b_nk<STR>(bf, Ks, kv0 + np * 16, ks * 16, lane);
-            mma16816(s[2 * np], qa[ks], bf[0], bf[1]);
-            mma16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
-          }
-        }
-      }
-      float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int col = kv0 + nt * 8 + (lane & 3) * 2;
-        if (nt >= nts || col >= N) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-        if (nt >= nts || col + 1 >= N) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-        mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
-        mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
-      }
-      mx_lo = quad_max(mx_lo); mx_hi = quad_max(mx_hi);
-      const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);
-      const float corr_lo = exp2f((m_lo - mn_lo) * scale_log2), corr_hi = exp2f((m_hi - mn_hi) * scale_log2);
-      m_lo = mn_lo; m_hi = mn_hi;
-      const float off_lo = mn_lo * scale_log2, off_hi = mn_hi * scale_log2;
-      float rs_lo = 0.f, rs_hi = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        s[nt][0] = exp2f(s[nt][0] * scale_log2 - off_lo);
-        s[nt][1] = exp2f(s[nt][1] * scale_log2 - off_lo);
-        s[nt][2] = exp2f(s[nt][2] * scale_log2 - off_hi);
-        s[nt][3] = exp2f(s[nt][3] * scale_log2 - off_hi);
-        rs_lo += s[nt][0] + s[nt][1];
-        rs_hi += s[nt][2] + s[nt][3];
-      }
-      l_lo = l_lo * corr_lo + rs_lo;
-      l_hi = l_hi * corr_hi + rs_hi;
-#pragma unroll
-      for (int i = 0; i < DT; ++i) {
-        oacc[i][0] *= corr_lo; oacc[i][1] *= corr_lo; oacc[i][2] *= corr_hi; oacc[i][3] *= corr_hi;
-      }
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        if (2 * kk < nts) {
-          uint32_t pa[4];
-          pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
-          pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
-          pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-          pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
-#pragma unroll
-          for (int dp = 0; dp < DT / 2; ++dp) {
-            uint32_t bf[4];
-            load_b_kn<STR>(bf, Vs, kv0 + kk * 16, dp * 16, lane);
-            mma16816(oacc[2 * dp], pa, bf[0], bf[1]);
-            mma16816(oacc[2 * dp + 1], pa, bf[2], bf[3]);
-          }
-        }
-      }
+    zero_acc<DT>(oacc);
+    SoftmaxState st{-INFINITY, -INFINITY, 0.f, 0.f};
+    int kv0 = 0;
+    for (; kv0 < full_end; kv0 += 64) fwd_chunk<HD, 8, false>(qa, oacc, st, k_nk, v_kn, kv0, N, scale_log2, lane);
+    switch ((Npad - kv0) >> 3) {
+      case 2: fwd_chunk<HD, 2, true>(qa, oacc, st, k_nk, v_kn, kv0, N, scale_log2, lane); break;
+      case 4: fwd_chunk<HD, 4, true>(qa, oacc, st, k_nk, v_kn, kv0, N, scale_log2, lane); break;
+      case 6: fwd_chunk<HD, 6, true>(qa, oacc, st, k_nk, v_kn, kv0, N, scale_log2, lane); break;
+      case 8: fwd_chunk<HD, 8, true>(qa, oacc, st, k_nk, v_kn, kv0, N, scale_log2, lane); break;
+      default: break;
     }
-    l_lo = quad_sum(l_lo); l_hi = quad_sum(l_hi);
+    const float l_lo = quad_sum(st.l_lo), l_hi = quad_sum(st.l_hi);
     const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
     const int r_lo = q0 + (lane >> 2), r_hi = r_lo + 8;
     __nv_bfloat16* orow_lo = o + (static_cast<long>(b) * N + r_lo) * m.D;
@@ -247,8 +301,8 @@ __global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_fwd_kernel(const
     }
     if (lse != nullptr && (lane & 3) == 0) {
       float* l = lse + (static_cast<long>(b) * H + h) * N;
-      if (r_lo < N) l[r_lo] = (m_lo * scale_log2 + log2f(l_lo)) * kLn2;
-      if (r_hi < N) l[r_hi] = (m_hi * scale_log2 + log2f(l_hi)) * kLn2;
+      if (r_lo < N) l[r_lo] = (st.m_lo * scale_log2 + log2f(l_lo)) * kLn2;
+      if (r_hi < N) l[r_hi] = (st.m_hi * scale_log2 + log2f(l_hi)) * kLn2;
     }
   }
 }
@@ -305,9 +359,34 @@ __device__ __forceinline__ void load_a_o_rows(uint32_t (&a)[HD / 16][4], const _
 
 // ------------------------------------------- backward pass A: dK, dV -------------------------------------------
 // Warps own 16 key rows.  S^T = K Q^T, P^T = exp(S^T*scale - lse[q]), dV += P^T dO, dP^T = V dO^T,
-// dS^T = P^T (dP^T - delta[q]), dK += scale * dS^T Q.
+// dS^T = P^T (dP^T - delta[q]), dK += scale * dS^T Q.   Padded queries have lse = +inf, hence P^T = 0.
+template <int HD, int NT>
+__device__ __forceinline__ void bwd_kv_chunk(const uint32_t (&ka)[HD / 16][4], const uint32_t (&va)[HD / 16][4],
+                                             float (&dk)[HD / 8][4], float (&dv)[HD / 8][4], uint32_t q_nk, uint32_t q_kn,
+                                             uint32_t do_nk, uint32_t do_kn, const float* lse_s, const float* del_s, int q0,
+                                             float scale_log2, int lane) {
+  float st[NT][4], dp[NT][4];
+  zero_acc<NT>(st);
+  zero_acc<NT>(dp);
+  mma_a_mt<HD, NT>(st, ka, q_nk, q0);
+  mma_a_mt<HD, NT>(dp, va, do_nk, q0);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int col = q0 + nt * 8 + (lane & 3) * 2;
+    const float2 l = *reinterpret_cast<const float2*>(lse_s + col);
+    const float2 d = *reinterpret_cast<const float2*>(del_s + col);
+    const float p0 = exp2f(fmaf(st[nt][0], scale_log2, -l.x)), p1 = exp2f(fmaf(st[nt][1], scale_log2, -l.y));
+    const float p2 = exp2f(fmaf(st[nt][2], scale_log2, -l.x)), p3 = exp2f(fmaf(st[nt][3], scale_log2, -l.y));
+    st[nt][0] = p0; st[nt][1] = p1; st[nt][2] = p2; st[nt][3] = p3;
+    dp[nt][0] = p0 * (dp[nt][0] - d.x); dp[nt][1] = p1 * (dp[nt][1] - d.y);
+    dp[nt][2] = p2 * (dp[nt][2] - d.x); dp[nt][3] = p3 * (dp[nt][3] - d.y);
+  }
+  mma_p_m<HD, NT>(dv, st, do_kn, q0);
+  mma_p_m<HD, NT>(dk, dp, q_kn, q0);
+}
+
 template <int HD>
-__global__ void __launch_bounds__(288) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(192, (HD <= 80) ? 2 : 1) attn_bwd_kv_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                           const __nv_bfloat16* __restrict__ d_o,
                                                           const float* __restrict__ lse, const float* __restrict__ delta,
                                                           __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
@@ -347,81 +426,25 @@ __global__ void __launch_bounds__(288) attn_bwd_kv_kernel(const __nv_bfloat16* _
   cp_async_wait_all();
   __syncthreads();
 
+  const uint32_t qs = static_cast<uint32_t>(__cvta_generic_to_shared(Qs));
+  const uint32_t dos = static_cast<uint32_t>(__cvta_generic_to_shared(dOs));
+  const uint32_t q_nk = qs + lane_off_nk<STR>(lane), q_kn = qs + lane_off_kn<STR>(lane);
+  const uint32_t do_nk = dos + lane_off_nk<STR>(lane), do_kn = dos + lane_off_kn<STR>(lane);
   const int ntiles = Npad / 16;
+  const int full_end = (Npad / 32) * 32;
   for (int kt = warp; kt < ntiles; kt += nwarps) {
     const int k0 = kt * 16;
     uint32_t ka[KS][4], va[KS][4];
     load_a_rows<HD>(ka, rows, ld3, 1, k0, N, cb, sm, lane);
     load_a_rows<HD>(va, rows, ld3, 2, k0, N, cb, sm, lane);
     float dk[DT][4], dv[DT][4];
-#pragma unroll
-    for (int i = 0; i < DT; ++i) {
-      dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
-      dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
-    }
-    for (int q0 = 0; q0 < Npad; q0 += 32) {
-      const int nts = min(4, (Npad - q0) >> 3);   // 2 or 4
-      float st[4][4], dp[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
-        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-      }
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-          if (2 * np < nts) {
-            uint32_t bf[4];
-            load_b_nk<STR>(bf, Qs, q0 + np * 16, ks * 16, lane);
-            mma16816(st[2 * np], ka[ks], bf[0], bf[1]);
-            mma16816(st[2 * np + 1], ka[ks], bf[2], bf[3]);
-            load_b_nk<STR>(bf, dOs, q0 + np * 16, ks * 16, lane);
-            mma16816(dp[2 * np], va[ks], bf[0], bf[1]);
-            mma16816(dp[2 * np + 1], va[ks], bf[2], bf[3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        if (nt < nts) {
-          const int col = q0 + nt * 8 + (lane & 3) * 2;
-          const float l0 = lse_s[col], l1 = lse_s[col + 1], d0 = del_s[col], d1 = del_s[col + 1];
-          const float p0 = exp2f(st[nt][0] * scale_log2 - l0), p1 = exp2f(st[nt][1] * scale_log2 - l1);
-          const float p2 = exp2f(st[nt][2] * scale_log2 - l0), p3 = exp2f(st[nt][3] * scale_log2 - l1);
-          st[nt][0] = p0; st[nt][1] = p1; st[nt][2] = p2; st[nt][3] = p3;
-          dp[nt][0] = p0 * (dp[nt][0] - d0); dp[nt][1] = p1 * (dp[nt][1] - d1);
-          dp[nt][2] = p2 * (dp[nt][2] - d0); dp[nt][3] = p3 * (dp[nt][3] - d1);
-        } else {
-          st[nt][0] = st[nt][1] = st[nt][2] = st[nt][3] = 0.f;
-          dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        if (2 * kk < nts) {
-          uint32_t pa[4], da[4];
-          pa[0] = pack_bf16(st[2 * kk][0], st[2 * kk][1]);
-          pa[1] = pack_bf16(st[2 * kk][2], st[2 * kk][3]);
-          pa[2] = pack_bf16(st[2 * kk + 1][0], st[2 * kk + 1][1]);
-          pa[3] = pack_bf16(st[2 * kk + 1][2], st[2 * kk + 1][3]);
-          da[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
-          da[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
-          da[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
-          da[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
-#pragma unroll
-          for (int dpi = 0; dpi < DT / 2; ++dpi) {
-            uint32_t bf[4];
-            load_b_kn<STR>(bf, dOs, q0 + kk * 16, dpi * 16, lane);
-            mma16816(dv[2 * dpi], pa, bf[0], bf[1]);
-            mma16816(dv[2 * dpi + 1], pa, bf[2], bf[3]);
-            load_b_kn<STR>(bf, Qs, q0 + kk * 16, dpi * 16, lane);
-            mma16816(dk[2 * dpi], da, bf[0], bf[1]);
-            mma16816(dk[2 * dpi + 1], da, bf[2], bf[3]);
-          }
-        }
-      }
-    }
+    zero_acc<DT>(dk);
+    zero_acc<DT>(dv);
+    int q0 = 0;
+    for (; q0 < full_end; q0 += 32)
+      bwd_kv_chunk<HD, 4>(ka, va, dk, dv, q_nk, q_kn, do_nk, do_kn, lse_s, del_s, q0, scale_log2, lane);
+    if (q0 < Npad) bwd_kv_chunk<HD, 2>(ka, va, dk, dv, q_nk, q_kn, do_nk, do_kn, lse_s, del_s, q0, scale_log2, lane);
+
     const int r_lo = k0 + (lane >> 2), r_hi = r_lo + 8;
 #pragma unroll
     for (int dt = 0; dt < DT; ++dt) {
@@ -441,8 +464,33 @@ __global__ void __launch_bounds__(288) attn_bwd_kv_kernel(const __nv_bfloat16* _
 
 // ------------------------------------------- backward pass B: dQ -------------------------------------------
 // Warps own 16 query rows.  S = Q K^T, P = exp(S*scale - lse), dP = dO V^T, dS = P (dP - delta), dQ = scale * dS K.
+template <int HD, int NT, bool MASK>
+__device__ __forceinline__ void bwd_q_chunk(const uint32_t (&qa)[HD / 16][4], const uint32_t (&doa)[HD / 16][4],
+                                            float (&dq)[HD / 8][4], uint32_t k_nk, uint32_t k_kn, uint32_t v_nk, int kv0,
+                                            int N, float lse_lo, float lse_hi, float del_lo, float del_hi,
+                                            float scale_log2, int lane) {
+  float s[NT][4], dp[NT][4];
+  zero_acc<NT>(s);
+  zero_acc<NT>(dp);
+  mma_a_mt<HD, NT>(s, qa, k_nk, kv0);
+  mma_a_mt<HD, NT>(dp, doa, v_nk, kv0);
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    float p0 = exp2f(fmaf(s[nt][0], scale_log2, -lse_lo)), p1 = exp2f(fmaf(s[nt][1], scale_log2, -lse_lo));
+    float p2 = exp2f(fmaf(s[nt][2], scale_log2, -lse_hi)), p3 = exp2f(fmaf(s[nt][3], scale_log2, -lse_hi));
+    if (MASK) {
+      const int col = kv0 + nt * 8 + (lane & 3) * 2;
+      if (col >= N) { p0 = 0.f; p2 = 0.f; }
+      if (col + 1 >= N) { p1 = 0.f; p3 = 0.f; }
+    }
+    dp[nt][0] = p0 * (dp[nt][0] - del_lo); dp[nt][1] = p1 * (dp[nt][1] - del_lo);
+    dp[nt][2] = p2 * (dp[nt][2] - del_hi); dp[nt][3] = p3 * (dp[nt][3] - del_hi);
+  }
+  mma_p_m<HD, NT>(dq, dp, k_kn, kv0);
+}
+
 template <int HD>
-__global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv,
+__global__ void __launch_bounds__(192, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                          const __nv_bfloat16* __restrict__ d_o,
                                                          const float* __restrict__ lse, const float* __restrict__ delta,
                                                          __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
@@ -475,7 +523,12 @@ __global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(con
   cp_async_wait_all();
   __syncthreads();
 
+  const uint32_t ks_ = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
+  const uint32_t vs_ = static_cast<uint32_t>(__cvta_generic_to_shared(Vs));
+  const uint32_t k_nk = ks_ + lane_off_nk<STR>(lane), k_kn = ks_ + lane_off_kn<STR>(lane);
+  const uint32_t v_nk = vs_ + lane_off_nk<STR>(lane);
   const int ntiles = Npad / 16;
+  const int full_end = (N / 32) * 32;
   for (int qt = warp; qt < ntiles; qt += nwarps) {
     const int q0 = qt * 16;
     uint32_t qa[KS][4], doa[KS][4];
@@ -488,61 +541,14 @@ __global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(con
     const float del_lo = r_lo < N ? delta[soff + r_lo] : 0.f;
     const float del_hi = r_hi < N ? delta[soff + r_hi] : 0.f;
     float dq[DT][4];
-#pragma unroll
-    for (int i = 0; i < DT; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-
-    for (int kv0 = 0; kv0 < Npad; kv0 += 32) {
-      const int nts = min(4, (Npad - kv0) >> 3);
-      float s[4][4], dp[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-        dp[i][0] = dp[i][1] = dp[i][2] = dp[i][3] = 0.f;
-      }
-#pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-          if (2 * np < nts) {
-            uint32_t bf[4];
-            load_b_nk<STR>(bf, Ks, kv0 + np * 16, ks * 16, lane);
-            mma16816(s[2 * np], qa[ks], bf[0], bf[1]);
-            mma16816(s[2 * np + 1], qa[ks], bf[2], bf[3]);
-            load_b_nk<STR>(bf, Vs, kv0 + np * 16, ks * 16, lane);
-            mma16816(dp[2 * np], doa[ks], bf[0], bf[1]);
-            mma16816(dp[2 * np + 1], doa[ks], bf[2], bf[3]);
-          }
-        }
-      }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int col = kv0 + nt * 8 + (lane & 3) * 2;
-        const bool v0 = nt < nts && col < N, v1 = nt < nts && col + 1 < N;
-        const float p0 = v0 ? exp2f(s[nt][0] * scale_log2 - lse_lo) : 0.f;
-        const float p1 = v1 ? exp2f(s[nt][1] * scale_log2 - lse_lo) : 0.f;
-        const float p2 = v0 ? exp2f(s[nt][2] * scale_log2 - lse_hi) : 0.f;
-        const float p3 = v1 ? exp2f(s[nt][3] * scale_log2 - lse_hi) : 0.f;
-        dp[nt][0] = p0 * (dp[nt][0] - del_lo); dp[nt][1] = p1 * (dp[nt][1] - del_lo);
-        dp[nt][2] = p2 * (dp[nt][2] - del_hi); dp[nt][3] = p3 * (dp[nt][3] - del_hi);
-      }
-#pragma unroll
-      for (int kk = 0; kk < 2; ++kk) {
-        if (2 * kk < nts) {
-          uint32_t da[4];
-          da[0] = pack_bf16(dp[2 * kk][0], dp[2 * kk][1]);
-          da[1] = pack_bf16(dp[2 * kk][2], dp[2 * kk][3]);
-          da[2] = pack_bf16(dp[2 * kk + 1][0], dp[2 * kk + 1][1]);
-          da[3] = pack_bf16(dp[2 * kk + 1][2], dp[2 * kk + 1][3]);
-#pragma unroll
-          for (int dpi = 0; dpi < DT / 2; ++dpi) {
-            uint32_t bf[4];
-            load_b_kn<STR>(bf, Ks, kv0 + kk * 16, dpi * 16, lane);
-            mma16816(dq[2 * dpi], da, bf[0], bf[1]);
-            mma16816(dq[2 * dpi + 1], da, bf[2], bf[3]);
-          }
-        }
-      }
-    }
+    zero_acc<DT>(dq);
+    int kv0 = 0;
+    for (; kv0 < full_end; kv0 += 32)
+      bwd_q_chunk<HD, 4, false>(qa, doa, dq, k_nk, k_kn, v_nk, kv0, N, lse_lo, lse_hi, del_lo, del_hi, scale_log2, lane);
+    if (Npad - kv0 >= 32)
+      bwd_q_chunk<HD, 4, true>(qa, doa, dq, k_nk, k_kn, v_nk, kv0, N, lse_lo, lse_hi, del_lo, del_hi, scale_log2, lane);
+    else if (Npad - kv0 == 16)
+      bwd_q_chunk<HD, 2, true>(qa, doa, dq, k_nk, k_kn, v_nk, kv0, N, lse_lo, lse_hi, del_lo, del_hi, scale_log2, lane);
 #pragma unroll
     for (int dt = 0; dt < DT; ++dt) {
       const int cq = cb[dt * 4 + (lane & 3)];
@@ -555,7 +561,7 @@ __global__ void __launch_bounds__(288, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(con
 // ------------------------------------------------------ host ------------------------------------------------------
 static int attn_warps(int N) {
   const int ntiles = (N + 15) / 16;
-  const int rounds = (ntiles + 8) / 9;   // at most 9 warps (288 threads) per CTA
+  const int rounds = (ntiles + 5) / 6;   // at most 6 warps (192 threads) per CTA: 2 CTAs/SM with <= 168 registers
   return (ntiles + rounds - 1) / rounds;
 }
 static int make_head_map(HeadMap* m, int H, int hd, int octic) {
