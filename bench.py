@@ -111,7 +111,7 @@ def cpu_reference_step_fn(batch: int):
             logits = O.octic_vit_forward(img, params, patch=MODEL["patch"], depth=MODEL["depth"], num_heads=MODEL["heads"])
         loss = torch.nn.functional.cross_entropy(logits.float(), tgt)
         loss.backward()
-        return float(loss)
+        return loss.item()
     return step
 
 
@@ -169,13 +169,10 @@ def run_ours(args):
     torch.manual_seed(1234 + rank)
     B = args.batch
     model = create_model(MODEL["name"], num_classes=MODEL["classes"], drop_path_rate=args.drop_path).to(dev).train()
-    params = [p for p in model.parameters() if p.requires_grad]
     # one flat fp32 gradient buffer: .grad tensors are views, the all-reduce is a single NCCL call over NVLink
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-    off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
+    from octic_vits_b200.parallel import FlatGrads
+    fg = FlatGrads(model.parameters())
+    flat = fg.flat
 
     img_dev = torch.randn(B, 3, MODEL["img"], MODEL["img"], device=dev)
     tgt_dev = torch.randint(0, MODEL["classes"], (B,), device=dev)
@@ -187,9 +184,7 @@ def run_ours(args):
         logits = model(img)
         loss = torch.nn.functional.cross_entropy(logits, tgt)
         loss.backward()
-        if world > 1:
-            dist.all_reduce(flat)
-            flat.div_(world)
+        fg.all_reduce()
         return loss
 
     def barrier():
