@@ -100,15 +100,22 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // Stage rows [0, Npad) of tensor s of (b, h) into smem (zero rows >= N) with 4-byte cp.async: the gather of the
-// head vector from the packed row happens here.  Caller must cp_async_wait_all() + __syncthreads().
+// head vector from the packed row happens here.  Thread -> fixed column pair, rows strided, so the column map is read
+// once and the loop body is a pointer bump + one cp.async.  Caller must cp_async_wait_all() + __syncthreads().
 template <int HD>
 __device__ __forceinline__ void stage_rows(__nv_bfloat16* dst, const __nv_bfloat16* src_rows, long ld, int s, int N,
                                            int Npad, const int* cb, const int* sm) {
-  constexpr int STR = HD + 8;
-  for (int idx = threadIdx.x; idx < Npad * (HD / 2); idx += blockDim.x) {
-    const int row = idx / (HD / 2), jp = idx - row * (HD / 2);
-    __nv_bfloat16* d = dst + row * STR + jp * 2;
-    if (row < N) cp_async4(d, src_rows + row * ld + cb[jp] + s * sm[jp]);
+  constexpr int STR = HD + 8, NP = HD / 2;
+  const int rows_per_iter = blockDim.x / NP;
+  const int jp = threadIdx.x % NP, r0 = threadIdx.x / NP;
+  if (r0 >= rows_per_iter) return;
+  const int col = cb[jp] + s * sm[jp];
+  const __nv_bfloat16* src = src_rows + static_cast<long>(r0) * ld + col;
+  __nv_bfloat16* d = dst + r0 * STR + jp * 2;
+  const long sstep = static_cast<long>(rows_per_iter) * ld;
+  const int dstep = rows_per_iter * STR;
+  for (int row = r0; row < Npad; row += rows_per_iter, src += sstep, d += dstep) {
+    if (row < N) cp_async4(d, src);
     else *reinterpret_cast<uint32_t*>(d) = 0u;
   }
 }
@@ -335,11 +342,16 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 template <int HD>
 __device__ __forceinline__ void stage_o_rows(__nv_bfloat16* dst, const __nv_bfloat16* src_rows, long ld, int N, int Npad,
                                              const int* ocb) {
-  constexpr int STR = HD + 8;
-  for (int idx = threadIdx.x; idx < Npad * (HD / 2); idx += blockDim.x) {
-    const int row = idx / (HD / 2), jp = idx - row * (HD / 2);
-    __nv_bfloat16* d = dst + row * STR + jp * 2;
-    if (row < N) cp_async4(d, src_rows + row * ld + ocb[jp]);
+  constexpr int STR = HD + 8, NP = HD / 2;
+  const int rows_per_iter = blockDim.x / NP;
+  const int jp = threadIdx.x % NP, r0 = threadIdx.x / NP;
+  if (r0 >= rows_per_iter) return;
+  const __nv_bfloat16* src = src_rows + static_cast<long>(r0) * ld + ocb[jp];
+  __nv_bfloat16* d = dst + r0 * STR + jp * 2;
+  const long sstep = static_cast<long>(rows_per_iter) * ld;
+  const int dstep = rows_per_iter * STR;
+  for (int row = r0; row < Npad; row += rows_per_iter, src += sstep, d += dstep) {
+    if (row < N) cp_async4(d, src);
     else *reinterpret_cast<uint32_t*>(d) = 0u;
   }
 }
@@ -562,7 +574,8 @@ __global__ void __launch_bounds__(192, (HD <= 80) ? 2 : 1) attn_bwd_q_kernel(con
 static int attn_warps(int N) {
   const int ntiles = (N + 15) / 16;
   const int rounds = (ntiles + 5) / 6;   // at most 6 warps (192 threads) per CTA: 2 CTAs/SM with <= 168 registers
-  return (ntiles + rounds - 1) / rounds;
+  const int w = (ntiles + rounds - 1) / rounds;
+  return w < 2 ? 2 : w;                  // the staging loops need blockDim >= hd/2 threads
 }
 static int make_head_map(HeadMap* m, int H, int hd, int octic) {
   if (H <= 0 || hd <= 0 || (hd % 16) != 0) return OCTIC_ERR_ARG;
