@@ -11,39 +11,10 @@
 // rows and runs an online-softmax loop over 64-key chunks with mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
 // Backward is two passes without atomics: pass A (warps own key rows) -> dK, dV; pass B (warps own query rows) -> dQ.
 // TODO(round 2): move QK^T / PV onto tcgen05 with S/P in TMEM.
-#include "octic_capi_internal.h"
+#include "attention_common.cuh"
+#include <stdlib.h>
 
 namespace octic {
-
-struct HeadMap {
-  int octic;   // 1: packed LinearD8 layout, 0: dense [3][H][hd]
-  int D;       // embed dim
-  int C;       // D / 8
-  int ch;      // hd / 8 = C / H
-  int hd;
-};
-
-// column of element j (even) of the head vector of (s, h) inside a qkv row, split as base + s * smul
-__device__ __forceinline__ void qkv_col(const HeadMap& m, int h, int j, int& base, int& smul) {
-  if (!m.octic) { base = h * m.hd + j; smul = m.D; return; }
-  if (j < 4 * m.ch) {
-    const int g = j / m.ch, jj = j - g * m.ch;
-    base = g * 3 * m.C + h * m.ch + jj; smul = m.C;
-  } else {
-    const int j2 = j - 4 * m.ch, r = j2 / (2 * m.ch), jj = j2 - r * 2 * m.ch;
-    base = 12 * m.C + r * 6 * m.C + h * 2 * m.ch + jj; smul = 2 * m.C;
-  }
-}
-// column of element j of head h inside an attention-output row (packed 5-tuple order, d8_layers.py:650-656)
-__device__ __forceinline__ int o_col(const HeadMap& m, int h, int j) {
-  if (!m.octic) return h * m.hd + j;
-  if (j < 4 * m.ch) {
-    const int g = j / m.ch, jj = j - g * m.ch;
-    return g * m.C + h * m.ch + jj;
-  }
-  const int j2 = j - 4 * m.ch, r = j2 / (2 * m.ch), jj = j2 - r * 2 * m.ch;
-  return 4 * m.C + r * 2 * m.C + h * 2 * m.ch + jj;
-}
 
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -88,8 +59,6 @@ __device__ __forceinline__ void load_b_kn(uint32_t (&b)[4], const __nv_bfloat16*
   ldsm_x4_t(b, M + (k0 + (mat & 1) * 8 + row) * STR + n0 + (mat >> 1) * 8);
 }
 
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
@@ -631,6 +600,17 @@ static int launch_bwd(const void* qkv, const void* o, const void* d_o, const flo
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
+// The tcgen05 kernels (attention_tc.cu) serve every shape inside their shared-memory / TMEM envelope; longer
+// sequences use the mma.sync kernels above.  OCTIC_ATTN_LEGACY=1 forces the latter (A/B timing, tests).
+static bool use_tc_path(int N, int hd, bool backward) {
+  static int legacy = -1;
+  if (legacy < 0) {
+    const char* e = getenv("OCTIC_ATTN_LEGACY");
+    legacy = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return legacy == 0 && attn_tc_supported(N, hd, backward);
+}
+
 }  // namespace octic
 
 using namespace octic;
@@ -644,6 +624,7 @@ int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int 
   int rc = make_head_map(&m, H, hd, octic_layout);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (use_tc_path(N, hd, false)) return launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, s);
   switch (hd) {
     case 32: return launch_fwd<32>(qkv, o, lse, B, N, H, m, s);
     case 64: return launch_fwd<64>(qkv, o, lse, B, N, H, m, s);
@@ -661,6 +642,15 @@ int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const f
   int rc = make_head_map(&m, H, hd, octic_layout);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (use_tc_path(N, hd, true)) {
+    const long total = static_cast<long>(B) * N * H;
+    int dgrid = static_cast<int>((total + 255) / 256);
+    if (dgrid > 148 * 16) dgrid = 148 * 16;
+    attn_delta_kernel<<<dgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
+                                            delta_ws, B, N, H, m);
+    if (cudaGetLastError() != cudaSuccess) return OCTIC_ERR_CUDA;
+    return launch_attn_bwd_tc(qkv, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+  }
   switch (hd) {
     case 32: return launch_bwd<32>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
     case 64: return launch_bwd<64>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);

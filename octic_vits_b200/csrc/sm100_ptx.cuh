@@ -146,6 +146,44 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+
+// D[tmem] (+)= A[tmem, bf16 pairs packed in 32-bit columns, lane = row] * B[smem desc].  A must be K-major.
+// (validated by tools/umma_probe.cu cases 10/11/15/18-21)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> TMEM: 32 lanes x 8 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// named barrier among `nthreads` threads (ids 1..15; 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// cp.async (LDGSTS): global -> shared without register staging
+__device__ __forceinline__ void cp_async_4(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 // ---------------------------------------- descriptors ----------------------------------------
 // Shared-memory matrix descriptor (tcgen05), field layout as in the PTX ISA "matrix descriptor":
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4
@@ -160,6 +198,32 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= static_cast<uint64_t>(kSwizzle128B) << 61;
   return d;
 }
+// SWIZZLE_32B flavour used by the attention kernels: a row-major [R][C] bf16 tile is kept as C/16 "atom columns" of
+// R x 32 B each; inside every 8-row group (256 B) the two 16-byte halves of a row are swapped when (row >> 2) & 1.
+// The same bytes serve as a K-major operand (contraction along the columns, K-step ks = atom column ks) and as an
+// MN-major operand (contraction along the rows).  Conventions validated on hardware by tools/umma_probe.cu.
+constexpr uint32_t kSwizzle32B = 6;
+__host__ __device__ __forceinline__ uint32_t sw32_off(int r, int c, int R) {
+  return static_cast<uint32_t>((c >> 4) * (R * 32) + r * 32 + ((((c >> 3) & 1) ^ ((r >> 2) & 1)) << 4) + (c & 7) * 2);
+}
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;          // SBO: 8 rows x 32 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(kSwizzle32B) << 61;
+  return d;
+}
+// K-major view: rows row0.. of the tile, K-step ks (columns 16 ks .. 16 ks + 15)
+__device__ __forceinline__ uint64_t desc_sw32_k(uint32_t base, int R, int row0, int ks) {
+  return make_desc_sw32(base + ks * (R * 32) + row0 * 32, 0);
+}
+// MN-major view: contraction rows krow0 .. krow0 + 15, MN extent starts at column 0 and spans atom columns R*32 B apart
+__device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t base, int R, int krow0) {
+  return make_desc_sw32(base + krow0 * 32, R * 32);
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M = 128.
 //   [4,6) D fmt: 1 = f32   [7,10) A fmt: 1 = bf16   [10,13) B fmt: 1 = bf16
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4

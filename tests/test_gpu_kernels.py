@@ -318,8 +318,11 @@ def _attn_reference(qkv_rows, B, N, H, hd, octic):
 
 
 @pytest.mark.parametrize("octic", [True, False])
-@pytest.mark.parametrize("B,N,H,hd", [(2, 257, 16, 80), (3, 197, 6, 64), (2, 17, 2, 64), (1, 261, 16, 64), (2, 64, 4, 32)])
+@pytest.mark.parametrize("B,N,H,hd", [(2, 257, 16, 80), (3, 197, 6, 64), (2, 17, 2, 64), (1, 261, 16, 64), (2, 64, 4, 32),
+                                      (2, 129, 2, 80), (2, 128, 2, 96), (1, 400, 2, 80), (1, 150, 2, 128), (3, 65, 2, 64)])
 def test_attention(B, N, H, hd, octic):
+    """tcgen05 path (attention_tc.cu) inside its envelope; N = 400 backward and hd = 128 / N = 150 ... exercise chunk
+    plans with 1..5 chunks, partial last tiles, and (N = 400 backward) the mma.sync fallback."""
     D = H * hd
     g = torch.Generator().manual_seed(N + hd)
     qkv = bf(torch.randn(B * N, 3 * D, generator=g) * 1.5).to(DEV)
@@ -329,6 +332,15 @@ def test_attention(B, N, H, hd, octic):
     (want * d_o.float()).sum().backward()
     o, lse = ops.attention_fwd(qkv, B, N, H, hd, octic)
     assert_close(o, want.detach(), rtol=2e-2, atol=2e-2)
+    # log-sum-exp of the scaled scores (natural log), [B, H, N]
+    q3 = qkv.float().reshape(B, N, 3 * D)
+    if octic:
+        qh, kh, _ = O.attention_heads_d8(O.unpack_rows(q3), H)
+    else:
+        t = q3.reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+        qh, kh = t[0], t[1]
+    want_lse = torch.logsumexp(qh @ kh.transpose(-1, -2) / hd ** 0.5, dim=-1)
+    assert_close(lse, want_lse, rtol=1e-3, atol=1e-3)
     dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, N, H, hd, octic)
     assert_close(dqkv, qin.grad, rtol=3e-2, atol=3e-2)
 
