@@ -84,6 +84,11 @@ typedef struct {
   int rows_per_sample;
   void* branch_out; long ldb; /* optional bf16 copy of acc + bias                                      */
   int remap_group; int remap_extra; int remap_off; /* EPI_RESID/EPI_F32 row remap: m' = m + (m/remap_group)*remap_extra + remap_off (0 = identity) */
+  /* EPI_BF16 head remap (0 heads = off).  Feature n of a group with n_g outputs is read as [S][H][c_g]
+   * (c_g = n_g / (S*H), even) and stored at column s*head_D + h*(head_D/H) + head_off[group] + j instead of
+   * c_col + n: the qkv LinearD8 (S = 3) and the proj dgrad (S = 1) emit head-major rows for the attention kernels
+   * (reference pack step octic_vits/d8_layers.py:632-641) straight from the GEMM epilogue. */
+  int head_H; int head_S; int head_D; int head_off[OCTIC_MAX_GROUPS];
 } octic_gemm_desc;
 
 int octic_gemm_bf16(const octic_gemm_desc* desc, void* stream);
@@ -118,12 +123,15 @@ int octic_linear_d8_pack_weights(const float* wA1, const float* wA2, const float
                                  void* wE_t, void* stream);
 
 /* y = LinearD8(x): x bf16 [T, Din] packed rows, bias fp32 [Dout/8] (A1 only) or NULL.  The epilogue fields of
- * `epi` (mode/out/ldo/gamma/resid/row_scale/branch_out) are honoured; a/b/groups/bias are filled in here. */
+ * `epi` (mode/out/ldo/gamma/resid/row_scale/branch_out, head_H/head_S) are honoured; a/b/groups/bias and the
+ * head_D/head_off fields are filled in here. */
 int octic_linear_d8_fwd(const void* x, int T, int Din, int Dout, const void* w1d, const void* wE_packed,
                         const float* bias, const octic_gemm_desc* epi, void* stream);
-/* dx = LinearD8^T(dy): dy bf16 [T, Dout] -> dx bf16 [T, Din] using the transposed packs. */
+/* dx = LinearD8^T(dy): dy bf16 [T, Dout] -> dx bf16 [T, Din] using the transposed packs.  head_H > 0: dx rows are
+ * written head-major ([H][hd], head vector [A1|A2|B1|B2|E0|E1]) instead of packed -- the d_o operand of
+ * octic_attention_bwd(OCTIC_ATTN_OCTIC_HEADMAJOR). */
 int octic_linear_d8_dgrad(const void* dy, int T, int Din, int Dout, const void* w1d_t, const void* wE_t,
-                          void* dx, void* stream);
+                          void* dx, int head_H, void* stream);
 /* dW_* += dy^T x per irrep (fp32 [Dout/8, Din/8] x4 and [Dout/4, Din/4]). */
 int octic_linear_d8_wgrad(const void* dy, const void* x, int T, int Din, int Dout, float* dwA1, float* dwA2,
                           float* dwB1, float* dwB2, float* dwE, void* stream);
@@ -177,17 +185,27 @@ int octic_colsum_bf16(const void* x, long ldx, long T, int n_cols, float* out, v
 
 /* ---------------------------------------------------------------------------------------------------------
  * Attention (AttentionD8, octic_vits/d8_layers.py:623-656; dense Attention, deit/vit.py:36-56).
- * qkv bf16 [B*N, 3D]: octic layout = packed LinearD8 output (per irrep [3][H][c_h]); dense = [3][H][hd].
- * The head vector [A1|A2|B1|B2|E0|E1] of d8_layers.py:632-641 is gathered on load and the output is scattered
- * straight back into the packed row of d8_layers.py:650-656, so the reference's cat/permute copies never exist.
- * softmax scale = hd^-1/2 (the SDPA default; AttentionD8.scale is dead code in the reference).
- * o bf16 [B*N, D]; lse fp32 [B, H, N] (natural log).
+ * qkv bf16 [B*N, 3D], o bf16 [B*N, D], lse fp32 [B, H, N] (natural log); softmax scale = hd^-1/2 (the SDPA default;
+ * AttentionD8.scale is dead code in the reference).  `layout` selects how head vectors sit in the rows:
+ *   OCTIC_ATTN_DENSE            qkv = [3][H][hd], o = [H][hd]                       (deit/vit.py:36-50)
+ *   OCTIC_ATTN_OCTIC_PACKED     qkv = packed LinearD8 output (per irrep [3][H][c_h]), o = packed octic row: the head
+ *                               vector [A1|A2|B1|B2|E0|E1] of d8_layers.py:632-641 is gathered on load and the output
+ *                               scattered back into the row of d8_layers.py:650-656 (mma.sync kernels)
+ *   OCTIC_ATTN_OCTIC_HEADMAJOR  qkv (and d_o in backward) = [3][H][hd] / [H][hd] with the head vector in the order
+ *                               [A1|A2|B1|B2|E0|E1] -- what octic_linear_d8_fwd / _dgrad write with head_remap set --
+ *                               while o and dqkv are packed octic rows.  tcgen05 kernels fed by TMA; the shape must
+ *                               satisfy octic_attention_headmajor_supported().
+ * In every case the reference's cat / permute / contiguous copies never exist.
  * --------------------------------------------------------------------------------------------------------- */
-int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int hd, int octic_layout,
+#define OCTIC_ATTN_DENSE 0
+#define OCTIC_ATTN_OCTIC_PACKED 1
+#define OCTIC_ATTN_OCTIC_HEADMAJOR 2
+int octic_attention_headmajor_supported(int N, int hd, int backward);
+int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int hd, int layout,
                         void* stream);
 /* delta_ws: caller-provided fp32 workspace [B, H, N] (receives rowsum(dO * O)). */
 int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_ws,
-                        void* dqkv, int B, int N, int H, int hd, int octic_layout, void* stream);
+                        void* dqkv, int B, int N, int H, int hd, int layout, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * PowerSpectrumInvariant (octic_vits/d8_invariantization.py:49-64): [T, 8C] fp32 -> [T, 6C] bf16

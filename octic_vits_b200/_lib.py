@@ -40,6 +40,7 @@ class GemmDesc(C.Structure):
         ("row_scale", C.c_void_p), ("rows_per_sample", C.c_int),
         ("branch_out", C.c_void_p), ("ldb", C.c_long),
         ("remap_group", C.c_int), ("remap_extra", C.c_int), ("remap_off", C.c_int),
+        ("head_H", C.c_int), ("head_S", C.c_int), ("head_D", C.c_int), ("head_off", C.c_int * OCTIC_MAX_GROUPS),
     ]
 
 
@@ -66,7 +67,7 @@ SIGNATURES = {
     "octic_gemm_wgrad_bf16": [C.POINTER(WgradDesc), _P],
     "octic_linear_d8_pack_weights": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P],
     "octic_linear_d8_fwd": [_P, _I, _I, _I, _P, _P, _P, C.POINTER(GemmDesc), _P],
-    "octic_linear_d8_dgrad": [_P, _I, _I, _I, _P, _P, _P, _P],
+    "octic_linear_d8_dgrad": [_P, _I, _I, _I, _P, _P, _P, _I, _P],
     "octic_linear_d8_wgrad": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "octic_linear_pack_weights": [_P, _I, _I, _P, _P, _P],
     "octic_gelu_d8_fwd": [_P, _L, _P, _L, _L, _I, _I, _P],
@@ -103,6 +104,8 @@ def load() -> C.CDLL:
     lib.octic_strerror.argtypes = [C.c_int]
     lib.octic_version.restype = C.c_int
     lib.octic_device_ok.restype = C.c_int
+    lib.octic_attention_headmajor_supported.restype = C.c_int
+    lib.octic_attention_headmajor_supported.argtypes = [C.c_int, C.c_int, C.c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -118,7 +121,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_attention_bwd": 3}
+KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_attention_bwd": 2}   # bwd: delta + main (legacy: +1)
 
 
 class _Stats:

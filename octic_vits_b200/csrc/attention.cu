@@ -10,7 +10,8 @@
 // One CTA per (batch, head): the whole K and V (<= 272 x 80 bf16 each) sit in shared memory; each warp owns 16 query
 // rows and runs an online-softmax loop over 64-key chunks with mma.sync.m16n8k16 (bf16 in, fp32 accumulate).
 // Backward is two passes without atomics: pass A (warps own key rows) -> dK, dV; pass B (warps own query rows) -> dQ.
-// TODO(round 2): move QK^T / PV onto tcgen05 with S/P in TMEM.
+// These mma.sync kernels are the fallback for the packed-input layout and for sequences outside the envelope of the
+// tcgen05 kernels in attention_tc.cu, which serve the model's hot path.
 #include "attention_common.cuh"
 #include <stdlib.h>
 
@@ -286,8 +287,8 @@ __global__ void __launch_bounds__(192, 2) attn_fwd_kernel(const __nv_bfloat16* _
 // ------------------------------------------- backward: delta = rowsum(dO * O) -------------------------------------------
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
                                                          const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
-                                                         int B, int N, int H, HeadMap m) {
-  // one thread per (b, n, h); delta laid out [B, H, N]
+                                                         int B, int N, int H, HeadMap m, int do_head_major) {
+  // one thread per (b, n, h); delta laid out [B, H, N]; o follows the map m, dO either m or head-major [H][hd]
   const long total = static_cast<long>(B) * N * H;
   for (long idx = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -299,8 +300,9 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
     float acc = 0.f;
     for (int j = 0; j < m.hd; j += 2) {
       const int c = o_col(m, h, j);
+      const int cd = do_head_major ? h * m.hd + j : c;
       const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(orow + c));
-      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(drow + c));
+      const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(drow + cd));
       acc += a.x * g.x + a.y * g.y;
     }
     delta[(static_cast<long>(b) * H + h) * N + n] = acc;
@@ -547,7 +549,7 @@ static int attn_warps(int N) {
   return w < 2 ? 2 : w;                  // the staging loops need blockDim >= hd/2 threads
 }
 static int make_head_map(HeadMap* m, int H, int hd, int octic) {
-  if (H <= 0 || hd <= 0 || (hd % 16) != 0) return OCTIC_ERR_ARG;
+  if (H <= 0 || hd <= 0 || (hd % 16) != 0 || octic < 0 || octic > 2) return OCTIC_ERR_ARG;
   m->octic = octic; m->hd = hd; m->D = H * hd; m->C = m->D / 8; m->ch = hd / 8;
   return OCTIC_OK;
 }
@@ -589,7 +591,7 @@ static int launch_bwd(const void* qkv, const void* o, const void* d_o, const flo
   int dgrid = static_cast<int>((total + 255) / 256);
   if (dgrid > 148 * 16) dgrid = 148 * 16;
   attn_delta_kernel<<<dgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
-                                          delta, B, N, H, m);
+                                          delta, B, N, H, m, 0);
   const int threads = attn_warps(N) * 32;
   attn_bwd_kv_kernel<HD><<<B * H, threads, smem_kv, s>>>(static_cast<const __nv_bfloat16*>(qkv),
                                                          static_cast<const __nv_bfloat16*>(d_o), lse, delta,
@@ -600,15 +602,22 @@ static int launch_bwd(const void* qkv, const void* o, const void* d_o, const flo
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
-// The tcgen05 kernels (attention_tc.cu) serve every shape inside their shared-memory / TMEM envelope; longer
-// sequences use the mma.sync kernels above.  OCTIC_ATTN_LEGACY=1 forces the latter (A/B timing, tests).
-static bool use_tc_path(int N, int hd, bool backward) {
+// The tcgen05 kernels (attention_tc.cu) read head-major q, k, v (layouts OCTIC_ATTN_DENSE and
+// OCTIC_ATTN_OCTIC_HEADMAJOR) and serve every shape inside their shared-memory / TMEM envelope; the mma.sync kernels
+// above serve the packed-input octic layout and longer dense sequences.  OCTIC_ATTN_LEGACY=1 forces the latter for
+// the dense layout (A/B timing, tests).
+static bool legacy_forced() {
   static int legacy = -1;
   if (legacy < 0) {
     const char* e = getenv("OCTIC_ATTN_LEGACY");
     legacy = (e != nullptr && e[0] == '1') ? 1 : 0;
   }
-  return legacy == 0 && attn_tc_supported(N, hd, backward);
+  return legacy != 0;
+}
+static bool use_tc_path(int N, int hd, int layout, bool backward) {
+  if (layout == OCTIC_ATTN_OCTIC_PACKED) return false;
+  if (layout == OCTIC_ATTN_DENSE && legacy_forced()) return false;
+  return attn_tc_supported(N, hd, backward);
 }
 
 }  // namespace octic
@@ -617,6 +626,10 @@ using namespace octic;
 
 extern "C" {
 
+int octic_attention_headmajor_supported(int N, int hd, int backward) {
+  return attn_tc_supported(N, hd, backward != 0) ? 1 : 0;
+}
+
 int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int hd, int octic_layout,
                         void* stream) {
   if (!qkv || !o || B <= 0 || N <= 0) return OCTIC_ERR_ARG;
@@ -624,7 +637,8 @@ int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int 
   int rc = make_head_map(&m, H, hd, octic_layout);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (use_tc_path(N, hd, false)) return launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, s);
+  if (use_tc_path(N, hd, octic_layout, false)) return launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, s);
+  if (octic_layout == OCTIC_ATTN_OCTIC_HEADMAJOR) return OCTIC_ERR_ARG;   // only the tcgen05 path reads this layout
   switch (hd) {
     case 32: return launch_fwd<32>(qkv, o, lse, B, N, H, m, s);
     case 64: return launch_fwd<64>(qkv, o, lse, B, N, H, m, s);
@@ -642,15 +656,16 @@ int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const f
   int rc = make_head_map(&m, H, hd, octic_layout);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (use_tc_path(N, hd, true)) {
+  if (use_tc_path(N, hd, octic_layout, true)) {
     const long total = static_cast<long>(B) * N * H;
     int dgrid = static_cast<int>((total + 255) / 256);
     if (dgrid > 148 * 16) dgrid = 148 * 16;
     attn_delta_kernel<<<dgrid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o),
-                                            delta_ws, B, N, H, m);
+                                            delta_ws, B, N, H, m, octic_layout == OCTIC_ATTN_OCTIC_HEADMAJOR);
     if (cudaGetLastError() != cudaSuccess) return OCTIC_ERR_CUDA;
     return launch_attn_bwd_tc(qkv, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
   }
+  if (octic_layout == OCTIC_ATTN_OCTIC_HEADMAJOR) return OCTIC_ERR_ARG;
   switch (hd) {
     case 32: return launch_bwd<32>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
     case 64: return launch_bwd<64>(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, m, s);

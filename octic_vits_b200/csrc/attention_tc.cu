@@ -1,29 +1,59 @@
 // Octic / dense multi-head attention on tcgen05 (sm_100a), forward and backward, for ViT-length sequences
-// (N = 65..~300 tokens: the whole K, V, Q, dO of one (image, head) live in shared memory).
+// (N = 1..~300 tokens: the whole K, V (and Q, dO in backward) of one (image, head) live in shared memory).
 //
 // Reference: AttentionD8.forward (octic_vits/d8_layers.py:623-656) = pack 5-tuple -> F.scaled_dot_product_attention ->
-// unpack; dense Attention (deit/vit.py:36-50).  As in attention.cu the head vector is gathered from the packed qkv
-// row while it is staged into shared memory (cp.async) and the result is scattered straight back into packed rows.
+// unpack; dense Attention (deit/vit.py:36-50).
 //
-// Layout.  Every operand tile is a row-major [rows][hd] bf16 matrix in the SWIZZLE_32B "atom column" format of
-// sm100_ptx.cuh: it can be fed to tcgen05.mma both K-major (contraction over hd: Q K^T, dO V^T) and MN-major
-// (contraction over tokens: P V, P^T dO, dS^T Q, dS K) without a transposed copy.  hd = 80 (ViT-H/14) costs no padding.
+// Input layout.  q, k, v (and dO in backward) are read HEAD-MAJOR: the head vector of (s, h) is the contiguous column
+// range [s*D + h*hd, +hd) of a [B, N, 3D] (dO: [B, N, D]) bf16 tensor.  That is the dense layout of deit/vit.py, and
+// for octic layers the qkv LinearD8 GEMM (and the proj dgrad GEMM) write it directly from their epilogues
+// (gemm_sm100.cu, "head remap"), so the reference's cat / permute / contiguous copies (d8_layers.py:632-641) never
+// exist and the operands arrive by TMA (3-D tensor map [B][N][cols]: rows past N are zero-filled by the hardware).
+// Outputs (o; dq, dk, dv) are scattered straight into the packed octic rows of d8_layers.py:650-656 (or the dense row).
 //
-// Forward (one CTA per (image, head), 128 threads = 128 TMEM lanes = 128 query rows per tile, two CTAs per SM):
+// Operand tiles.  A row-major [rows][hd] bf16 matrix is kept in the SWIZZLE_32B "atom column" format of sm100_ptx.cuh
+// (exactly what a TMA box of 16 columns x rows produces): it feeds tcgen05.mma both K-major (contraction over hd:
+// Q K^T, dO V^T) and MN-major (contraction over tokens: P V, P^T dO, dS^T Q, dS K) without a transposed copy, and
+// hd = 80 (ViT-H/14) costs no padding.
+//
+// Warp specialisation.  One control warp (one elected lane) issues every TMA load and every tcgen05.mma; the math
+// warps never issue MMAs and never __syncthreads with the control warp: all hand-offs are mbarriers
+// (MMA -> math: tcgen05.commit; math -> MMA: one arrive per math thread).
+//
+// Forward (CTA = (image, head); 4 math warps = 128 TMEM lanes = 128 query rows per tile; two CTAs per SM):
 //   pass 1  S chunk = Q_tile K_chunk^T -> TMEM (two ping-pong buffers) -> row max           (exact, no online rescale)
 //   pass 2  S chunk again -> p = exp2(s*c - max*c) -> bf16 P written in place over S in TMEM -> O += P V_chunk with
 //           the A operand read from TMEM (tcgen05.mma .ts form), accumulators in TMEM.
-//   The tensor pipe executes MMAs in issue order, so "O += P_c V_c" followed by "S chunk c+2" into the same columns
-//   needs no barrier; the only synchronisation per chunk is one mbarrier wait + one __syncthreads.
-// Backward (one CTA per (image, head), 256 threads: two warps per TMEM lane quarter split the columns):
-//   phase 1 (lanes = keys)     S^T = K Q^T, dP^T = V dO^T per query chunk -> P^T, dS^T (bf16, in place) ->
+// Backward (CTA = (image, head); 8 math warps: two warps per TMEM lane quarter split the columns; one CTA per SM):
+//   phase 0 (lanes = keys)     S^T = K Q^T, dP^T = V dO^T per query chunk -> P^T, dS^T (bf16, in place) ->
 //                              dV += P^T dO, dK += dS^T Q
-//   phase 2 (lanes = queries)  S = Q K^T, dP = dO V^T per key chunk -> dS in place -> dQ += dS K
+//   phase 1 (lanes = queries)  S = Q K^T, dP = dO V^T per key chunk -> dS in place -> dQ += dS K
+//   The (phase, tile, chunk) jobs form one flat pipeline: the first-level MMAs of job g+2 are issued as soon as the
+//   second-level MMAs of job g are, across tile and phase boundaries.
 //   delta = rowsum(dO * O) comes from attn_delta_kernel (attention.cu).
 #include "attention_common.cuh"
 #include "sm100_ptx.cuh"
 
 namespace octic {
+
+// Optional in-kernel timeline (tools/attn_trace.cu builds this file with -DOCTIC_ATTN_TRACE): CTA 0 records
+// (clock64 << 8 | event id) for the control thread (slot 0) and math thread 0 (slot 1).
+#ifdef OCTIC_ATTN_TRACE
+__device__ long long g_trace[2 * 2048];
+__device__ int g_trace_n[2];
+// store-only (the event counter lives in a register of the recording thread): no load latency is added to the timeline
+#define OCTIC_TRACE_DECL int tr_i_ = 0
+#define OCTIC_TRACE(slot, id)                                                                           \
+  do {                                                                                                  \
+    if (blockIdx.x == 0 && tr_i_ < 2048) {                                                              \
+      g_trace[(slot) * 2048 + tr_i_] = (static_cast<long long>(clock64()) << 8) | (id);                 \
+      g_trace_n[slot] = ++tr_i_;                                                                        \
+    }                                                                                                   \
+  } while (0)
+#else
+#define OCTIC_TRACE_DECL do { } while (0)
+#define OCTIC_TRACE(slot, id) do { } while (0)
+#endif
 
 struct ChunkPlan {
   int n;
@@ -56,46 +86,32 @@ __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&b);
 }
 
-template <int GRAN>
-__device__ __forceinline__ void cp_async_g(uint32_t dst, const void* src) {
-  if (GRAN == 16) cp_async_16(dst, src); else cp_async_4(dst, src);
-}
-template <int GRAN>
-__device__ __forceinline__ void st_zero_g(uint32_t dst) {
-  if (GRAN == 16) asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
-  else asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"(0u) : "memory");
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
 }
 
-// Stage rows [0, nrows) of a [R][HD] SWIZZLE_32B tile: rows < nvalid come from global (row r at src + r*ld, element
-// unit u at column `col` chosen per thread by the caller's map), the rest are zero-filled.  A "unit" is GRAN bytes.
-// Caller: cp_async_commit_wait_all(); fence_proxy_async_smem(); __syncthreads().
-template <int HD, int GRAN>
-__device__ __forceinline__ void stage_tile(uint32_t dst, int R, const __nv_bfloat16* src, long ld, int nvalid, int nrows,
-                                           const int* cb, const int* sm, int s) {
-  constexpr int EU = GRAN / 2, NU = HD / EU;
-  const int rpi = blockDim.x / NU;
-  const int u = threadIdx.x % NU, r0 = threadIdx.x / NU;
-  if (r0 >= rpi) return;
-  const int c = u * EU;
-  const int col = cb[u] + (sm != nullptr ? s * sm[u] : 0);
-  const uint32_t cbase = dst + (c >> 4) * (R * 32) + (c & 7) * 2;
-  const int half = (c >> 3) & 1;
-  const __nv_bfloat16* g = src + static_cast<long>(r0) * ld + col;
-  const long gstep = static_cast<long>(rpi) * ld;
-  for (int r = r0; r < nrows; r += rpi, g += gstep) {
-    const uint32_t a = cbase + r * 32 + ((half ^ ((r >> 2) & 1)) << 4);
-    if (r < nvalid) cp_async_g<GRAN>(a, g);
-    else st_zero_g<GRAN>(a);
-  }
+// One thread: rows [row0, row0 + R) x columns [col0, col0 + HD) of image b -> an [R][HD] SWIZZLE_32B tile at dst.
+// The map's box is 16 columns x box_rows rows (box_rows divides R).  Completion: R * HD * 2 bytes on `bar`.
+template <int HD>
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int col0, int row0,
+                                              int b, int R, int box_rows) {
+#pragma unroll
+  for (int a = 0; a < HD / 16; ++a)
+    for (int r = 0; r < R; r += box_rows)
+      tma_load_3d(dst + a * (R * 32) + r * 32, map, bar, col0 + 16 * a, row0 + r, b);
 }
 
 // Rows [0, nvalid) of a plain row-major [.][HD] bf16 staging tile -> global rows (scatter through the column map).
+// Executed by the `nthreads` math threads (thread index tid).
 template <int HD, int GRAN>
 __device__ __forceinline__ void store_tile(const uint8_t* stg, __nv_bfloat16* dst, long ld, int nvalid, const int* cb,
-                                           const int* sm, int s) {
+                                           const int* sm, int s, int tid, int nthreads) {
   constexpr int EU = GRAN / 2, NU = HD / EU;
-  const int rpi = blockDim.x / NU;
-  const int u = threadIdx.x % NU, r0 = threadIdx.x / NU;
+  const int rpi = nthreads / NU;
+  const int u = tid % NU, r0 = tid / NU;
   if (r0 >= rpi) return;
   const int col = cb[u] + (sm != nullptr ? s * sm[u] : 0);
   for (int r = r0; r < nvalid; r += rpi) {
@@ -106,179 +122,319 @@ __device__ __forceinline__ void store_tile(const uint8_t* stg, __nv_bfloat16* ds
   }
 }
 
-// 16 fp32 accumulator columns of this thread's TMEM lane -> * scale -> bf16 -> 32 bytes of its staging row
-__device__ __forceinline__ void acc_piece_to_stg(uint32_t taddr, float scale, uint8_t* dst) {
-  uint32_t r[16];
-  tmem_ld_32x16(taddr, r);
+// pieces [P0, P1) (16 fp32 accumulator columns each; compile-time range) of this thread's TMEM lane -> * scale -> bf16
+// -> 32 bytes each of its staging row.  All loads are issued before the single wait (TMEM latency paid once).
+template <int P0, int P1>
+__device__ __forceinline__ void acc_pieces_to_stg(uint32_t taddr, float scale, uint8_t* dst_row) {
+  uint32_t r[P1 - P0][16];
+#pragma unroll
+  for (int i = 0; i < P1 - P0; ++i) tmem_ld_32x16(taddr + (P0 + i) * 16, r[i]);
   tmem_ld_wait();
-  uint4 v0, v1;
-  v0.x = pack2_bf16(__uint_as_float(r[0]) * scale, __uint_as_float(r[1]) * scale);
-  v0.y = pack2_bf16(__uint_as_float(r[2]) * scale, __uint_as_float(r[3]) * scale);
-  v0.z = pack2_bf16(__uint_as_float(r[4]) * scale, __uint_as_float(r[5]) * scale);
-  v0.w = pack2_bf16(__uint_as_float(r[6]) * scale, __uint_as_float(r[7]) * scale);
-  v1.x = pack2_bf16(__uint_as_float(r[8]) * scale, __uint_as_float(r[9]) * scale);
-  v1.y = pack2_bf16(__uint_as_float(r[10]) * scale, __uint_as_float(r[11]) * scale);
-  v1.z = pack2_bf16(__uint_as_float(r[12]) * scale, __uint_as_float(r[13]) * scale);
-  v1.w = pack2_bf16(__uint_as_float(r[14]) * scale, __uint_as_float(r[15]) * scale);
-  *reinterpret_cast<uint4*>(dst) = v0;
-  *reinterpret_cast<uint4*>(dst + 16) = v1;
+#pragma unroll
+  for (int i = 0; i < P1 - P0; ++i) {
+    uint4 v0, v1;
+    v0.x = pack2_bf16(__uint_as_float(r[i][0]) * scale, __uint_as_float(r[i][1]) * scale);
+    v0.y = pack2_bf16(__uint_as_float(r[i][2]) * scale, __uint_as_float(r[i][3]) * scale);
+    v0.z = pack2_bf16(__uint_as_float(r[i][4]) * scale, __uint_as_float(r[i][5]) * scale);
+    v0.w = pack2_bf16(__uint_as_float(r[i][6]) * scale, __uint_as_float(r[i][7]) * scale);
+    v1.x = pack2_bf16(__uint_as_float(r[i][8]) * scale, __uint_as_float(r[i][9]) * scale);
+    v1.y = pack2_bf16(__uint_as_float(r[i][10]) * scale, __uint_as_float(r[i][11]) * scale);
+    v1.z = pack2_bf16(__uint_as_float(r[i][12]) * scale, __uint_as_float(r[i][13]) * scale);
+    v1.w = pack2_bf16(__uint_as_float(r[i][14]) * scale, __uint_as_float(r[i][15]) * scale);
+    *reinterpret_cast<uint4*>(dst_row + (P0 + i) * 32) = v0;
+    *reinterpret_cast<uint4*>(dst_row + (P0 + i) * 32 + 16) = v1;
+  }
+}
+// column-half hh of a KS-piece accumulator: pieces [0, (KS+1)/2) or [(KS+1)/2, KS)
+template <int KS>
+__device__ __forceinline__ void acc_half_to_stg(uint32_t taddr, int hh, float scale, uint8_t* dst_row) {
+  if (hh == 0) acc_pieces_to_stg<0, (KS + 1) / 2>(taddr, scale, dst_row);
+  else acc_pieces_to_stg<(KS + 1) / 2, KS>(taddr, scale, dst_row);
+}
+
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Backward math on one 16-column piece, branch-free over the 16 independent elements (the compiler interleaves them):
+//   p = exp2(x * scale_log2 - lse), ds = p * (y - delta); columns >= nvalid get p = 0.
+// COLS: lse / delta vary along the columns (phase 0: lanes are keys, columns are queries; read from shared memory at
+// lse_addr / del_addr); otherwise they are the per-lane constants lse_r / del_r (phase 1).
+template <bool COLS>
+__device__ __forceinline__ void bwd_piece(const uint32_t (&rx)[16], const uint32_t (&ry)[16], uint32_t (&pkp)[8],
+                                          uint32_t (&pkd)[8], float scale_log2, uint32_t lse_addr, uint32_t del_addr,
+                                          float lse_r, float del_r, int nvalid) {
+  float ls[16], dl[16];
+  if (COLS) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 a = lds_f4(lse_addr + q * 16), d = lds_f4(del_addr + q * 16);
+      ls[4 * q] = a.x; ls[4 * q + 1] = a.y; ls[4 * q + 2] = a.z; ls[4 * q + 3] = a.w;
+      dl[4 * q] = d.x; dl[4 * q + 1] = d.y; dl[4 * q + 2] = d.z; dl[4 * q + 3] = d.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { ls[i] = lse_r; dl[i] = del_r; }
+  }
+  float pv[16], dv[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pv[i] = exp2f(fmaf(__uint_as_float(rx[i]), scale_log2, -ls[i]));
+  if (nvalid < 16) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pv[i] = i < nvalid ? pv[i] : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) dv[i] = pv[i] * (__uint_as_float(ry[i]) - dl[i]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    pkp[i] = pack2_bf16(pv[2 * i], pv[2 * i + 1]);
+    pkd[i] = pack2_bf16(dv[2 * i], dv[2 * i + 1]);
+  }
 }
 
 // =====================================================================================================================
 //  forward
 // =====================================================================================================================
+constexpr int kFwdMathThreads = 256;
+constexpr int kFwdThreads = kFwdMathThreads + 32;
+
 template <int HD, int GRAN>
-__global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ o,
-                                                          float* __restrict__ lse, int N, int H, HeadMap m,
-                                                          float scale_log2, ChunkPlan cp) {
-  constexpr int KS = HD / 16, CW = tc_chunk_width(HD), OCOL = 2 * CW, NU = HD / (GRAN / 2), NPMAX = CW / 16;
+__global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKV,
+                                                                     const __grid_constant__ CUtensorMap tmQ,
+                                                                     __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
+                                                                     int N, int H, HeadMap m, float scale_log2,
+                                                                     const __grid_constant__ ChunkPlan cp,
+                                                                     int kv_box_rows) {
+  constexpr int KS = HD / 16, CW = tc_chunk_width(HD), OCOL = 2 * CW, NU = HD / (GRAN / 2);
+  constexpr int NPW = (CW / 16 + 1) / 2;        // max 16-column pieces per warp in one job
+  constexpr int KS0 = (KS + 1) / 2;             // epilogue: accumulator pieces handled by column-half 0
   constexpr uint32_t kTmemCols = 256;
+  enum { BAR_K = 0, BAR_V = 1, BAR_Q = 2, BAR_SFULL = 3, BAR_SDONE = 5, BAR_OFULL = 7, BAR_QFREE = 8, NBARS = 9 };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Rk = cp.off[cp.n - 1] + cp.w[cp.n - 1];
   const uint32_t kv_bytes = static_cast<uint32_t>(Rk) * HD * 2;
+  constexpr uint32_t q_bytes = 128 * HD * 2;
   uint8_t* Ks = smem;
   uint8_t* Vs = Ks + kv_bytes;
   uint8_t* Qs = Vs + kv_bytes;
-  int* cb = reinterpret_cast<int*>(Qs + 128 * HD * 2);
-  int* sm = cb + NU;
-  int* ocb = sm + NU;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ocb + NU);     // [0], [1]: S buffers; [2]: O complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  float* xch = reinterpret_cast<float*>(Qs + q_bytes);           // [2][128] row max / row sum exchange between warp pairs
+  int* ocb = reinterpret_cast<int*>(xch + 256);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ocb + NU + (NU & 1));
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
-  const long ld3 = 3L * m.D;
-  const __nv_bfloat16* rows = qkv + static_cast<long>(b) * N * ld3;
   __nv_bfloat16* orows = o + static_cast<long>(b) * N * m.D;
 
-  if (tid < NU) {
-    int base, smul;
-    qkv_col(m, h, tid * (GRAN / 2), base, smul);
-    cb[tid] = base; sm[tid] = smul;
-    ocb[tid] = o_col(m, h, tid * (GRAN / 2));
-  }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+  if (tid < NU) ocb[tid] = o_col(m, h, tid * (GRAN / 2));
+  if (tid == kFwdMathThreads) {
+    tma_prefetch_desc(&tmKV);
+    tma_prefetch_desc(&tmQ);
+    mbar_init(&bars[BAR_K], 1); mbar_init(&bars[BAR_V], 1); mbar_init(&bars[BAR_Q], 1);
+    mbar_init(&bars[BAR_SFULL], 1); mbar_init(&bars[BAR_SFULL + 1], 1);
+    mbar_init(&bars[BAR_SDONE], kFwdMathThreads); mbar_init(&bars[BAR_SDONE + 1], kFwdMathThreads);
+    mbar_init(&bars[BAR_OFULL], 1);
+    mbar_init(&bars[BAR_QFREE], kFwdMathThreads);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  __syncthreads();
-  const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs);
-  stage_tile<HD, GRAN>(k_addr, Rk, rows, ld3, N, Rk, cb, sm, 1);
-  stage_tile<HD, GRAN>(v_addr, Rk, rows, ld3, N, Rk, cb, sm, 2);
-  stage_tile<HD, GRAN>(q_addr, 128, rows, ld3, min(128, N), 128, cb, sm, 0);
-  cp_async_commit_wait_all();
-  fence_proxy_async_smem();
+  if (warp == 8) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-
-  auto issue_l1 = [&](int c, int buf) {      // S chunk c = Q_tile K_c^T  -> buffer buf
-    const uint32_t idesc = make_idesc_bf16(128, cp.w[c], 0, 0);
-    const uint32_t d = tmem_base + buf * CW;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      umma_bf16(d, desc_sw32_k(q_addr, 128, 0, ks), desc_sw32_k(k_addr, Rk, cp.off[c], ks), idesc, ks != 0);
-    umma_commit(&bars[buf]);
-  };
-  auto issue_l2 = [&](int c, int buf, bool first) {   // O (+)= P_c V_c, P read from TMEM
-    const uint32_t idesc = make_idesc_bf16(128, HD, 0, 1);
-    const int nk = cp.w[c] >> 4;
-    for (int kk = 0; kk < nk; ++kk)
-      umma_bf16_ts(tmem_base + OCOL, tmem_base + buf * CW + kk * 8, desc_sw32_mn(v_addr, Rk, cp.off[c] + 16 * kk), idesc,
-                   !(first && kk == 0));
-  };
-
-  uint32_t ph[2] = {0u, 0u}, pho = 0u;
+  const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs);
   const int nt = (N + 127) >> 7, nc = cp.n, njobs = 2 * nc;
-  for (int t = 0; t < nt; ++t) {
-    const bool warp_valid = t * 128 + warp * 32 < N;
-    if (tid == 0) issue_l1(0, 0);
-    float mx = -INFINITY, l = 0.f, moff = 0.f;
-    for (int j = 0; j < njobs; ++j) {
-      const int c = j < nc ? j : j - nc, buf = j & 1;
-      if (tid == 0 && j + 1 < njobs) issue_l1(j + 1 < nc ? j + 1 : j + 1 - nc, (j + 1) & 1);
-      mbar_wait(&bars[buf], ph[buf]);
-      ph[buf] ^= 1u;
-      tc_fence_after();
-      if (warp_valid) {
-        const int w = cp.w[c], k0 = cp.off[c];
-        const uint32_t ta = t_lane + buf * CW;
-        const bool need_mask = k0 + w > N;
-        uint32_t r[NPMAX][16];
+
+  if (warp == 8) {
+    // ------------------------------------------------ control warp ------------------------------------------------
+    // The whole warp runs the loops (so addresses and descriptors stay warp-uniform); lane 0 issues TMA / MMA / commit.
+    const bool leader = lane == 0;
+    OCTIC_TRACE_DECL;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const int colq = h * HD, colk = m.D + h * HD, colv = 2 * m.D + h * HD;
+    if (leader) {
+      mbar_arrive_expect_tx(&bars[BAR_K], kv_bytes);
+      tma_load_tile<HD>(k_addr, &tmKV, &bars[BAR_K], colk, 0, b, Rk, kv_box_rows);
+      mbar_arrive_expect_tx(&bars[BAR_Q], q_bytes);
+      tma_load_tile<HD>(q_addr, &tmQ, &bars[BAR_Q], colq, 0, b, 128, 128);
+      mbar_arrive_expect_tx(&bars[BAR_V], kv_bytes);
+      tma_load_tile<HD>(v_addr, &tmKV, &bars[BAR_V], colv, 0, b, Rk, kv_box_rows);
+    }
+    const uint32_t q_lo = desc_lo_sw32(q_addr, 0), k_lo = desc_lo_sw32(k_addr, 0), v_lo = desc_lo_sw32(v_addr, Rk * 32);
+    const uint32_t q_step = (128 * 32) >> 4, k_step = static_cast<uint32_t>(Rk * 32) >> 4;
+    const uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
+
+    auto issue_s = [&](int c, int buf) {      // S chunk c = Q_tile K_c^T  -> buffer buf
+      const uint32_t idesc = make_idesc_bf16(128, cp.w[c], 0, 0);
+      const uint32_t d = tb + buf * CW, kb = k_lo + cp.off[c] * 2;
+      if (elect_one()) {
 #pragma unroll
-        for (int p = 0; p < NPMAX; ++p)
-          if (p * 16 < w) tmem_ld_32x16(ta + p * 16, r[p]);
-        tmem_ld_wait();
-        if (j < nc) {
+        for (int ks = 0; ks < KS; ++ks) umma_ss_lohi(d, q_lo + ks * q_step, kb + ks * k_step, kDescHiSw32, idesc, ks != 0);
+        umma_commit(&bars[BAR_SFULL + buf]);
+      }
+    };
+    auto issue_pv = [&](int c, int buf, bool first, bool last) {   // O (+)= P_c V_c, P read from TMEM
+      const int nk = cp.w[c] >> 4;
+      const uint32_t a = tb + buf * CW, vb = v_lo + cp.off[c] * 2;
+      if (elect_one()) {
 #pragma unroll
-          for (int p = 0; p < NPMAX; ++p)
-            if (p * 16 < w) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float v = __uint_as_float(r[p][i]);
-                if (need_mask && k0 + p * 16 + i >= N) v = -INFINITY;
-                mx = fmaxf(mx, v);
-              }
-            }
-          if (j == nc - 1) moff = mx * scale_log2;
-        } else {
-#pragma unroll
-          for (int p = 0; p < NPMAX; ++p)
-            if (p * 16 < w) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float e0 = exp2f(fmaf(__uint_as_float(r[p][2 * i]), scale_log2, -moff));
-                float e1 = exp2f(fmaf(__uint_as_float(r[p][2 * i + 1]), scale_log2, -moff));
-                if (need_mask) {
-                  if (k0 + p * 16 + 2 * i >= N) e0 = 0.f;
-                  if (k0 + p * 16 + 2 * i + 1 >= N) e1 = 0.f;
-                }
-                l += e0 + e1;
-                pk[i] = pack2_bf16(e0, e1);
-              }
-              tmem_st_32x8(ta + p * 8, pk);
-            }
-          tmem_st_wait();
+        for (int kk = 0; kk < CW / 16; ++kk)
+          if (kk < nk) umma_ts_lohi(tb + OCOL, a + kk * 8, vb + kk * 32, kDescHiSw32, idesc_pv, !(first && kk == 0));
+        if (last) umma_commit(&bars[BAR_OFULL]);
+      }
+    };
+
+    mbar_wait(&bars[BAR_K], 0);
+    bool v_ready = false;
+    uint32_t phq = 0, phd0 = 0, phd1 = 0, phf = 0;
+    for (int t = 0; t < nt; ++t) {
+      if (t > 0) {
+        mbar_wait(&bars[BAR_QFREE], phf);      // epilogue of tile t-1 has drained O and the staging copy in Qs
+        phf ^= 1u;
+        if (leader) {
+          mbar_arrive_expect_tx(&bars[BAR_Q], q_bytes);
+          tma_load_tile<HD>(q_addr, &tmQ, &bars[BAR_Q], colq, t * 128, b, 128, 128);
         }
       }
-      tc_fence_before();
-      __syncthreads();
-      if (j >= nc && tid == 0) {
+      mbar_wait(&bars[BAR_Q], phq);
+      phq ^= 1u;
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1 < nc ? 1 : 1 - nc, 1);
+      for (int j = 0; j < njobs; ++j) {
+        const int buf = j & 1;
+        if (buf == 0) { mbar_wait(&bars[BAR_SDONE], phd0); phd0 ^= 1u; }
+        else { mbar_wait(&bars[BAR_SDONE + 1], phd1); phd1 ^= 1u; }
         tc_fence_after();
-        issue_l2(c, buf, j == nc);
-        if (j == njobs - 1) umma_commit(&bars[2]);
+        if (leader) OCTIC_TRACE(0, 1);
+        if (j >= nc) {
+          if (!v_ready) { mbar_wait(&bars[BAR_V], 0); v_ready = true; }
+          issue_pv(j - nc, buf, j == nc, j == njobs - 1);
+        }
+        if (j + 2 < njobs) issue_s(j + 2 < nc ? j + 2 : j + 2 - nc, buf);
+        if (leader) OCTIC_TRACE(0, 2);
       }
     }
-    mbar_wait(&bars[2], pho);
-    pho ^= 1u;
-    tc_fence_after();
-    const int row = t * 128 + tid;
-    if (warp_valid) {
-      const float inv = 1.0f / l;
+  } else {
+    // -------------------------------------------------- math warps --------------------------------------------------
+    // Two warps per TMEM lane quarter (q4) split the columns of every chunk and of the output accumulator (hh).
+    const int q4 = warp & 3, hh = warp >> 2;
+    const int rloc = q4 * 32 + lane;                   // row inside the tile
+    OCTIC_TRACE_DECL;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    uint32_t phs0 = 0, phs1 = 0, pho = 0u;
+    for (int t = 0; t < nt; ++t) {
+      const bool warp_valid = t * 128 + q4 * 32 < N;
+      float mx = -INFINITY, l = 0.f, moff = 0.f;
+      for (int j = 0; j < njobs; ++j) {
+        const int c = j < nc ? j : j - nc, buf = j & 1;
+        if (buf == 0) { mbar_wait(&bars[BAR_SFULL], phs0); phs0 ^= 1u; }
+        else { mbar_wait(&bars[BAR_SFULL + 1], phs1); phs1 ^= 1u; }
+        tc_fence_after();
+        if (tid == 0) OCTIC_TRACE(1, 3);
+        if (warp_valid) {
+          const int w = cp.w[c], k0 = cp.off[c];
+          const int np = w >> 4, np0 = (np + 1) >> 1;
+          const int pb = hh == 0 ? 0 : np0, pe = hh == 0 ? np0 : np;
+          const uint32_t ta = t_lane + buf * CW;
+          uint32_t r[NPW][16];
 #pragma unroll
-      for (int p = 0; p < KS; ++p) acc_piece_to_stg(t_lane + OCOL + p * 16, inv, Qs + tid * (HD * 2) + p * 32);
-      if (lse != nullptr && row < N) lse[(static_cast<long>(b) * H + h) * N + row] = (mx * scale_log2 + log2f(l)) * kLn2;
-    }
-    tc_fence_before();
-    __syncthreads();
-    store_tile<HD, GRAN>(Qs, orows + static_cast<long>(t) * 128 * m.D, m.D, min(128, N - t * 128), ocb, nullptr, 0);
-    __syncthreads();
-    if (t + 1 < nt) {
-      stage_tile<HD, GRAN>(q_addr, 128, rows + static_cast<long>(t + 1) * 128 * ld3, ld3, min(128, N - (t + 1) * 128), 128,
-                           cb, sm, 0);
-      cp_async_commit_wait_all();
-      fence_proxy_async_smem();
-      __syncthreads();
+          for (int pp = 0; pp < NPW; ++pp)
+            if (pb + pp < pe) tmem_ld_32x16(ta + (pb + pp) * 16, r[pp]);
+          tmem_ld_wait();
+          if (tid == 0) OCTIC_TRACE(1, 4);
+          if (j < nc) {
+            float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+            for (int pp = 0; pp < NPW; ++pp)
+              if (pb + pp < pe) {
+                const int nvalid = N - (k0 + (pb + pp) * 16);
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[pp][i]);
+                if (nvalid < 16) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+                }
+              }
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            if (j == nc - 1) {
+              // combine the two column halves of the row
+              xch[hh * 128 + rloc] = mx;
+              named_bar_sync(1 + q4, 64);
+              mx = fmaxf(mx, xch[(hh ^ 1) * 128 + rloc]);
+              moff = mx * scale_log2;
+            }
+          } else {
+            // both warps of this lane quarter hold their S columns in registers before either overwrites them with P
+            tc_fence_before();
+            named_bar_sync(1 + q4, 64);
+            tc_fence_after();
+            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+            for (int pp = 0; pp < NPW; ++pp)
+              if (pb + pp < pe) {
+                const int nvalid = N - (k0 + (pb + pp) * 16);
+                float e[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[pp][i]), scale_log2, -moff));
+                if (nvalid < 16) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) e[i] = i < nvalid ? e[i] : 0.f;
+                }
+                uint32_t pk[8];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                  l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
+                  pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
+                  pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
+                }
+                tmem_st_32x8(ta + (pb + pp) * 8, pk);
+              }
+            l += (l0 + l1) + (l2 + l3);
+            tmem_st_wait();
+          }
+        }
+        tc_fence_before();
+        if (tid == 0) OCTIC_TRACE(1, 5);
+        mbar_arrive(&bars[BAR_SDONE + buf]);
+      }
+      if (warp_valid) {
+        // total row sum = both column halves (written before, read after the pair barrier)
+        xch[hh * 128 + rloc] = l;
+        named_bar_sync(1 + q4, 64);
+        l += xch[(hh ^ 1) * 128 + rloc];
+      }
+      mbar_wait(&bars[BAR_OFULL], pho);
+      pho ^= 1u;
+      tc_fence_after();
+      if (tid == 0) OCTIC_TRACE(1, 6);
+      const int row = t * 128 + rloc;
+      if (warp_valid) {
+        const float inv = 1.0f / l;
+        acc_half_to_stg<KS>(t_lane + OCOL, hh, inv, Qs + rloc * (HD * 2));
+        if (hh == 0 && lse != nullptr && row < N)
+          lse[(static_cast<long>(b) * H + h) * N + row] = (mx * scale_log2 + log2f(l)) * kLn2;
+      }
+      tc_fence_before();
+      named_bar_sync(5, kFwdMathThreads);
+      store_tile<HD, GRAN>(Qs, orows + static_cast<long>(t) * 128 * m.D, m.D, min(128, N - t * 128), ocb, nullptr, 0, tid,
+                           kFwdMathThreads);
+      fence_proxy_async_smem();      // the next Q tile arrives in Qs through the async proxy
+      if (tid == 0) OCTIC_TRACE(1, 7);
+      mbar_arrive(&bars[BAR_QFREE]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -287,17 +443,25 @@ __global__ void __launch_bounds__(128) attn_fwd_tc_kernel(const __nv_bfloat16* _
 // =====================================================================================================================
 //  backward
 // =====================================================================================================================
+constexpr int kBwdMathThreads = 256;
+constexpr int kBwdThreads = kBwdMathThreads + 32;
+
 template <int HD, int GRAN>
-__global__ void __launch_bounds__(256, 1) attn_bwd_tc_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                             const __nv_bfloat16* __restrict__ d_o,
-                                                             const float* __restrict__ lse, const float* __restrict__ delta,
-                                                             __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
-                                                             float scale, float scale_log2, ChunkPlan cp) {
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,
+                                                                     const __grid_constant__ CUtensorMap tmDO,
+                                                                     const float* __restrict__ lse,
+                                                                     const float* __restrict__ delta,
+                                                                     __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
+                                                                     float scale, float scale_log2,
+                                                                     const __grid_constant__ ChunkPlan cp,
+                                                                     int box_rows) {
   constexpr int KS = HD / 16, CW = tc_chunk_width(HD), ACC = 4 * CW, NU = HD / (GRAN / 2);
   constexpr int NPW = (CW / 16 + 1) / 2;        // max 16-column pieces per warp in the math step
   constexpr int KS0 = (KS + 1) / 2;             // epilogue: pieces of the accumulator handled by column-half 0
   constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t stg_bytes = 128 * HD * 2;
   static_assert(ACC + 2 * HD <= 512, "TMEM budget");
+  enum { BAR_KQ = 0, BAR_VDO = 1, BAR_LFULL = 2, BAR_MDONE = 4, BAR_ACC = 6, NBARS = 7 };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Rk = cp.off[cp.n - 1] + cp.w[cp.n - 1];
@@ -306,187 +470,212 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_tc_kernel(const __nv_bfloat16
   uint8_t* Ks = Qs + mat_bytes;
   uint8_t* Vs = Ks + mat_bytes;
   uint8_t* dOs = Vs + mat_bytes;
-  uint8_t* stg = dOs + mat_bytes;                 // [128][HD] bf16 staging; also absorbs the A-tile over-read of dOs
-  float* lse_s = reinterpret_cast<float*>(stg + 128 * HD * 2);
+  uint8_t* stg = dOs + mat_bytes;                 // 2 x [128][HD] bf16 staging; also absorbs the A-tile over-read of dOs
+  float* lse_s = reinterpret_cast<float*>(stg + 2 * stg_bytes);
   float* del_s = lse_s + Rk;
   int* cb = reinterpret_cast<int*>(del_s + Rk);
   int* sm = cb + NU;
-  int* ocb = sm + NU;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ocb + NU);     // [0], [1]: first-level buffers; [2]: accumulators complete
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + NU + ((2 * NU) & 1));
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int q4 = warp & 3, hh = warp >> 2;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const long ld3 = 3L * m.D;
-  const __nv_bfloat16* rows = qkv + static_cast<long>(b) * N * ld3;
-  const __nv_bfloat16* dorows = d_o + static_cast<long>(b) * N * m.D;
   __nv_bfloat16* drows = dqkv + static_cast<long>(b) * N * ld3;
 
   if (tid < NU) {
     int base, smul;
     qkv_col(m, h, tid * (GRAN / 2), base, smul);
     cb[tid] = base; sm[tid] = smul;
-    ocb[tid] = o_col(m, h, tid * (GRAN / 2));
   }
-  if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+  if (tid == kBwdMathThreads) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(&bars[BAR_KQ], 1); mbar_init(&bars[BAR_VDO], 1);
+    mbar_init(&bars[BAR_LFULL], 1); mbar_init(&bars[BAR_LFULL + 1], 1);
+    mbar_init(&bars[BAR_MDONE], kBwdMathThreads); mbar_init(&bars[BAR_MDONE + 1], kBwdMathThreads);
+    mbar_init(&bars[BAR_ACC], 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
-  for (int i = tid; i < Rk; i += blockDim.x) {
-    const long off = (static_cast<long>(b) * H + h) * N + i;
-    lse_s[i] = i < N ? lse[off] * kLog2e : INFINITY;     // +inf -> P = 0 for padded queries
-    del_s[i] = i < N ? delta[off] : 0.f;
+  if (warp == 8) tmem_alloc(tmem_ptr, kTmemCols);
+  if (tid < kBwdMathThreads) {
+    for (int i = tid; i < Rk; i += kBwdMathThreads) {
+      const long off = (static_cast<long>(b) * H + h) * N + i;
+      lse_s[i] = i < N ? lse[off] * kLog2e : INFINITY;     // +inf -> P = 0 for padded queries
+      del_s[i] = i < N ? delta[off] : 0.f;
+    }
+    for (int i = tid; i < static_cast<int>(2 * stg_bytes / 16); i += kBwdMathThreads)
+      reinterpret_cast<uint4*>(stg)[i] = make_uint4(0u, 0u, 0u, 0u);
   }
-  for (int i = tid; i < 128 * HD * 2 / 16; i += blockDim.x) reinterpret_cast<uint4*>(stg)[i] = make_uint4(0u, 0u, 0u, 0u);
-  __syncthreads();
-  const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), do_addr = smem_u32(dOs);
-  stage_tile<HD, GRAN>(q_addr, Rk, rows, ld3, N, Rk, cb, sm, 0);
-  stage_tile<HD, GRAN>(k_addr, Rk, rows, ld3, N, Rk, cb, sm, 1);
-  stage_tile<HD, GRAN>(v_addr, Rk, rows, ld3, N, Rk, cb, sm, 2);
-  stage_tile<HD, GRAN>(do_addr, Rk, dorows, m.D, N, Rk, ocb, nullptr, 0);
-  cp_async_commit_wait_all();
-  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-
-  // first level: X = A1[tile rows] B1[chunk rows]^T -> buffer, Y = A2[tile rows] B2[chunk rows]^T -> buffer + CW
-  auto issue_l1 = [&](uint32_t a1, uint32_t b1, uint32_t a2, uint32_t b2, int row0, int c, int buf) {
-    const uint32_t idesc = make_idesc_bf16(128, cp.w[c], 0, 0);
-    const uint32_t d = tmem_base + buf * 2 * CW;
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      umma_bf16(d, desc_sw32_k(a1, Rk, row0, ks), desc_sw32_k(b1, Rk, cp.off[c], ks), idesc, ks != 0);
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-      umma_bf16(d + CW, desc_sw32_k(a2, Rk, row0, ks), desc_sw32_k(b2, Rk, cp.off[c], ks), idesc, ks != 0);
-    umma_commit(&bars[buf]);
-  };
-  // second level: acc (+)= (bf16 in TMEM at a_col) * B[chunk rows] (MN-major)
-  auto issue_l2 = [&](uint32_t acc_col, uint32_t a_col, uint32_t bmat, int c, bool first) {
-    const uint32_t idesc = make_idesc_bf16(128, HD, 0, 1);
-    const int nk = cp.w[c] >> 4;
-    for (int kk = 0; kk < nk; ++kk)
-      umma_bf16_ts(tmem_base + acc_col, tmem_base + a_col + kk * 8, desc_sw32_mn(bmat, Rk, cp.off[c] + 16 * kk), idesc,
-                   !(first && kk == 0));
-  };
-  // accumulator -> * sc -> bf16 staging -> packed global rows (tensor s of the qkv row)
-  auto flush_acc = [&](uint32_t acc_col, float sc, int row0, int s, bool warp_valid) {
-    if (warp_valid) {
-      const int p0 = hh == 0 ? 0 : KS0, p1 = hh == 0 ? KS0 : KS;
-      for (int p = p0; p < p1; ++p)
-        acc_piece_to_stg(t_lane + acc_col + p * 16, sc, stg + (q4 * 32 + lane) * (HD * 2) + p * 32);
-    }
-    tc_fence_before();
-    __syncthreads();
-    store_tile<HD, GRAN>(stg, drows + static_cast<long>(row0) * ld3, ld3, min(128, N - row0), cb, sm, s);
-    __syncthreads();
-  };
-
-  uint32_t ph[2] = {0u, 0u}, pha = 0u;
+  const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), do_addr = smem_u32(dOs);
   const int nt = (N + 127) >> 7, nc = cp.n;
+  const int jobs_per_phase = nt * nc, G = 2 * jobs_per_phase;
 
-  for (int phase = 0; phase < 2; ++phase) {
-    for (int t = 0; t < nt; ++t) {
-      const int row0 = t * 128;
-      const int my_row = row0 + q4 * 32 + lane;
-      const bool warp_valid = row0 + q4 * 32 < N;
-      // phase 0: lanes = keys,    X = S^T = K Q^T,  Y = dP^T = V dO^T
-      // phase 1: lanes = queries, X = S   = Q K^T,  Y = dP   = dO V^T
-      const uint32_t a1 = phase == 0 ? k_addr : q_addr, b1 = phase == 0 ? q_addr : k_addr;
-      const uint32_t a2 = phase == 0 ? v_addr : do_addr, b2 = phase == 0 ? do_addr : v_addr;
-      float lse_r = 0.f, del_r = 0.f;
-      if (phase == 1) {
-        lse_r = my_row < Rk ? lse_s[my_row] : INFINITY;
-        del_r = my_row < Rk ? del_s[my_row] : 0.f;
+  if (warp == 8) {
+    // ------------------------------------------------ control warp ------------------------------------------------
+    // The whole warp runs the loops (so addresses and descriptors stay warp-uniform); lane 0 issues TMA / MMA / commit.
+    const bool leader = lane == 0;
+    OCTIC_TRACE_DECL;
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    if (leader) {
+      mbar_arrive_expect_tx(&bars[BAR_KQ], 2 * mat_bytes);
+      tma_load_tile<HD>(k_addr, &tmQKV, &bars[BAR_KQ], m.D + h * HD, 0, b, Rk, box_rows);
+      tma_load_tile<HD>(q_addr, &tmQKV, &bars[BAR_KQ], h * HD, 0, b, Rk, box_rows);
+      mbar_arrive_expect_tx(&bars[BAR_VDO], 2 * mat_bytes);
+      tma_load_tile<HD>(v_addr, &tmQKV, &bars[BAR_VDO], 2 * m.D + h * HD, 0, b, Rk, box_rows);
+      tma_load_tile<HD>(do_addr, &tmDO, &bars[BAR_VDO], h * HD, 0, b, Rk, box_rows);
+    }
+    // low descriptor words: K-major views (first level) and MN-major views (second level, LBO = atom-column stride)
+    const uint32_t mstep = static_cast<uint32_t>(Rk * 32) >> 4;       // one K-step = next atom column
+    const uint32_t qk = desc_lo_sw32(q_addr, 0), kk_ = desc_lo_sw32(k_addr, 0), vk = desc_lo_sw32(v_addr, 0),
+                   dok = desc_lo_sw32(do_addr, 0);
+    const uint32_t qm = desc_lo_sw32(q_addr, Rk * 32), km = desc_lo_sw32(k_addr, Rk * 32), dom = desc_lo_sw32(do_addr, Rk * 32);
+    const uint32_t idesc_l2 = make_idesc_bf16(128, HD, 0, 1);
+
+    // first level of job g: X = A1[tile rows] B1[chunk rows]^T -> buffer, Y = A2[tile rows] B2[chunk rows]^T -> +CW
+    //   phase 0: lanes = keys,    X = S^T = K Q^T,  Y = dP^T = V dO^T
+    //   phase 1: lanes = queries, X = S   = Q K^T,  Y = dP   = dO V^T
+    auto issue_l1 = [&](int g) {
+      const int phase = g >= jobs_per_phase, r = g - phase * jobs_per_phase, t = r / nc, c = r - t * nc, buf = g & 1;
+      const uint32_t a1 = (phase == 0 ? kk_ : qk) + t * 256, b1 = (phase == 0 ? qk : kk_) + cp.off[c] * 2;
+      const uint32_t a2 = (phase == 0 ? vk : dok) + t * 256, b2 = (phase == 0 ? dok : vk) + cp.off[c] * 2;
+      const uint32_t idesc = make_idesc_bf16(128, cp.w[c], 0, 0);
+      const uint32_t d = tb + buf * 2 * CW;
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) umma_ss_lohi(d, a1 + ks * mstep, b1 + ks * mstep, kDescHiSw32, idesc, ks != 0);
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) umma_ss_lohi(d + CW, a2 + ks * mstep, b2 + ks * mstep, kDescHiSw32, idesc, ks != 0);
+        umma_commit(&bars[BAR_LFULL + buf]);
       }
-      if (tid == 0) issue_l1(a1, b1, a2, b2, row0, 0, 0);
-      for (int c = 0; c < nc; ++c) {
-        const int buf = c & 1;
-        if (tid == 0 && c + 1 < nc) issue_l1(a1, b1, a2, b2, row0, c + 1, (c + 1) & 1);
-        mbar_wait(&bars[buf], ph[buf]);
-        ph[buf] ^= 1u;
-        tc_fence_after();
-        if (warp_valid) {
-          const int w = cp.w[c], k0 = cp.off[c];
-          const int np = w >> 4, np0 = (np + 1) >> 1;
-          const int pb = hh == 0 ? 0 : np0, pe = hh == 0 ? np0 : np;
-          const uint32_t tx = t_lane + buf * 2 * CW, ty = tx + CW;
-          uint32_t rx[NPW][16], ry[NPW][16];
+    };
+    // second level: acc (+)= (bf16 in TMEM at a_col) * B[chunk rows] (MN-major)
+    auto issue_l2 = [&](uint32_t acc_col, uint32_t a_col, uint32_t bm, int c, bool first) {
+      const int nk = cp.w[c] >> 4;
+      const uint32_t bb = bm + cp.off[c] * 2;
+      if (elect_one()) {
 #pragma unroll
-          for (int pp = 0; pp < NPW; ++pp)
-            if (pb + pp < pe) {
-              tmem_ld_32x16(tx + (pb + pp) * 16, rx[pp]);
-              tmem_ld_32x16(ty + (pb + pp) * 16, ry[pp]);
-            }
-          tmem_ld_wait();
-          // both warps of this lane quarter hold their inputs in registers before either overwrites the columns
-          tc_fence_before();
-          named_bar_sync(1 + q4, 64);
+        for (int kk = 0; kk < CW / 16; ++kk)
+          if (kk < nk) umma_ts_lohi(tb + acc_col, tb + a_col + kk * 8, bb + kk * 32, kDescHiSw32, idesc_l2, !(first && kk == 0));
+      }
+    };
+
+    mbar_wait(&bars[BAR_KQ], 0);
+    mbar_wait(&bars[BAR_VDO], 0);
+    tc_fence_after();
+    issue_l1(0);
+    if (G > 1) issue_l1(1);
+    uint32_t phd0 = 0u, phd1 = 0u;
+    for (int g = 0; g < G; ++g) {
+      const int phase = g >= jobs_per_phase, r = g - phase * jobs_per_phase, c = r % nc, buf = g & 1;
+      if (buf == 0) { mbar_wait(&bars[BAR_MDONE], phd0); phd0 ^= 1u; }
+      else { mbar_wait(&bars[BAR_MDONE + 1], phd1); phd1 ^= 1u; }
+      tc_fence_after();
+      if (leader) OCTIC_TRACE(0, 1);
+      const uint32_t xcol = buf * 2 * CW, ycol = xcol + CW;
+      if (phase == 0) {
+        issue_l2(ACC + HD, xcol, dom, c, c == 0);    // dV += P^T dO
+        issue_l2(ACC, ycol, qm, c, c == 0);          // dK += dS^T Q
+      } else {
+        issue_l2(ACC, ycol, km, c, c == 0);          // dQ += dS K
+      }
+      if (c == nc - 1 && elect_one()) umma_commit(&bars[BAR_ACC]);
+      if (g + 2 < G) issue_l1(g + 2);
+      if (leader) OCTIC_TRACE(0, 2);
+    }
+  } else {
+    // -------------------------------------------------- math warps --------------------------------------------------
+    const int q4 = warp & 3, hh = warp >> 2;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    uint8_t* my_stg = stg + (q4 * 32 + lane) * (HD * 2);
+    const uint32_t lse_sa = smem_u32(lse_s), del_sa = smem_u32(del_s);
+    OCTIC_TRACE_DECL;
+    uint32_t phl[2] = {0u, 0u}, pha = 0u;
+    int g = 0;
+    for (int phase = 0; phase < 2; ++phase) {
+      for (int t = 0; t < nt; ++t) {
+        const int row0 = t * 128;
+        const int my_row = row0 + q4 * 32 + lane;
+        const bool warp_valid = row0 + q4 * 32 < N;
+        float lse_r = 0.f, del_r = 0.f;
+        if (phase == 1) {
+          lse_r = my_row < Rk ? lse_s[my_row] : INFINITY;
+          del_r = my_row < Rk ? del_s[my_row] : 0.f;
+        }
+        for (int c = 0; c < nc; ++c, ++g) {
+          const int buf = g & 1;
+          mbar_wait(&bars[BAR_LFULL + buf], phl[buf]);
+          phl[buf] ^= 1u;
           tc_fence_after();
+          if (tid == 0) OCTIC_TRACE(1, 3);
+          if (warp_valid) {
+            const int w = cp.w[c], k0 = cp.off[c];
+            const int np = w >> 4, np0 = (np + 1) >> 1;
+            const int pb = hh == 0 ? 0 : np0, pe = hh == 0 ? np0 : np;
+            const uint32_t tx = t_lane + buf * 2 * CW, ty = tx + CW;
+            uint32_t rx[NPW][16], ry[NPW][16];
 #pragma unroll
-          for (int pp = 0; pp < NPW; ++pp)
-            if (pb + pp < pe) {
-              const int col0 = k0 + (pb + pp) * 16;
-              uint32_t pkp[8], pkd[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float p0, p1, d0, d1;
-                if (phase == 0) {
-                  const float2 l2 = *reinterpret_cast<const float2*>(lse_s + col0 + 2 * i);
-                  const float2 dl = *reinterpret_cast<const float2*>(del_s + col0 + 2 * i);
-                  p0 = exp2f(fmaf(__uint_as_float(rx[pp][2 * i]), scale_log2, -l2.x));
-                  p1 = exp2f(fmaf(__uint_as_float(rx[pp][2 * i + 1]), scale_log2, -l2.y));
-                  d0 = p0 * (__uint_as_float(ry[pp][2 * i]) - dl.x);
-                  d1 = p1 * (__uint_as_float(ry[pp][2 * i + 1]) - dl.y);
-                } else {
-                  p0 = exp2f(fmaf(__uint_as_float(rx[pp][2 * i]), scale_log2, -lse_r));
-                  p1 = exp2f(fmaf(__uint_as_float(rx[pp][2 * i + 1]), scale_log2, -lse_r));
-                  if (col0 + 2 * i >= N) p0 = 0.f;
-                  if (col0 + 2 * i + 1 >= N) p1 = 0.f;
-                  d0 = p0 * (__uint_as_float(ry[pp][2 * i]) - del_r);
-                  d1 = p1 * (__uint_as_float(ry[pp][2 * i + 1]) - del_r);
-                }
-                pkp[i] = pack2_bf16(p0, p1);
-                pkd[i] = pack2_bf16(d0, d1);
+            for (int pp = 0; pp < NPW; ++pp)
+              if (pb + pp < pe) {
+                tmem_ld_32x16(tx + (pb + pp) * 16, rx[pp]);
+                tmem_ld_32x16(ty + (pb + pp) * 16, ry[pp]);
               }
-              if (phase == 0) tmem_st_32x8(tx + (pb + pp) * 8, pkp);
-              tmem_st_32x8(ty + (pb + pp) * 8, pkd);
-            }
-          tmem_st_wait();
+            tmem_ld_wait();
+            if (tid == 0) OCTIC_TRACE(1, 4);
+            // both warps of this lane quarter hold their inputs in registers before either overwrites the columns
+            tc_fence_before();
+            named_bar_sync(1 + q4, 64);
+            tc_fence_after();
+            if (tid == 0) OCTIC_TRACE(1, 8);
+#pragma unroll
+            for (int pp = 0; pp < NPW; ++pp)
+              if (pb + pp < pe) {
+                const int col0 = k0 + (pb + pp) * 16;
+                uint32_t pkp[8], pkd[8];
+                if (phase == 0) {
+                  // padded query columns carry lse = +inf (p = 0) and delta = 0: no explicit mask
+                  bwd_piece<true>(rx[pp], ry[pp], pkp, pkd, scale_log2, lse_sa + col0 * 4, del_sa + col0 * 4, 0.f, 0.f, 16);
+                  tmem_st_32x8(tx + (pb + pp) * 8, pkp);
+                } else {
+                  bwd_piece<false>(rx[pp], ry[pp], pkp, pkd, scale_log2, 0u, 0u, lse_r, del_r, N - col0);
+                }
+                tmem_st_32x8(ty + (pb + pp) * 8, pkd);
+              }
+            tmem_st_wait();
+          }
+          tc_fence_before();
+          if (tid == 0) OCTIC_TRACE(1, 5);
+          mbar_arrive(&bars[BAR_MDONE + buf]);
+        }
+        // ---- flush the accumulators of this tile: TMEM -> bf16 staging -> packed global rows ----
+        mbar_wait(&bars[BAR_ACC], pha);
+        pha ^= 1u;
+        tc_fence_after();
+        if (tid == 0) OCTIC_TRACE(1, 6);
+        named_bar_sync(5, kBwdMathThreads);          // the previous flush's global stores have read the staging tiles
+        if (warp_valid) {
+          acc_half_to_stg<KS>(t_lane + ACC, hh, scale, my_stg);                               // dK or dQ
+          if (phase == 0) acc_half_to_stg<KS>(t_lane + ACC + HD, hh, 1.0f, my_stg + stg_bytes);   // dV
         }
         tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t xcol = buf * 2 * CW, ycol = xcol + CW;
-          if (phase == 0) {
-            issue_l2(ACC + HD, xcol, do_addr, c, c == 0);    // dV += P^T dO
-            issue_l2(ACC, ycol, q_addr, c, c == 0);          // dK += dS^T Q
-          } else {
-            issue_l2(ACC, ycol, k_addr, c, c == 0);          // dQ += dS K
-          }
-          if (c == nc - 1) umma_commit(&bars[2]);
-        }
-      }
-      mbar_wait(&bars[2], pha);
-      pha ^= 1u;
-      tc_fence_after();
-      if (phase == 0) {
-        flush_acc(ACC, scale, row0, 1, warp_valid);          // dK
-        flush_acc(ACC + HD, 1.0f, row0, 2, warp_valid);      // dV
-      } else {
-        flush_acc(ACC, scale, row0, 0, warp_valid);          // dQ
+        named_bar_sync(5, kBwdMathThreads);
+        const int nvalid = min(128, N - row0);
+        store_tile<HD, GRAN>(stg, drows + static_cast<long>(row0) * ld3, ld3, nvalid, cb, sm, phase == 0 ? 1 : 0, tid,
+                             kBwdMathThreads);
+        if (phase == 0)
+          store_tile<HD, GRAN>(stg + stg_bytes, drows + static_cast<long>(row0) * ld3, ld3, nvalid, cb, sm, 2, tid,
+                               kBwdMathThreads);
+        if (tid == 0) OCTIC_TRACE(1, 7);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
@@ -497,13 +686,44 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_tc_kernel(const __nv_bfloat16
 // =====================================================================================================================
 constexpr int kMaxSmem = 232448;   // 227 KiB
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn attn_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+// bf16 [B][N][cols] (contiguous); box = 16 columns x box_rows rows x 1 image, SWIZZLE_32B, zero fill out of bounds
+static int make_map_rows(CUtensorMap* map, const void* base, int B, int N, long cols, int box_rows) {
+  EncodeTiledFn enc = attn_encode_fn();
+  if (enc == nullptr) return OCTIC_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (cols * 2) % 16 != 0) return OCTIC_ERR_ALIGN;
+  if (box_rows < 1 || box_rows > 256) return OCTIC_ERR_ARG;
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(B)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * static_cast<cuuint64_t>(N)};
+  cuuint32_t box[3] = {16, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OCTIC_OK : OCTIC_ERR_TMAP;
+}
+static int pick_box_rows(int Rk) { return Rk > 256 ? Rk / 2 : Rk; }
+
 static size_t fwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 3 * nu * 4 + 3 * 8 + 16 + 1024;
+  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 256 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 1024;
 }
 static size_t bwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(4 * Rk + 128) * hd * 2 + 2 * Rk * 4 + 3 * nu * 4 + 3 * 8 + 16 + 1024;
+  return static_cast<size_t>(4 * Rk + 256) * hd * 2 + 2 * Rk * 4 + (2 * nu + 1) * 4 + 7 * 8 + 16 + 1024;
 }
 
 bool attn_tc_supported(int N, int hd, bool backward) {
@@ -511,6 +731,7 @@ bool attn_tc_supported(int N, int hd, bool backward) {
   ChunkPlan p;
   if (N < 1 || !make_plan(&p, N, hd)) return false;
   const int Rk = (N + 15) / 16 * 16;
+  if (Rk > 512) return false;
   return (backward ? bwd_smem(Rk, hd, 4) : fwd_smem(Rk, hd, 4)) <= static_cast<size_t>(kMaxSmem);
 }
 
@@ -527,9 +748,15 @@ static int launch_fwd_t(const void* qkv, void* o, float* lse, int B, int N, int 
       return OCTIC_ERR_CUDA;
     done = true;
   }
+  CUtensorMap tmKV, tmQ;
+  const int br = pick_box_rows(Rk);
+  int rc = make_map_rows(&tmKV, qkv, B, N, 3L * m.D, br);
+  if (rc) return rc;
+  rc = make_map_rows(&tmQ, qkv, B, N, 3L * m.D, 128);
+  if (rc) return rc;
   const float scale_log2 = kLog2e / sqrtf(static_cast<float>(HD));
-  attn_fwd_tc_kernel<HD, GRAN><<<B * H, 128, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(o),
-                                                        lse, N, H, m, scale_log2, cp);
+  attn_fwd_tc_kernel<HD, GRAN><<<B * H, kFwdThreads, smem, s>>>(tmKV, tmQ, static_cast<__nv_bfloat16*>(o), lse, N, H, m,
+                                                                scale_log2, cp, br);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 template <int HD, int GRAN>
@@ -543,10 +770,15 @@ static int launch_bwd_t(const void* qkv, const void* d_o, const float* lse, cons
       return OCTIC_ERR_CUDA;
     done = true;
   }
+  CUtensorMap tmQKV, tmDO;
+  const int br = pick_box_rows(Rk);
+  int rc = make_map_rows(&tmQKV, qkv, B, N, 3L * m.D, br);
+  if (rc) return rc;
+  rc = make_map_rows(&tmDO, d_o, B, N, m.D, br);
+  if (rc) return rc;
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
-  attn_bwd_tc_kernel<HD, GRAN><<<B * H, 256, smem, s>>>(static_cast<const __nv_bfloat16*>(qkv),
-                                                        static_cast<const __nv_bfloat16*>(d_o), lse, delta,
-                                                        static_cast<__nv_bfloat16*>(dqkv), N, H, m, scale, kLog2e * scale, cp);
+  attn_bwd_tc_kernel<HD, GRAN><<<B * H, kBwdThreads, smem, s>>>(tmQKV, tmDO, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
+                                                                N, H, m, scale, kLog2e * scale, cp, br);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
@@ -560,6 +792,7 @@ static int launch_bwd_t(const void* qkv, const void* d_o, const float* lse, cons
     default: return OCTIC_ERR_ARG;                                                     \
   }
 
+// m describes the OUTPUT rows (o / dqkv: packed octic or dense); the inputs qkv (and d_o) are head-major.
 int launch_attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, const HeadMap& m, cudaStream_t s) {
   ChunkPlan cp;
   if (!attn_tc_supported(N, m.hd, false) || !make_plan(&cp, N, m.hd)) return OCTIC_ERR_ARG;

@@ -120,6 +120,14 @@ static void fill_d8_groups(octic_gemm_desc* d, int Ci, int Co, bool has_bias) {
     G.a_col = 4 * Ci + r * 2 * Ci; G.k = 2 * Ci; G.b_map = 1; G.b_row = 0; G.n = 2 * Co;
     G.c_col = 4 * Co + r * 2 * Co; G.bias_off = -1;
   }
+  if (d->head_H > 0 && d->head_S > 0) {
+    // head vector [A1 | A2 | B1 | B2 | E row 0 | E row 1], c_h = Co / (S * H) columns per 1-D irrep
+    const int ch = Co / (d->head_S * d->head_H);
+    d->head_D = 8 * Co / d->head_S;
+    for (int g = 0; g < 4; ++g) d->head_off[g] = g * ch;
+    d->head_off[4] = 4 * ch;
+    d->head_off[5] = 6 * ch;
+  }
 }
 
 int octic_linear_d8_fwd(const void* x, int T, int Din, int Dout, const void* w1d, const void* wE_packed,
@@ -138,8 +146,8 @@ int octic_linear_d8_fwd(const void* x, int T, int Din, int Dout, const void* w1d
 }
 
 int octic_linear_d8_dgrad(const void* dy, int T, int Din, int Dout, const void* w1d_t, const void* wE_t, void* dx,
-                          void* stream) {
-  if (!dy || !w1d_t || !wE_t || !dx || Din % 8 || Dout % 8) return OCTIC_ERR_ARG;
+                          int head_H, void* stream) {
+  if (!dy || !w1d_t || !wE_t || !dx || Din % 8 || Dout % 8 || head_H < 0) return OCTIC_ERR_ARG;
   const int Ci = Din / 8, Co = Dout / 8;
   octic_gemm_desc d;
   memset(&d, 0, sizeof(d));
@@ -147,6 +155,9 @@ int octic_linear_d8_dgrad(const void* dy, int T, int Din, int Dout, const void* 
   d.b0 = w1d_t; d.b0_rows = 4L * Ci; d.b0_cols = roundup64(Co); d.b0_ld = roundup64(Co);
   d.b1 = wE_t; d.b1_rows = 2L * Ci; d.b1_cols = roundup64(2 * Co); d.b1_ld = roundup64(2 * Co);
   // roles of (Ci, Co) swap: contraction over the output features, result has Din columns
+  d.mode = OCTIC_EPI_BF16;
+  d.head_H = head_H;
+  d.head_S = 1;
   fill_d8_groups(&d, Co, Ci, false);
   const int ns[2] = {Ci, 2 * Ci};
   d.block_n = pick_block_n(ns, 2);

@@ -218,7 +218,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (cv1) b1 = __ldg(p.bias + G.bias_off + n0 + col + 1);
           }
           const uint32_t rd = stg + (rsel * 33 + cp) * 4;
-          const long o0 = static_cast<long>(row0 + rsel) * p.ldo + G.c_col + n0 + col;
+          int ocol = G.c_col + n0 + col;
+          if (MODE == EPI_BF16 && p.head_H > 0) {
+            // feature n = [s][h][j] of this group -> head-major column (pairs never straddle: c_g is even)
+            const int cg_all = G.n / p.head_S, cg = cg_all / p.head_H, n = n0 + col;
+            const int s_ = n / cg_all, rem = n - s_ * cg_all, h_ = rem / cg, j_ = rem - h_ * cg;
+            ocol = s_ * p.head_D + h_ * (p.head_D / p.head_H) + G.head_off + j_;
+          }
+          const long o0 = static_cast<long>(row0 + rsel) * p.ldo + ocol;
           __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out) + o0;
           __nv_bfloat16* pre = (MODE == EPI_GELU_BF16 && p.branch_out != nullptr)
                                    ? reinterpret_cast<__nv_bfloat16*>(p.branch_out) + o0 : nullptr;
@@ -586,7 +593,16 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
     G.bias_off = s.bias_off;
     G.tile_begin = tiles;
     tiles += G.n_tiles;
+    G.head_off = d->head_off[i];
+    if (d->head_H > 0) {
+      if (d->mode != EPI_BF16 || d->head_S < 1 || d->head_D % d->head_H || s.n % (d->head_S * d->head_H) ||
+          ((s.n / (d->head_S * d->head_H)) & 1) || (G.head_off & 1))
+        return OCTIC_ERR_ARG;
+    }
   }
+  p.head_H = d->head_H;
+  p.head_S = d->head_S;
+  p.head_D = d->head_D;
   p.tiles_per_m = tiles;
   const int b_stage_bytes = d->block_n * kBlockK * 2;
   int stages = (kMaxDynSmem - 1024 - (8 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);

@@ -12,7 +12,7 @@ namespace octic {
 enum { EPI_BF16 = OCTIC_EPI_BF16, EPI_RESID = OCTIC_EPI_RESID, EPI_F32 = OCTIC_EPI_F32, EPI_GELU_BF16 = OCTIC_EPI_GELU_BF16 };
 
 struct GemmGroup {
-  int a_col, k_blocks, b_map, b_row, n, n_tiles, c_col, bias_off, tile_begin;
+  int a_col, k_blocks, b_map, b_row, n, n_tiles, c_col, bias_off, tile_begin, head_off;
 };
 struct GemmParams {
   int M, num_groups, block_n, tiles_per_m, num_m_blocks, num_stages, mode;
@@ -29,6 +29,7 @@ struct GemmParams {
   void* branch_out;
   long ldb;
   int remap_group, remap_extra, remap_off;
+  int head_H, head_S, head_D;
 };
 
 struct WgradGroup {

@@ -224,6 +224,41 @@ __device__ __forceinline__ uint64_t desc_sw32_mn(uint32_t base, int R, int krow0
   return make_desc_sw32(base + krow0 * 32, R * 32);
 }
 
+// Lean issue path for MMA-issuing warps: every SWIZZLE_32B descriptor shares one high word, and moving an operand by
+// `bytes` inside shared memory adds bytes >> 4 to the low word (shared memory is < 256 KiB, the 14-bit address field
+// cannot carry).  Callers keep the low words in (warp-uniform) registers and pay one integer add per MMA.
+constexpr uint32_t kDescHiSw32 = (256u >> 4) | (1u << 14) | (kSwizzle32B << 29);
+__device__ __forceinline__ uint32_t desc_lo_sw32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ void umma_ss_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_lohi(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32, M = 128.
 //   [4,6) D fmt: 1 = f32   [7,10) A fmt: 1 = bf16   [10,13) B fmt: 1 = bf16
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4

@@ -58,17 +58,22 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 # LinearD8  (reference octic_vits/d8_layers.py:104-127)
 # ----------------------------------------------------------------------------------------------------------------
 class LinearD8Fn(torch.autograd.Function):
-    """y_bf16[T, Dout] = LinearD8(x_bf16[T, Din])."""
+    """y_bf16[T, Dout] = LinearD8(x_bf16[T, Din]).
+
+    head = (H, S) makes the GEMM epilogue write y head-major ([S][H][hd], head vector [A1|A2|B1|B2|E0|E1]) -- the qkv
+    operand of the tcgen05 attention (reference pack step d8_layers.py:632-641); backward still receives the packed
+    dqkv the attention backward scatters.  dgrad_heads = H makes backward emit dx head-major (proj feeding d_o)."""
 
     @staticmethod
-    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias):
+    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, head=(0, 0), dgrad_heads: int = 0):
         x = _c(x)
         pk = packed_d8((wA1, wA2, wB1, wB2, wE))
         y = torch.empty(x.shape[0], pk.dout, dtype=torch.bfloat16, device=x.device)
-        ops.linear_d8(x, pk, bias, EPI_BF16, out=y)
+        ops.linear_d8(x, pk, bias, EPI_BF16, out=y, head=head)
         ctx.save_for_backward(x)
         ctx.pk = pk
         ctx.has_bias = bias is not None
+        ctx.dgrad_heads = dgrad_heads
         return y
 
     @staticmethod
@@ -76,10 +81,10 @@ class LinearD8Fn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         pk = ctx.pk
         dy = _c(dy)
-        dx = ops.linear_d8_dgrad(dy, pk) if ctx.needs_input_grad[0] else None
+        dx = ops.linear_d8_dgrad(dy, pk, ctx.dgrad_heads) if ctx.needs_input_grad[0] else None
         dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
         db = ops.colsum_bf16(dy, pk.dout // 8) if (ctx.has_bias and ctx.needs_input_grad[6]) else None
-        return (dx, *dws, db)
+        return (dx, *dws, db, None, None)
 
 
 class LinearD8ResidualFn(torch.autograd.Function):
@@ -88,7 +93,7 @@ class LinearD8ResidualFn(torch.autograd.Function):
     (reference d8_layers.py:698-707, 759-776, 205-212, 249-282)."""
 
     @staticmethod
-    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, gamma, resid, row_scale, rows_per_sample):
+    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, gamma, resid, row_scale, rows_per_sample, dgrad_heads: int = 0):
         x = _c(x)
         pk = packed_d8((wA1, wA2, wB1, wB2, wE))
         need_branch = gamma is not None and ctx.needs_input_grad[7]
@@ -100,6 +105,7 @@ class LinearD8ResidualFn(torch.autograd.Function):
         ctx.pk = pk
         ctx.rows_per_sample = rows_per_sample
         ctx.has_bias = bias is not None
+        ctx.dgrad_heads = dgrad_heads
         return out
 
     @staticmethod
@@ -109,10 +115,10 @@ class LinearD8ResidualFn(torch.autograd.Function):
         dout = _c(dout)
         dy, dgamma, colsum = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
                                                 want_colsum=ctx.has_bias)
-        dx = ops.linear_d8_dgrad(dy, pk) if ctx.needs_input_grad[0] else None
+        dx = ops.linear_d8_dgrad(dy, pk, ctx.dgrad_heads) if ctx.needs_input_grad[0] else None
         dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
         db = colsum[: pk.dout // 8] if ctx.has_bias else None
-        return (dx, *dws, db, dgamma, dout, None, None)
+        return (dx, *dws, db, dgamma, dout, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -259,19 +265,22 @@ class GeluD8Fn(torch.autograd.Function):
 # attention core  (reference d8_layers.py:632-656 + F.scaled_dot_product_attention; deit/vit.py:36-50)
 # ----------------------------------------------------------------------------------------------------------------
 class AttentionFn(torch.autograd.Function):
+    """layout: ops.ATTN_DENSE, ops.ATTN_OCTIC_PACKED or ops.ATTN_OCTIC_HEADMAJOR (qkv and the incoming d_o head-major,
+    o and the outgoing dqkv packed octic rows)."""
+
     @staticmethod
-    def forward(ctx, qkv, B: int, N: int, H: int, hd: int, octic: bool):
+    def forward(ctx, qkv, B: int, N: int, H: int, hd: int, layout: int):
         qkv = _c(qkv)
-        o, lse = ops.attention_fwd(qkv, B, N, H, hd, octic, want_lse=any(ctx.needs_input_grad))
+        o, lse = ops.attention_fwd(qkv, B, N, H, hd, layout, want_lse=any(ctx.needs_input_grad))
         ctx.save_for_backward(qkv, o, lse)
-        ctx.cfg = (B, N, H, hd, octic)
+        ctx.cfg = (B, N, H, hd, layout)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         qkv, o, lse = ctx.saved_tensors
-        B, N, H, hd, octic = ctx.cfg
-        return ops.attention_bwd(qkv, o, _c(d_o), lse, B, N, H, hd, octic), None, None, None, None, None
+        B, N, H, hd, layout = ctx.cfg
+        return ops.attention_bwd(qkv, o, _c(d_o), lse, B, N, H, hd, layout), None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------

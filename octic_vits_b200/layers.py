@@ -100,9 +100,9 @@ class LinearD8(nn.Module):
         OF.require_cuda(x)
         return OF.unpack_five(self.forward_packed(x))
 
-    def forward_packed(self, x: Tensor) -> Tensor:
-        """bf16 (or fp32, cast here) [.., Din] -> bf16 [.., Dout]"""
-        y = OF.LinearD8Fn.apply(_as_bf16(_rows(x)), *self.weights(), self.lin_A1.bias)
+    def forward_packed(self, x: Tensor, head=(0, 0), dgrad_heads: int = 0) -> Tensor:
+        """bf16 (or fp32, cast here) [.., Din] -> bf16 [.., Dout].  head / dgrad_heads: see OF.LinearD8Fn (attention)."""
+        y = OF.LinearD8Fn.apply(_as_bf16(_rows(x)), *self.weights(), self.lin_A1.bias, head, dgrad_heads)
         return y.view(*x.shape[:-1], self.output_channels)
 
     def extra_repr(self) -> str:
@@ -274,28 +274,43 @@ class AttentionD8(nn.Module):
         self.proj_drop = DropoutD8(proj_drop)
         self.rope = rope
 
+    def head_major(self, N: int) -> bool:
+        """True when the tcgen05 attention kernels cover (N, head_dim): qkv then leaves its GEMM head-major and the
+        proj dgrad returns d_o head-major, so q, k, v, dO reach the kernels by TMA (no gather, no copies)."""
+        H = self.num_heads
+        return (self.dim // (8 * H)) % 2 == 0 and OF.ops.attention_headmajor_ok(N, self.dim // H)
+
     def core_packed(self, x: Tensor) -> Tensor:
-        """packed bf16/fp32 [B, N, D] -> attention output before `proj`, packed bf16 [B, N, D]"""
+        """packed bf16/fp32 [B, N, D] -> attention output before `proj`, packed bf16 [B, N, D].  When head_major(N),
+        the consumer (`proj`) must be called with dgrad_heads=num_heads."""
         B, N, D = x.shape
-        qkv = self.qkv.forward_packed(x)
-        o = OF.AttentionFn.apply(_rows(qkv), B, N, self.num_heads, D // self.num_heads, True)
+        H = self.num_heads
+        if self.head_major(N):
+            qkv = self.qkv.forward_packed(x, head=(H, 3))
+            o = OF.AttentionFn.apply(_rows(qkv), B, N, H, D // H, OF.ops.ATTN_OCTIC_HEADMAJOR)
+        else:
+            qkv = self.qkv.forward_packed(x)
+            o = OF.AttentionFn.apply(_rows(qkv), B, N, H, D // H, OF.ops.ATTN_OCTIC_PACKED)
         return o.view(B, N, D)
 
     def forward(self, xs):
         x = OF.pack_five(xs)
         OF.require_cuda(x)
-        y = self.proj.forward_packed(self.core_packed(x))
+        hm = self.head_major(x.shape[1])
+        y = self.proj.forward_packed(self.core_packed(x), dgrad_heads=self.num_heads if hm else 0)
         return self.proj_drop(OF.unpack_five(y))
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # octic blocks
 # ----------------------------------------------------------------------------------------------------------------
-def _branch_residual(lin: LinearD8, a: Tensor, scale_mod, x: Tensor, row_scale: Optional[Tensor]) -> Tensor:
+def _branch_residual(lin: LinearD8, a: Tensor, scale_mod, x: Tensor, row_scale: Optional[Tensor],
+                     dgrad_heads: int = 0) -> Tensor:
     """x + row_scale * gamma * lin(a) with everything after the GEMM fused into its epilogue."""
     B, N, D = x.shape
     gamma = scale_mod.packed_alpha() if scale_mod is not None else None
-    out = OF.LinearD8ResidualFn.apply(_as_bf16(_rows(a)), *lin.weights(), lin.lin_A1.bias, gamma, _rows(x), row_scale, N)
+    out = OF.LinearD8ResidualFn.apply(_as_bf16(_rows(a)), *lin.weights(), lin.lin_A1.bias, gamma, _rows(x), row_scale, N,
+                                      dgrad_heads)
     return out.view(B, N, D)
 
 
@@ -327,7 +342,8 @@ class _OcticBlockBase(nn.Module):
         s2 = self._dp(2).sample(B, x.device) if isinstance(self._dp(2), DropPathD8) else None
         xn, x = self.norm1.forward_packed(x, passthrough=True)
         a = self.attn.core_packed(xn)
-        x = _branch_residual(self.attn.proj, a, ls1, x, s1)
+        x = _branch_residual(self.attn.proj, a, ls1, x, s1,
+                             dgrad_heads=self.attn.num_heads if self.attn.head_major(x.shape[1]) else 0)
         xn, x = self.norm2.forward_packed(x, passthrough=True)
         h = self.mlp.fc1.forward_packed(xn)
         h = self.mlp.act.forward_packed(h)
@@ -622,7 +638,7 @@ class Attention(nn.Module):
     def core_packed(self, x: Tensor) -> Tensor:
         B, N, D = x.shape
         qkv = OF.LinearFn.apply(_as_bf16(_rows(x)), self.qkv.weight, self.qkv.bias, False, False)
-        return OF.AttentionFn.apply(qkv, B, N, self.num_heads, D // self.num_heads, False).view(B, N, D)
+        return OF.AttentionFn.apply(qkv, B, N, self.num_heads, D // self.num_heads, OF.ops.ATTN_DENSE).view(B, N, D)
 
     def forward(self, x):
         OF.require_cuda(x)

@@ -102,7 +102,7 @@ def pack_linear(w: torch.Tensor, need_t: bool = True) -> PackedDense:
 # GEMM front ends
 # ----------------------------------------------------------------------------------------------------------------
 def _epilogue_desc(mode: int, out=None, gamma=None, resid_in=None, resid_out=None, row_scale=None,
-                   rows_per_sample: int = 1, branch_out=None, remap=(0, 0, 0)) -> GemmDesc:
+                   rows_per_sample: int = 1, branch_out=None, remap=(0, 0, 0), head=(0, 0)) -> GemmDesc:
     d = GemmDesc()
     d.mode = mode
     if out is not None:
@@ -121,6 +121,7 @@ def _epilogue_desc(mode: int, out=None, gamma=None, resid_in=None, resid_out=Non
         d.branch_out = branch_out.data_ptr()
         d.ldb = branch_out.stride(0)
     d.remap_group, d.remap_extra, d.remap_off = remap
+    d.head_H, d.head_S = head      # (heads, S): EPI_BF16 output rows head-major [S][H][hd] (see octic_b200.h)
     return d
 
 
@@ -143,13 +144,15 @@ def linear_d8(x: torch.Tensor, pk: PackedD8, bias: Optional[torch.Tensor], mode:
          _ptr(bias), C.byref(d), _stream(), flops=2.0 * x.shape[0] * pk.din * pk.dout * 3 / 16)
 
 
-def linear_d8_dgrad(dy: torch.Tensor, pk: PackedD8) -> torch.Tensor:
+def linear_d8_dgrad(dy: torch.Tensor, pk: PackedD8, head_H: int = 0) -> torch.Tensor:
+    """dx = LinearD8^T(dy); head_H > 0 writes dx rows head-major (the d_o operand of the tcgen05 attention backward)."""
     _req(dy, torch.bfloat16, "dy")
     if dy.shape[1] != pk.dout or dy.stride(0) != pk.dout:
         raise _lib.OcticError("dy must be a dense [T, Dout] bf16 matrix")
     dx = torch.empty(dy.shape[0], pk.din, dtype=torch.bfloat16, device=dy.device)
     call("octic_linear_d8_dgrad", dy.data_ptr(), dy.shape[0], pk.din, pk.dout, pk.w1d_t.data_ptr(),
-         pk.wE_t.data_ptr(), dx.data_ptr(), _stream(), flops=2.0 * dy.shape[0] * pk.din * pk.dout * 3 / 16)
+         pk.wE_t.data_ptr(), dx.data_ptr(), int(head_H), _stream(),
+         flops=2.0 * dy.shape[0] * pk.din * pk.dout * 3 / 16)
     return dx
 
 
@@ -286,18 +289,27 @@ def colsum_bf16(x: torch.Tensor, n_cols: Optional[int] = None) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------
 # attention
 # ----------------------------------------------------------------------------------------------------------------
-def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, octic: bool, want_lse: bool = True):
+ATTN_DENSE, ATTN_OCTIC_PACKED, ATTN_OCTIC_HEADMAJOR = 0, 1, 2
+
+
+def attention_headmajor_ok(N: int, hd: int, backward: bool = True) -> bool:
+    """True when the tcgen05 attention kernels (head-major q, k, v by TMA) cover this sequence length / head dim."""
+    return bool(_lib.load().octic_attention_headmajor_supported(int(N), int(hd), int(backward)))
+
+
+def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, layout: int, want_lse: bool = True):
     _req(qkv, torch.bfloat16, "qkv")
     D = H * hd
     if tuple(qkv.shape) != (B * N, 3 * D) or not qkv.is_contiguous():
         raise _lib.OcticError(f"qkv must be contiguous [B*N, 3*D] = [{B * N}, {3 * D}], got {tuple(qkv.shape)}")
     o = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
     lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device) if want_lse else None
-    call("octic_attention_fwd", qkv.data_ptr(), o.data_ptr(), _ptr(lse), B, N, H, hd, int(octic), _stream())
+    call("octic_attention_fwd", qkv.data_ptr(), o.data_ptr(), _ptr(lse), B, N, H, hd, int(layout), _stream(),
+         flops=4.0 * B * H * N * N * hd)
     return o, lse
 
 
-def attention_bwd(qkv, o, d_o, lse, B: int, N: int, H: int, hd: int, octic: bool) -> torch.Tensor:
+def attention_bwd(qkv, o, d_o, lse, B: int, N: int, H: int, hd: int, layout: int) -> torch.Tensor:
     for t, nm in ((qkv, "qkv"), (o, "o"), (d_o, "d_o")):
         _req(t, torch.bfloat16, nm)
         if not t.is_contiguous():
@@ -305,7 +317,7 @@ def attention_bwd(qkv, o, d_o, lse, B: int, N: int, H: int, hd: int, octic: bool
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
     call("octic_attention_bwd", qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-         dqkv.data_ptr(), B, N, H, hd, int(octic), _stream())
+         dqkv.data_ptr(), B, N, H, hd, int(layout), _stream(), flops=10.0 * B * H * N * N * hd)
     return dqkv
 
 

@@ -32,7 +32,8 @@ def test_library_exports_every_header_symbol(lib):
     assert len(names) >= 25
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/octic_b200.h but not exported"
-    bound = set(_lib.SIGNATURES) | {"octic_strerror", "octic_version", "octic_device_ok"}
+    bound = set(_lib.SIGNATURES) | {"octic_strerror", "octic_version", "octic_device_ok",
+                                      "octic_attention_headmajor_supported"}
     assert set(names) == bound, set(names) ^ bound
     assert lib.octic_version() >= 100
     assert lib.octic_strerror(-2).decode().startswith("pointer or leading dimension")

@@ -14,9 +14,11 @@ pytestmark = pytest.mark.gpu
 if torch.cuda.is_available():
     from octic_vits_b200 import ops
     from octic_vits_b200._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID
+from octic_vits_b200._lib import OcticError
 from oracle import octic_oracle as O
 
 DEV = "cuda"
+ATTN_DENSE, ATTN_OCTIC_PACKED, ATTN_OCTIC_HEADMAJOR = 0, 1, 2     # include/octic_b200.h OCTIC_ATTN_*
 
 
 def setup_module(module):
@@ -317,20 +319,44 @@ def _attn_reference(qkv_rows, B, N, H, hd, octic):
     return o.transpose(1, 2).reshape(B * N, D)
 
 
-@pytest.mark.parametrize("octic", [True, False])
-@pytest.mark.parametrize("B,N,H,hd", [(2, 257, 16, 80), (3, 197, 6, 64), (2, 17, 2, 64), (1, 261, 16, 64), (2, 64, 4, 32),
-                                      (2, 129, 2, 80), (2, 128, 2, 96), (1, 400, 2, 80), (1, 150, 2, 128), (3, 65, 2, 64)])
-def test_attention(B, N, H, hd, octic):
-    """tcgen05 path (attention_tc.cu) inside its envelope; N = 400 backward and hd = 128 / N = 150 ... exercise chunk
-    plans with 1..5 chunks, partial last tiles, and (N = 400 backward) the mma.sync fallback."""
+def _o_head_perm(H, hd):
+    """perm[c] = head-major column (h*hd + j) that packed octic column c of an attention-output row holds."""
+    idx = torch.arange(H * hd, dtype=torch.float32).reshape(1, H, 1, hd)
+    return O.pack_rows(O.attention_unpack_d8(idx)).reshape(-1).long()
+
+
+def _qkv_head_major(qkv_rows, B, N, H, hd):
+    """packed LinearD8 qkv rows -> head-major [B*N, 3, H, hd] rows (what the GEMM head remap writes)."""
+    q, k, v = O.attention_heads_d8(O.unpack_rows(qkv_rows.float().reshape(B, N, -1)), H)
+    return torch.stack((q, k, v), 0).permute(1, 3, 0, 2, 4).reshape(B * N, 3 * H * hd)
+
+
+ATTN_SHAPES = [(2, 257, 16, 80), (3, 197, 6, 64), (2, 17, 2, 64), (1, 261, 16, 64), (2, 64, 4, 32), (2, 129, 2, 80),
+               (2, 128, 2, 96), (1, 400, 2, 80), (1, 150, 2, 128), (3, 65, 2, 64), (5, 1, 2, 64), (2, 272, 2, 80)]
+
+
+@pytest.mark.parametrize("layout", [ATTN_DENSE, ATTN_OCTIC_PACKED, ATTN_OCTIC_HEADMAJOR])
+@pytest.mark.parametrize("B,N,H,hd", ATTN_SHAPES)
+def test_attention(B, N, H, hd, layout):
+    """Dense and head-major octic layouts run the tcgen05 kernels (attention_tc.cu) inside their envelope -- chunk
+    plans with 1..5 chunks, partial last tiles, N = 1 -- and the mma.sync kernels outside it (N = 400 backward,
+    hd = 128 backward); the packed octic layout always runs the mma.sync kernels."""
     D = H * hd
+    octic = layout != ATTN_DENSE
+    if layout == ATTN_OCTIC_HEADMAJOR and not ops.attention_headmajor_ok(N, hd, True):
+        pytest.skip("outside the envelope of the tcgen05 kernels: the module falls back to the packed layout")
     g = torch.Generator().manual_seed(N + hd)
     qkv = bf(torch.randn(B * N, 3 * D, generator=g) * 1.5).to(DEV)
     d_o = bf(torch.randn(B * N, D, generator=g)).to(DEV)
     qin = qkv.float().clone().requires_grad_(True)
     want = _attn_reference(qin, B, N, H, hd, octic)
     (want * d_o.float()).sum().backward()
-    o, lse = ops.attention_fwd(qkv, B, N, H, hd, octic)
+    qkv_in, d_o_in = qkv, d_o
+    if layout == ATTN_OCTIC_HEADMAJOR:
+        qkv_in = bf(_qkv_head_major(qkv, B, N, H, hd)).contiguous()
+        d_o_in = torch.empty_like(d_o)
+        d_o_in[:, _o_head_perm(H, hd).to(DEV)] = d_o
+    o, lse = ops.attention_fwd(qkv_in, B, N, H, hd, layout)
     assert_close(o, want.detach(), rtol=2e-2, atol=2e-2)
     # log-sum-exp of the scaled scores (natural log), [B, H, N]
     q3 = qkv.float().reshape(B, N, 3 * D)
@@ -341,8 +367,41 @@ def test_attention(B, N, H, hd, octic):
         qh, kh = t[0], t[1]
     want_lse = torch.logsumexp(qh @ kh.transpose(-1, -2) / hd ** 0.5, dim=-1)
     assert_close(lse, want_lse, rtol=1e-3, atol=1e-3)
-    dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, N, H, hd, octic)
+    dqkv = ops.attention_bwd(qkv_in, o, d_o_in, lse, B, N, H, hd, layout)
     assert_close(dqkv, qin.grad, rtol=3e-2, atol=3e-2)
+
+
+def test_attention_headmajor_rejects_unsupported():
+    """The head-major layout exists only on the tcgen05 path: outside its envelope the C ABI refuses (no silent gather)."""
+    B, N, H, hd = 1, 700, 2, 64
+    assert not ops.attention_headmajor_ok(N, hd, False)
+    qkv = torch.zeros(B * N, 3 * H * hd, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(OcticError):
+        ops.attention_fwd(qkv, B, N, H, hd, ATTN_OCTIC_HEADMAJOR)
+
+
+@pytest.mark.parametrize("B,N,H,hd", [(2, 257, 16, 80), (3, 197, 6, 64), (1, 33, 2, 32)])
+def test_linear_d8_head_remap(B, N, H, hd):
+    """qkv LinearD8 with head=(H, 3) writes head-major rows (reference pack step d8_layers.py:632-641 fused into the
+    GEMM epilogue); dgrad with head_H writes the proj input gradient head-major.  Same values, permuted columns."""
+    D = H * hd
+    xs = rnd5(B, N, D // 8, seed=5)
+    w = d8_weights(D, 3 * D)
+    x = bf(O.pack_rows(xs)).reshape(B * N, D).contiguous()
+    pk = pack_d8(w)
+    y_packed = torch.empty(B * N, 3 * D, dtype=torch.bfloat16, device=DEV)
+    ops.linear_d8(x, pk, w["lin_A1.bias"], EPI_BF16, out=y_packed)
+    y_head = torch.empty_like(y_packed)
+    ops.linear_d8(x, pk, w["lin_A1.bias"], EPI_BF16, out=y_head, head=(H, 3))
+    assert torch.equal(y_head, bf(_qkv_head_major(y_packed, B, N, H, hd)))
+    wp = d8_weights(D, D)
+    pkp = pack_d8(wp)
+    dy = bf(O.pack_rows(rnd5(B, N, D // 8, seed=6))).reshape(B * N, D).contiguous()
+    dx_packed = ops.linear_d8_dgrad(dy, pkp)
+    dx_head = ops.linear_d8_dgrad(dy, pkp, head_H=H)
+    want = torch.empty_like(dx_packed)
+    want[:, _o_head_perm(H, hd).to(DEV)] = dx_packed
+    assert torch.equal(dx_head, want)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,63 @@
+// In-kernel timeline of the tcgen05 attention forward kernel (CTA 0): build with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --use_fast_math -DOCTIC_ATTN_TRACE \
+//        -o build/attn_trace tools/attn_trace.cu -lcuda
+// and run on a B200:  build/attn_trace [B]   (prints cycle deltas between events of the control and math threads)
+#include "../octic_vits_b200/csrc/attention_tc.cu"
+#include <cstdio>
+#include <vector>
+
+using namespace octic;
+
+int main(int argc, char** argv) {
+  const int B = argc > 1 ? atoi(argv[1]) : 20, N = 257, H = 16, hd = 80, D = H * hd;
+  const bool bwd = argc > 2 && argv[2][0] == 'b';
+  const int octic = argc > 3 ? atoi(argv[3]) : 0;
+  const size_t nq = static_cast<size_t>(B) * N * 3 * D;
+  std::vector<__nv_bfloat16> h(nq);
+  unsigned s = 12345u;
+  for (size_t i = 0; i < nq; ++i) {
+    s = s * 1664525u + 1013904223u;
+    h[i] = __float2bfloat16((static_cast<float>(s >> 8) / 16777216.0f - 0.5f) * 3.0f);
+  }
+  __nv_bfloat16 *qkv, *o, *dqkv;
+  float *lse, *delta;
+  cudaMalloc(&dqkv, nq * 2);
+  cudaMalloc(&delta, static_cast<size_t>(B) * H * N * 4);
+  cudaMemset(delta, 0, static_cast<size_t>(B) * H * N * 4);
+  cudaMalloc(&qkv, nq * 2);
+  cudaMalloc(&o, static_cast<size_t>(B) * N * D * 2);
+  cudaMalloc(&lse, static_cast<size_t>(B) * H * N * 4);
+  cudaMemcpy(qkv, h.data(), nq * 2, cudaMemcpyHostToDevice);
+  HeadMap m;
+  m.octic = octic; m.hd = hd; m.D = D; m.C = D / 8; m.ch = hd / 8;
+  for (int it = 0; it < 3; ++it) {
+    int zero[2] = {0, 0};
+    cudaMemcpyToSymbol(g_trace_n, zero, sizeof(zero));
+    if (bwd && it == 0) {
+      launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
+      cudaDeviceSynchronize();
+      cudaMemcpyToSymbol(g_trace_n, zero, sizeof(zero));
+    }
+    int rc = bwd ? launch_attn_bwd_tc(qkv, o /* stands in for dO */, lse, delta, dqkv, B, N, H, m, 0)
+                 : launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (rc || e != cudaSuccess) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
+  }
+  std::vector<long long> tr(2 * 2048);
+  int n[2];
+  cudaMemcpyFromSymbol(tr.data(), g_trace, sizeof(long long) * 2 * 2048);
+  cudaMemcpyFromSymbol(n, g_trace_n, sizeof(n));
+  long long t0 = tr[2048] >> 8;
+  for (int slot = 0; slot < 2; ++slot) {
+    printf("slot %d: %d events (id:cycles since first math event, delta)\n", slot, n[slot]);
+    long long prev = t0;
+    for (int i = 0; i < n[slot] && i < 2048; ++i) {
+      const long long v = tr[slot * 2048 + i], t = v >> 8;
+      printf("  %lld:%lld(+%lld)", v & 255, t - t0, t - prev);
+      prev = t;
+      if (i % 6 == 5) printf("\n");
+    }
+    printf("\n");
+  }
+  return 0;
+}

@@ -21,7 +21,9 @@ ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--only", default="")
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--attn-layout", type=int, default=2, help="0 dense, 1 packed octic (mma.sync), 2 head-major octic (tcgen05)")
 args = ap.parse_args()
+ATTN_LAYOUT = args.attn_layout
 
 peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {
     "hbm_gbs": 6650.0, "bf16_tflops": 1590.0}
@@ -60,7 +62,7 @@ res_out = torch.empty(T, D, device=dev)
 branch = torch.empty(T, D, dtype=bf, device=dev)
 _, stats8 = ops.layernorm_fwd(x32, alpha, beta, 1e-5, True)
 _, stats2 = ops.layernorm_fwd(x32, alpha, alpha, 1e-6, False)
-o_attn, lse = ops.attention_fwd(qkv, B, N, H, hd, True)
+o_attn, lse = ops.attention_fwd(qkv, B, N, H, hd, ATTN_LAYOUT)
 oct_f = 2.0 * T * D * 3 / 16   # x Dout
 
 CASES = {
@@ -74,8 +76,8 @@ CASES = {
     "gelu_bwd": (lambda: ops.gelu_bwd(g4, h4), T * 4 * D * 6, 0),
     "layerscale_bwd": (lambda: ops.layerscale_bwd(dres, dyb, gamma, None, N), T * D * 8, 0),
     "colsum": (lambda: ops.colsum_bf16(h4, 4 * C), T * 4 * C * 2, 0),
-    "attn_fwd": (lambda: ops.attention_fwd(qkv, B, N, H, hd, True), T * D * 8, 4.0 * B * H * N * N * hd),
-    "attn_bwd": (lambda: ops.attention_bwd(qkv, o_attn, dyb, lse, B, N, H, hd, True), T * D * 18, 10.0 * B * H * N * N * hd),
+    "attn_fwd": (lambda: ops.attention_fwd(qkv, B, N, H, hd, ATTN_LAYOUT), T * D * 8, 4.0 * B * H * N * N * hd),
+    "attn_bwd": (lambda: ops.attention_bwd(qkv, o_attn, dyb, lse, B, N, H, hd, ATTN_LAYOUT), T * D * 18, 10.0 * B * H * N * N * hd),
     "d8_qkv": (lambda: ops.linear_d8(xb, pk_qkv, None, EPI_BF16, out=out3), T * D * 8, oct_f * 3 * D),
     "d8_proj_resid": (lambda: ops.linear_d8(xb, pk_proj, None, EPI_RESID, gamma=gamma, resid_in=x32, resid_out=res_out,
                                             branch_out=branch), T * D * (2 + 4 + 4 + 2), oct_f * D),
