@@ -23,10 +23,18 @@ __device__ __forceinline__ float erf_as(float x) {
 }
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erf_as(x * kInvSqrt2)); }
 // d/dx gelu(x) = Phi(x) + x * phi(x)      (reference octic_vits/d8_gelu.py:16-26)
+// The erf approximation needs exp(-(x/sqrt2)^2) = exp(-x^2/2), the same exponential as the pdf: one MUFU.EX2 and
+// one MUFU.RCP per element in total (the kernels using this are otherwise co-bound by the MUFU pipe).
 __device__ __forceinline__ float gelu_grad_f(float x) {
-  const float cdf = 0.5f * (1.0f + erf_as(x * kInvSqrt2));
-  const float pdf = kInvSqrt2Pi * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  const float z = fabsf(x) * kInvSqrt2;
+  const float e = __expf(-0.5f * x * x);
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));   // MUFU.RCP
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfv = copysignf(1.0f - poly * t * e, x);
+  return fmaf(x, kInvSqrt2Pi * e, 0.5f * (1.0f + erfv));
 }
 
 // Isotypic -> regular (inverse D8 Fourier transform), reference octic_vits/d8_utils.py:276-303.
@@ -255,6 +263,192 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
   const int nchunks = D / 4;
   const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
   const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  // per-lane chunk geometry is token independent: the segment id of each of the lane's chunks is packed 3 bits apiece
+  // into one register (7 = chunk past the row), so the row loads below issue back to back with no index math between
+  unsigned long long segpack = 0;
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) {
+    const int ch = lane + 32 * j;
+    segpack |= static_cast<unsigned long long>(ch < nchunks ? seg_of<D8>(ch * 4, C) : 7) << (3 * j);
+  }
+  static_assert(NCH <= 21, "segpack holds 21 chunks");
+  for (long t = warp_global; t < T_rows; t += nwarps) {
+    float v[NCH][4];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int ch = min(lane + 32 * j, nchunks - 1);      // clamped: the load is unconditional, the value is masked
+      Vec<float, 4>::load(x + t * ldx + ch * 4, v[j]);
+    }
+    int seg[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) seg[j] = static_cast<int>((segpack >> (3 * j)) & 7ull);
+    float sum[NSEG];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) sum[s] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const float s4 = (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) sum[s] += (seg[j] == s) ? s4 : 0.f;
+    }
+    float mean[NSEG], var[NSEG];
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+      const float n = D8 ? (s < 4 ? C : 2 * C) : D;
+      mean[s] = warp_sum(sum[s]) / n;
+      var[s] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float mu = 0.f;
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) mu = (seg[j] == s) ? mean[s] : mu;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[j][i] -= mu; q += v[j][i] * v[j][i]; }
+#pragma unroll
+      for (int s = 0; s < NSEG; ++s) var[s] += (seg[j] == s) ? q : 0.f;
+    }
+    float S = 0.f;
+#pragma unroll
+    for (int s = 0; s < NSEG; ++s) {
+      const float n = D8 ? (s < 4 ? C : 2 * C) : D;
+      const float w = D8 ? (s < 4 ? 1.0f : 0.5f) : 1.0f;
+      S += w * (warp_sum(var[s]) / n);
+    }
+    // D8: std = (sqrt2/4) * sqrt(S + eps)  ->  rstd = sqrt(8 / (S + eps));   plain: rstd = 1/sqrt(var + eps)
+    const float rstd = D8 ? sqrtf(8.0f / (S + eps)) : rsqrtf(S + eps);
+    if (stats != nullptr && lane == 0) {
+      if (D8) {
+#pragma unroll
+        for (int s = 0; s < NSEG; ++s) stats[t * 8 + s] = mean[s];
+        stats[t * 8 + 6] = rstd;
+      } else {
+        stats[t * 2] = mean[0];
+        stats[t * 2 + 1] = rstd;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      if (seg[j] != 7) {
+        const int col = (lane + 32 * j) * 4;
+        float a[4], o[4];
+        Vec<float, 4>::load(alpha + col, a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] = v[j][i] * rstd * a[i];
+        if (beta != nullptr && (!D8 || col < C)) {
+          float b[4];
+          Vec<float, 4>::load(beta + col, b);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) o[i] += b[i];
+        }
+        Vec<TY, 4>::store(y + t * ldy + col, o);
+      }
+    }
+  }
+}
+
+// LayerNormD8 forward, lane-contiguous fast path (C % 16 == 0: ViT-S/L/H widths 48, 128, 160).  One warp per token;
+// lane l owns the CPL = C/16 consecutive float4 chunks [l*CPL, (l+1)*CPL), which all lie inside ONE irrep segment
+// (lanes 0-3 A1, 4-7 A2, 8-11 B1, 12-15 B2, 16-23 E row 0, 24-31 E row 1).  The six means / variances of
+// d8_layers.py:166-186 are therefore plain group reductions (two or three xor-shuffles) with no per-chunk segment
+// selection: ~5x fewer instructions and half the registers of the generic kernel.
+template <typename TY, int CPL>
+__global__ void __launch_bounds__(256) layernorm_d8_fwd_lc_kernel(const float* __restrict__ x, long ldx,
+                                                                  const float* __restrict__ alpha,
+                                                                  const float* __restrict__ beta, float eps,
+                                                                  TY* __restrict__ y, long ldy, float* __restrict__ stats,
+                                                                  long T_rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  const int col0 = lane * CPL * 4;
+  const bool is_e = lane >= 16;
+  const float inv_n = 1.0f / static_cast<float>(is_e ? 2 * C : C);
+  for (long t = warp_global; t < T_rows; t += nwarps) {
+    float v[CPL][4];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) Vec<float, 4>::load(x + t * ldx + col0 + 4 * j, v[j]);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) { s0 += v[j][0] + v[j][1]; s1 += v[j][2] + v[j][3]; }
+    float sm = s0 + s1;
+    sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+    sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+    {
+      const float o4 = __shfl_xor_sync(0xffffffffu, sm, 4);
+      if (is_e) sm += o4;
+    }
+    const float mean = sm * inv_n;
+    float q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[j][i] -= mean;
+      q0 += v[j][0] * v[j][0] + v[j][1] * v[j][1];
+      q1 += v[j][2] * v[j][2] + v[j][3] * v[j][3];
+    }
+    float q = q0 + q1;
+    q += __shfl_xor_sync(0xffffffffu, q, 1);
+    q += __shfl_xor_sync(0xffffffffu, q, 2);
+    {
+      const float o4 = __shfl_xor_sync(0xffffffffu, q, 4);
+      if (is_e) q += o4;
+    }
+    const float var = q * inv_n;
+    // S = var_A1 + var_A2 + var_B1 + var_B2 + (var_E0 + var_E1) / 2
+    const float S = (__shfl_sync(0xffffffffu, var, 0) + __shfl_sync(0xffffffffu, var, 4)) +
+                    (__shfl_sync(0xffffffffu, var, 8) + __shfl_sync(0xffffffffu, var, 12)) +
+                    0.5f * (__shfl_sync(0xffffffffu, var, 16) + __shfl_sync(0xffffffffu, var, 24));
+    const float rstd = sqrtf(8.0f / (S + eps));       // std = (sqrt2/4) * sqrt(S + eps)
+    if (stats != nullptr) {
+      if (lane < 16 && (lane & 3) == 0) stats[t * 8 + (lane >> 2)] = mean;
+      if (lane == 16 || lane == 24) stats[t * 8 + 4 + ((lane - 16) >> 3)] = mean;
+      if (lane == 0) stats[t * 8 + 6] = rstd;
+    }
+    float o[CPL][4];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      float a[4];
+      Vec<float, 4>::load(alpha + col0 + 4 * j, a);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[j][i] = v[j][i] * rstd * a[i];
+      if (beta != nullptr && lane < 4) {              // lanes 0-3 hold exactly the A1 columns [0, C)
+        float bb[4];
+        Vec<float, 4>::load(beta + col0 + 4 * j, bb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[j][i] += bb[i];
+      }
+    }
+    TY* yr = y + t * ldy + col0;
+    if constexpr (sizeof(TY) == 2 && (CPL % 2) == 0) {
+#pragma unroll
+      for (int j = 0; j < CPL; j += 2) {               // 16-byte stores: two chunks = 8 bf16
+        float w8[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { w8[i] = o[j][i]; w8[4 + i] = o[j + 1 < CPL ? j + 1 : j][i]; }
+        Vec<TY, 8>::store(yr + 4 * j, w8);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) Vec<TY, 4>::store(yr + 4 * j, o[j]);
+    }
+  }
+}
+
+// Generic one-warp-per-token kernel (any segment layout; used for nn.LayerNorm, where it needs only 80 registers).
+template <typename TY, bool D8, int NCH>
+__global__ void __launch_bounds__(256) layernorm_fwd_plain_kernel(const float* __restrict__ x, long ldx,
+                                                            const float* __restrict__ alpha,
+                                                            const float* __restrict__ beta, float eps,
+                                                            TY* __restrict__ y, long ldy, float* __restrict__ stats,
+                                                            long T_rows, int D) {
+  constexpr int NSEG = D8 ? 6 : 1;
+  const int lane = threadIdx.x & 31;
+  const int C = D / 8;
+  const int nchunks = D / 4;
+  const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
   for (long t = warp_global; t < T_rows; t += nwarps) {
     float v[NCH][4];
     int seg[NCH];
@@ -341,7 +535,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 // flight together.
 constexpr int kLnG = 4;   // tokens per reduction round
 template <typename TDY, bool D8>
-__global__ void __launch_bounds__(512) layernorm_bwd_kernel(const TDY* __restrict__ dy, long lddy,
+__global__ void __maxnreg__(96) layernorm_bwd_kernel(const TDY* __restrict__ dy, long lddy,
                                                              const float* __restrict__ x, long ldx,
                                                              const float* __restrict__ stats,
                                                              const float* __restrict__ alpha,
@@ -369,7 +563,13 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const TDY* __restric
   (void)tokens_per_block;
   const long t1 = T_rows;
   for (long tb = static_cast<long>(blockIdx.x) * kLnG; tb < t1; tb += static_cast<long>(gridDim.x) * kLnG) {
-    float yh[kLnG][4], dyh[kLnG][4], rstd[kLnG], q[kLnG], s4[kLnG];
+    float yh[kLnG][4], dyh[kLnG][4], rstd[kLnG], q[kLnG], s4[kLnG], din[kLnG][4];
+    // the skip-gradient rows are fetched together with x / dy (one DRAM round trip per round, not two)
+#pragma unroll
+    for (int u = 0; u < kLnG; ++u) {
+      if (dx_in != nullptr) Vec<float, 4>::load(dx_in + min(tb + u, t1 - 1) * lddx + (active ? col : 0), din[u]);
+      else { din[u][0] = 0.f; din[u][1] = 0.f; din[u][2] = 0.f; din[u][3] = 0.f; }
+    }
 #pragma unroll
     for (int u = 0; u < kLnG; ++u) {
       const long t = tb + u;
@@ -436,12 +636,8 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const TDY* __restric
         float o[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] = rstd[u] * (dyh[u][i] - m - coef * yh[u][i] * Q);
-        if (dx_in != nullptr) {
-          float b[4];
-          Vec<float, 4>::load(dx_in + t * lddx + col, b);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) o[i] += b[i];
-        }
+        for (int i = 0; i < 4; ++i) o[i] += din[u][i];
         Vec<float, 4>::store(dx_out + t * lddx + col, o);
       }
     }
@@ -458,8 +654,9 @@ __global__ void __launch_bounds__(512) layernorm_bwd_kernel(const TDY* __restric
 // --------------------------------------------- layer-scale backward ---------------------------------------------
 // Threads own float4 column groups, CTAs own row ranges: dy = gamma * s * dres (bf16), dgamma += dres * s * branch,
 // colsum += dy.
-template <int NV, bool HAS_BRANCH>   // NV float4 groups per thread (D/4 <= 256 * NV)
-__global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __restrict__ dres, long lddres,
+template <int NV, bool HAS_BRANCH>   // NV float4 groups per thread (D/4 <= blockDim.x * NV; the launcher sizes the block
+                                     // so that every thread owns a column group: no idle second pass)
+__global__ void __launch_bounds__(512) layerscale_bwd_kernel(const float* __restrict__ dres, long lddres,
                                                              const __nv_bfloat16* __restrict__ branch, long ldbr,
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ row_scale, int rows_per_sample,
@@ -475,7 +672,7 @@ __global__ void __launch_bounds__(256) layerscale_bwd_kernel(const float* __rest
   (void)rows_per_block;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int ch = threadIdx.x + 256 * j;
+    const int ch = threadIdx.x + blockDim.x * j;
     if (ch >= nchunks) continue;
     const int col = ch * 4;
     float g[4] = {1.f, 1.f, 1.f, 1.f}, ag[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
@@ -754,14 +951,22 @@ static int ln_fwd_common(bool d8, const float* x, long ldx, const float* alpha, 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(T * 32, 256, 148 * 8);
   const int smem = 0;
+  // lane-contiguous fast path: C % 16 == 0 with C/16 chunks per lane in {3, 8, 10} (ViT-S / L / H)
+  const int lc_cpl = (d8 && (D % 128) == 0 && (ldy % 8) == 0) ? D / 128 : 0;
   if (y_dtype == OCTIC_BF16) {
     __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
-    if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, __nv_bfloat16, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
-    else OCTIC_LN_DISPATCH(layernorm_fwd_kernel, __nv_bfloat16, false, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+    if (d8 && lc_cpl == 10) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 10><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8 && lc_cpl == 8) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 8><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8 && lc_cpl == 3) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 3><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, __nv_bfloat16, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+    else OCTIC_LN_DISPATCH(layernorm_fwd_plain_kernel, __nv_bfloat16, false, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
   } else if (y_dtype == OCTIC_F32) {
     float* yy = static_cast<float*>(y);
-    if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, float, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
-    else OCTIC_LN_DISPATCH(layernorm_fwd_kernel, float, false, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+    if (d8 && lc_cpl == 10) layernorm_d8_fwd_lc_kernel<float, 10><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8 && lc_cpl == 8) layernorm_d8_fwd_lc_kernel<float, 8><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8 && lc_cpl == 3) layernorm_d8_fwd_lc_kernel<float, 3><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, float, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
+    else OCTIC_LN_DISPATCH(layernorm_fwd_plain_kernel, float, false, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
   } else {
     return OCTIC_ERR_ARG;
   }
@@ -829,24 +1034,27 @@ int octic_layerscale_bwd(const float* dres, long lddres, const void* branch, lon
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int rows_per_block = 4;
   long want = (T + rows_per_block - 1) / rows_per_block;
-  const int grid = static_cast<int>(want < 148 * 3 ? want : 148 * 3);   // 3 CTAs of 256 threads per SM
   const int nchunks = D / 4;
+  const int nv = (nchunks + 511) / 512;                              // column groups per thread
+  const int block = ((nchunks + nv - 1) / nv + 31) / 32 * 32;        // D = 1280 -> 320 threads, one float4 column each
+  const int per_sm = block <= 128 ? 8 : (block <= 256 ? 4 : (block <= 384 ? 3 : 2));
+  const int grid = static_cast<int>(want < 148L * per_sm ? want : 148L * per_sm);
   const __nv_bfloat16* br = static_cast<const __nv_bfloat16*>(branch);
   __nv_bfloat16* d = static_cast<__nv_bfloat16*>(dy);
 #define OCTIC_LS_LAUNCH(NVV)                                                                                        \
   do {                                                                                                            \
     if (br != nullptr)                                                                                            \
-      layerscale_bwd_kernel<NVV, true><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale,             \
-                                                            rows_per_sample, d, lddy, dgamma, colsum, T, D,        \
-                                                            rows_per_block);                                       \
+      layerscale_bwd_kernel<NVV, true><<<grid, block, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale,           \
+                                                              rows_per_sample, d, lddy, dgamma, colsum, T, D,      \
+                                                              rows_per_block);                                     \
     else                                                                                                          \
-      layerscale_bwd_kernel<NVV, false><<<grid, 256, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale,            \
-                                                             rows_per_sample, d, lddy, dgamma, colsum, T, D,       \
-                                                             rows_per_block);                                      \
+      layerscale_bwd_kernel<NVV, false><<<grid, block, 0, s>>>(dres, lddres, br, ldbr, gamma, row_scale,          \
+                                                               rows_per_sample, d, lddy, dgamma, colsum, T, D,     \
+                                                               rows_per_block);                                    \
   } while (0)
-  if (nchunks <= 256) OCTIC_LS_LAUNCH(1);
-  else if (nchunks <= 512) OCTIC_LS_LAUNCH(2);
-  else if (nchunks <= 1024) OCTIC_LS_LAUNCH(4);
+  if (nv == 1) OCTIC_LS_LAUNCH(1);
+  else if (nv == 2) OCTIC_LS_LAUNCH(2);
+  else if (nv <= 4) OCTIC_LS_LAUNCH(4);
   else return OCTIC_ERR_ARG;
   return last_err();
 }
