@@ -26,7 +26,7 @@ constexpr int kGemmThreads = 320;          // TN kernel: 2 + 8 epilogue warps
 constexpr int kWgradThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
-constexpr int kStagingWords = 32 * 33;                // per epilogue warp: 32 rows x (32+1) words
+constexpr int kStagingWords = 32 * 36;                // per epilogue warp: 32 rows x (32+1) words, or x 36 (16-byte rows)
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;                       // columns between the two accumulator stages
 
@@ -62,6 +62,18 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&b);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -181,7 +193,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int q = warp & 3;
     const int half = ew >> 2;
     const uint32_t stg = smem_u32(smem + L.stg_off) + ew * kStagingWords * 4;
+    // EPI_RESID: the fp32 residual rows of the warp's NEXT 32 x 32 chunk are fetched while the current chunk is
+    // processed (and, across tiles, while the MMAs of the next tile run): the epilogue is otherwise paced by one
+    // DRAM round trip per 8 rows.  res_ok is warp-uniform.
+    float res[32];
+    bool res_ok = false;
+    auto prefetch_resid = [&](int tile_, int c0_) {
+      res_ok = false;
+      if (MODE != EPI_RESID || p.resid_in == nullptr || p.remap_group != 0 || tile_ >= total_tiles) return;
+      int mb_, g_, nb_;
+      decode(tile_, mb_, g_, nb_);
+      const GemmGroup& G_ = p.g[g_];
+      const int n0_ = nb_ * p.block_n, row0_ = mb_ * kBlockM + q * 32;
+      if (c0_ + 32 > min(p.block_n, G_.n - n0_) || row0_ + 32 > p.M) return;
+      const float* rin_ = p.resid_in + static_cast<long>(row0_) * p.ldr + G_.c_col + n0_ + c0_ + lane;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) res[rr] = rin_[rr * p.ldr];
+      res_ok = true;
+    };
     int it = 0;
+    prefetch_resid(blockIdx.x, half * 32);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       int m_blk, g, n_blk;
       decode(tile, m_blk, g, n_blk);
@@ -197,14 +228,71 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const bool has_bias = p.bias != nullptr && G.bias_off >= 0;
 
-      for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + c0, r);
-        tmem_ld_wait();
+      // One 32-column chunk: registers (thread = row) -> per-warp smem transpose -> coalesced global I/O.
+      auto process_chunk = [&](const uint32_t (&r)[32], int c0) {
+        const bool full = (rmax == 32) && (c0 + 32 <= n_valid);
+        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+          // Vector path (full chunk, 16-byte aligned bf16 rows, no head remap): rows are staged 36 words apart so both
+          // the 16-byte writes (thread = row) and the 16-byte reads (4 lanes per row, 8 columns each) are conflict
+          // free; every store instruction then writes 8 rows x 64 B.  ~3x fewer instructions than the 4-byte path.
+          const int ocol0 = G.c_col + n0 + c0;
+          const bool vec = full && p.head_H == 0 && ((ocol0 | static_cast<int>(p.ldo)) & 7) == 0 &&
+                           (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
+                           (MODE != EPI_GELU_BF16 || p.branch_out == nullptr || (reinterpret_cast<uintptr_t>(p.branch_out) & 15) == 0);
+          if (vec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sts_v4(stg + lane * 144 + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+            __syncwarp();
+            const int cq = lane & 3, rsub = lane >> 2;
+            float bias8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bias8[i] = has_bias ? __ldg(p.bias + G.bias_off + n0 + c0 + cq * 8 + i) : 0.f;
+            const long obase = static_cast<long>(row0 + rsub) * p.ldo + ocol0 + cq * 8;
+            __nv_bfloat16* outv = reinterpret_cast<__nv_bfloat16*>(p.out) + obase;
+            __nv_bfloat16* prev = (MODE == EPI_GELU_BF16 && p.branch_out != nullptr)
+                                      ? reinterpret_cast<__nv_bfloat16*>(p.branch_out) + obase : nullptr;
+#pragma unroll
+            for (int h2 = 0; h2 < 4; h2 += 2) {        // two 8-row passes at a time (register budget)
+              float v[2][8];
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const uint32_t a = stg + ((h2 + u) * 8 + rsub) * 144 + cq * 32;
+                const float4 x0 = lds_v4(a), x1 = lds_v4(a + 16);
+                v[u][0] = x0.x + bias8[0]; v[u][1] = x0.y + bias8[1]; v[u][2] = x0.z + bias8[2]; v[u][3] = x0.w + bias8[3];
+                v[u][4] = x1.x + bias8[4]; v[u][5] = x1.y + bias8[5]; v[u][6] = x1.z + bias8[6]; v[u][7] = x1.w + bias8[7];
+              }
+              if (MODE == EPI_GELU_BF16) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  uint4 h;
+                  h.x = pack_bf16x2(v[u][0], v[u][1]); h.y = pack_bf16x2(v[u][2], v[u][3]);
+                  h.z = pack_bf16x2(v[u][4], v[u][5]); h.w = pack_bf16x2(v[u][6], v[u][7]);
+                  if (prev != nullptr) *reinterpret_cast<uint4*>(prev + static_cast<long>(h2 + u) * 8 * p.ldo) = h;
+                  // the reference rounds the pre-activation to bf16 before nn.GELU under autocast
+                  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+                    v[u][2 * i] = gelu_fast(hf.x);
+                    v[u][2 * i + 1] = gelu_fast(hf.y);
+                  }
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                uint4 o;
+                o.x = pack_bf16x2(v[u][0], v[u][1]); o.y = pack_bf16x2(v[u][2], v[u][3]);
+                o.z = pack_bf16x2(v[u][4], v[u][5]); o.w = pack_bf16x2(v[u][6], v[u][7]);
+                *reinterpret_cast<uint4*>(outv + static_cast<long>(h2 + u) * 8 * p.ldo) = o;
+              }
+            }
+            __syncwarp();
+            return;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) sts_u32(stg + (lane * 33 + j) * 4, r[j]);
         __syncwarp();
-        const bool full = (rmax == 32) && (c0 + 32 <= n_valid);
 
         if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
           // lane -> (row parity, column pair): each store instruction writes 2 rows x 64 B
@@ -231,19 +319,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                    ? reinterpret_cast<__nv_bfloat16*>(p.branch_out) + o0 : nullptr;
           const long step = 2 * p.ldo;
           if (full) {
+            // eight row pairs at a time: all shared-memory reads first, then the (independent) math, then the stores,
+            // so the GELU chains of different rows overlap instead of running one after the other
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-              float v0 = lds_f32(rd + rr * 264) + b0;
-              float v1 = lds_f32(rd + rr * 264 + 4) + b1;
-              if (MODE == EPI_GELU_BF16) {
-                const __nv_bfloat162 hb = __floats2bfloat162_rn(v0, v1);
-                if (pre != nullptr) *reinterpret_cast<__nv_bfloat162*>(pre + rr * step) = hb;
-                // the reference rounds the pre-activation to bf16 before nn.GELU under autocast
-                const float2 hf = __bfloat1622float2(hb);
-                v0 = gelu_fast(hf.x);
-                v1 = gelu_fast(hf.y);
+            for (int h8 = 0; h8 < 16; h8 += 8) {
+              float v0[8], v1[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                v0[i] = lds_f32(rd + (h8 + i) * 264) + b0;
+                v1[i] = lds_f32(rd + (h8 + i) * 264 + 4) + b1;
               }
-              *reinterpret_cast<__nv_bfloat162*>(outp + rr * step) = __floats2bfloat162_rn(v0, v1);
+              if (MODE == EPI_GELU_BF16) {
+                __nv_bfloat162 hb[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) hb[i] = __floats2bfloat162_rn(v0[i], v1[i]);
+                if (pre != nullptr) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) *reinterpret_cast<__nv_bfloat162*>(pre + (h8 + i) * step) = hb[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  // the reference rounds the pre-activation to bf16 before nn.GELU under autocast
+                  const float2 hf = __bfloat1622float2(hb[i]);
+                  v0[i] = gelu_fast(hf.x);
+                  v1[i] = gelu_fast(hf.y);
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                *reinterpret_cast<__nv_bfloat162*>(outp + (h8 + i) * step) = __floats2bfloat162_rn(v0[i], v1[i]);
             }
           } else if (cv0) {
             for (int rr = 0; rr < 16; ++rr) {
@@ -297,13 +401,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int r8 = 0; r8 < 32; r8 += 8) {
                 float base[8];
                 // all loads of a batch before its stores (resid_in may alias resid_out)
+                if (res_ok) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
+                  for (int i = 0; i < 8; ++i) base[i] = res[r8 + i];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
+                }
+                float acc[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = lds_f32(rd + (r8 + i) * 132) + bv;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   const int rr = r8 + i;
-                  float v = lds_f32(rd + rr * 132) + bv;
-                  const __nv_bfloat16 vb = __float2bfloat16(v);
+                  const __nv_bfloat16 vb = __float2bfloat16(acc[i]);
                   if (br != nullptr) br[rr * p.ldb] = vb;
                   // the reference's Linear emits bf16 under autocast; keep that rounding point
                   rout[rr * p.ldr] = base[i] + (rr < boundary ? s_a : s_b) * gv * __bfloat162float(vb);
@@ -341,6 +452,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __syncwarp();
+      };
+      // The TMEM load of the warp's next chunk is in flight while the current one is transposed and stored
+      // (tcgen05.ld latency is a few hundred cycles; with K = 160 / 320 the epilogue paces the octic GEMMs).
+      if constexpr (MODE == EPI_RESID) {
+        uint32_t ra[32];
+        for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
+          tmem_ld_32x32(t_addr + c0, ra);
+          tmem_ld_wait();
+          // stage the accumulators, then (res[] is consumed inside) fetch the residual rows of the next chunk
+          process_chunk(ra, c0);
+          if (c0 + 64 < n_valid) prefetch_resid(tile, c0 + 64);
+          else prefetch_resid(tile + gridDim.x, half * 32);
+        }
+        if (half * 32 >= n_valid) prefetch_resid(tile + gridDim.x, half * 32);
+      } else {
+        uint32_t ra[32], rb[32];
+        int c0 = half * 32;
+        if (c0 < n_valid) tmem_ld_32x32(t_addr + c0, ra);
+        while (c0 < n_valid) {
+          tmem_ld_wait();
+          if (c0 + 64 < n_valid) tmem_ld_32x32(t_addr + c0 + 64, rb);
+          process_chunk(ra, c0);
+          c0 += 64;
+          if (c0 >= n_valid) break;
+          tmem_ld_wait();
+          if (c0 + 64 < n_valid) tmem_ld_32x32(t_addr + c0 + 64, ra);
+          process_chunk(rb, c0);
+          c0 += 64;
+        }
       }
       tc_fence_before();
       __syncwarp();
