@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     tma_prefetch_desc(&tmQ);
     mbar_init(&bars[BAR_K], 1); mbar_init(&bars[BAR_V], 1); mbar_init(&bars[BAR_Q], 1);
     mbar_init(&bars[BAR_SFULL], 1); mbar_init(&bars[BAR_SFULL + 1], 1);
-    mbar_init(&bars[BAR_SDONE], kFwdMathThreads); mbar_init(&bars[BAR_SDONE + 1], kFwdMathThreads);
+    mbar_init(&bars[BAR_SDONE], kFwdMathThreads / 2); mbar_init(&bars[BAR_SDONE + 1], kFwdMathThreads / 2);
     mbar_init(&bars[BAR_OFULL], 1);
     mbar_init(&bars[BAR_QFREE], kFwdMathThreads);
     fence_mbar_init();
@@ -320,97 +320,114 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     }
   } else {
     // -------------------------------------------------- math warps --------------------------------------------------
-    // Two warps per TMEM lane quarter (q4) split the columns of every chunk and of the output accumulator (hh).
-    const int q4 = warp & 3, hh = warp >> 2;
+    // Warp (q4, bsel) owns TMEM lane quarter q4 of S buffer bsel: it handles the jobs j with (j & 1) == bsel.  Pass 1
+    // loads the whole chunk (row max); pass 2 streams 16-column pieces (load of piece p+1 in flight while piece p is
+    // exponentiated) and writes P in place -- hazard free inside one warp, since output piece p lands on columns of
+    // input piece p/2.  Row max / row sum are combined between the two warps of a quarter once per tile; for the
+    // output accumulator the pair splits the columns (hh = bsel).
+    const int q4 = warp & 3, bsel = warp >> 2, hh = bsel;
     const int rloc = q4 * 32 + lane;                   // row inside the tile
     OCTIC_TRACE_DECL;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-    uint32_t phs0 = 0, phs1 = 0, pho = 0u;
+    const uint32_t ta = t_lane + bsel * CW;
+    uint32_t phs = 0u, pho = 0u;
     for (int t = 0; t < nt; ++t) {
       const bool warp_valid = t * 128 + q4 * 32 < N;
       float mx = -INFINITY, l = 0.f, moff = 0.f;
       for (int j = 0; j < njobs; ++j) {
-        const int c = j < nc ? j : j - nc, buf = j & 1;
-        if (buf == 0) { mbar_wait(&bars[BAR_SFULL], phs0); phs0 ^= 1u; }
-        else { mbar_wait(&bars[BAR_SFULL + 1], phs1); phs1 ^= 1u; }
+        const int c = j < nc ? j : j - nc;
+        if (j == nc && warp_valid) {
+          // all pass-1 jobs of both warps are done: combine the two partial row maxima
+          xch[bsel * 128 + rloc] = mx;
+          named_bar_sync(1 + q4, 64);
+          mx = fmaxf(mx, xch[(bsel ^ 1) * 128 + rloc]);
+          moff = mx * scale_log2;
+        }
+        if ((j & 1) != bsel) continue;
+        mbar_wait(&bars[BAR_SFULL + bsel], phs);
+        phs ^= 1u;
         tc_fence_after();
         if (tid == 0) OCTIC_TRACE(1, 3);
         if (warp_valid) {
           const int w = cp.w[c], k0 = cp.off[c];
-          const int np = w >> 4, np0 = (np + 1) >> 1;
-          const int pb = hh == 0 ? 0 : np0, pe = hh == 0 ? np0 : np;
-          const uint32_t ta = t_lane + buf * CW;
-          uint32_t r[NPW][16];
-#pragma unroll
-          for (int pp = 0; pp < NPW; ++pp)
-            if (pb + pp < pe) tmem_ld_32x16(ta + (pb + pp) * 16, r[pp]);
-          tmem_ld_wait();
-          if (tid == 0) OCTIC_TRACE(1, 4);
+          const int np = w >> 4;
+          // Pieces are fetched in batches of up to PB (one TMEM round trip of ~300 cycles per batch instead of per
+          // piece).  In pass 2 the in-place P write of batch [b0, b1) lands on S columns of pieces < b1: all loaded.
+          constexpr int PB = 2;
           if (j < nc) {
             float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-            for (int pp = 0; pp < NPW; ++pp)
-              if (pb + pp < pe) {
-                const int nvalid = N - (k0 + (pb + pp) * 16);
-                float v[16];
+            for (int b0 = 0; b0 < CW / 16; b0 += PB) {
+              if (b0 < np) {
+                uint32_t r[PB][16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[pp][i]);
-                if (nvalid < 16) {
+                for (int u = 0; u < PB; ++u)
+                  if (b0 + u < CW / 16 && b0 + u < np) tmem_ld_32x16(ta + (b0 + u) * 16, r[u]);
+                tmem_ld_wait();
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
-                }
+                for (int u = 0; u < PB; ++u)
+                  if (b0 + u < CW / 16 && b0 + u < np) {
+                    const int nvalid = N - (k0 + (b0 + u) * 16);
+                    float v[16];
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
-                }
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[u][i]);
+                    if (nvalid < 16) {
+#pragma unroll
+                      for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                      m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+                    }
+                  }
               }
-            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-            if (j == nc - 1) {
-              // combine the two column halves of the row
-              xch[hh * 128 + rloc] = mx;
-              named_bar_sync(1 + q4, 64);
-              mx = fmaxf(mx, xch[(hh ^ 1) * 128 + rloc]);
-              moff = mx * scale_log2;
             }
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           } else {
-            // both warps of this lane quarter hold their S columns in registers before either overwrites them with P
-            tc_fence_before();
-            named_bar_sync(1 + q4, 64);
-            tc_fence_after();
             float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-            for (int pp = 0; pp < NPW; ++pp)
-              if (pb + pp < pe) {
-                const int nvalid = N - (k0 + (pb + pp) * 16);
-                float e[16];
+            for (int b0 = 0; b0 < CW / 16; b0 += PB) {
+              if (b0 < np) {
+                uint32_t r[PB][16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[pp][i]), scale_log2, -moff));
-                if (nvalid < 16) {
+                for (int u = 0; u < PB; ++u)
+                  if (b0 + u < CW / 16 && b0 + u < np) tmem_ld_32x16(ta + (b0 + u) * 16, r[u]);
+                tmem_ld_wait();
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) e[i] = i < nvalid ? e[i] : 0.f;
-                }
-                uint32_t pk[8];
+                for (int u = 0; u < PB; ++u)
+                  if (b0 + u < CW / 16 && b0 + u < np) {
+                    const int nvalid = N - (k0 + (b0 + u) * 16);
+                    float e[16];
 #pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
-                  pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
-                  pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
-                }
-                tmem_st_32x8(ta + (pb + pp) * 8, pk);
+                    for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[u][i]), scale_log2, -moff));
+                    if (nvalid < 16) {
+#pragma unroll
+                      for (int i = 0; i < 16; ++i) e[i] = i < nvalid ? e[i] : 0.f;
+                    }
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                      l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
+                      pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
+                      pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
+                    }
+                    tmem_st_32x8(ta + (b0 + u) * 8, pk);
+                  }
               }
+            }
             l += (l0 + l1) + (l2 + l3);
             tmem_st_wait();
           }
         }
         tc_fence_before();
         if (tid == 0) OCTIC_TRACE(1, 5);
-        mbar_arrive(&bars[BAR_SDONE + buf]);
+        mbar_arrive(&bars[BAR_SDONE + bsel]);
       }
       if (warp_valid) {
-        // total row sum = both column halves (written before, read after the pair barrier)
-        xch[hh * 128 + rloc] = l;
+        // total row sum = both warps of the quarter (written before, read after the pair barrier)
+        xch[bsel * 128 + rloc] = l;
         named_bar_sync(1 + q4, 64);
-        l += xch[(hh ^ 1) * 128 + rloc];
+        l += xch[(bsel ^ 1) * 128 + rloc];
       }
       mbar_wait(&bars[BAR_OFULL], pho);
       pho ^= 1u;
@@ -493,7 +510,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     tma_prefetch_desc(&tmDO);
     mbar_init(&bars[BAR_KQ], 1); mbar_init(&bars[BAR_VDO], 1);
     mbar_init(&bars[BAR_LFULL], 1); mbar_init(&bars[BAR_LFULL + 1], 1);
-    mbar_init(&bars[BAR_MDONE], kBwdMathThreads); mbar_init(&bars[BAR_MDONE + 1], kBwdMathThreads);
+    mbar_init(&bars[BAR_MDONE], kBwdMathThreads / 2); mbar_init(&bars[BAR_MDONE + 1], kBwdMathThreads / 2);
     mbar_init(&bars[BAR_ACC], 1);
     fence_mbar_init();
   }
@@ -589,12 +606,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     }
   } else {
     // -------------------------------------------------- math warps --------------------------------------------------
-    const int q4 = warp & 3, hh = warp >> 2;
+    // Warp (q4, bsel) owns TMEM lane quarter q4 of first-level buffer bsel: it handles every job g with (g & 1) == bsel
+    // and streams the job's 16-column pieces (load of piece p+1 in flight while piece p is computed).  Writing the
+    // bf16 outputs in place is hazard free inside one warp: output piece p lands on columns of input piece p/2, which
+    // the warp has already consumed.  The two warps of a quarter sit on the same SM sub-partition and cover each
+    // other's TMEM round trips.  For the accumulator flush (once per tile) the pair splits the columns (hh = bsel).
+    const int q4 = warp & 3, bsel = warp >> 2, hh = bsel;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     uint8_t* my_stg = stg + (q4 * 32 + lane) * (HD * 2);
     const uint32_t lse_sa = smem_u32(lse_s), del_sa = smem_u32(del_s);
+    const uint32_t tx = t_lane + bsel * 2 * CW, ty = tx + CW;
     OCTIC_TRACE_DECL;
-    uint32_t phl[2] = {0u, 0u}, pha = 0u;
+    uint32_t phl = 0u, pha = 0u;
     int g = 0;
     for (int phase = 0; phase < 2; ++phase) {
       for (int t = 0; t < nt; ++t) {
@@ -607,49 +630,50 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
           del_r = my_row < Rk ? del_s[my_row] : 0.f;
         }
         for (int c = 0; c < nc; ++c, ++g) {
-          const int buf = g & 1;
-          mbar_wait(&bars[BAR_LFULL + buf], phl[buf]);
-          phl[buf] ^= 1u;
+          if ((g & 1) != bsel) continue;
+          mbar_wait(&bars[BAR_LFULL + bsel], phl);
+          phl ^= 1u;
           tc_fence_after();
           if (tid == 0) OCTIC_TRACE(1, 3);
           if (warp_valid) {
             const int w = cp.w[c], k0 = cp.off[c];
-            const int np = w >> 4, np0 = (np + 1) >> 1;
-            const int pb = hh == 0 ? 0 : np0, pe = hh == 0 ? np0 : np;
-            const uint32_t tx = t_lane + buf * 2 * CW, ty = tx + CW;
-            uint32_t rx[NPW][16], ry[NPW][16];
+            const int np = w >> 4;
+            // three register sets: the loads of pieces p+1 and p+2 are in flight while piece p is computed (a TMEM
+            // round trip costs ~300 cycles, a piece of math ~150)
+            uint32_t rx[3][16], ry[3][16];
+            tmem_ld_32x16(tx, rx[0]);
+            tmem_ld_32x16(ty, ry[0]);
+            if (1 < np) {
+              tmem_ld_32x16(tx + 16, rx[1]);
+              tmem_ld_32x16(ty + 16, ry[1]);
+            }
 #pragma unroll
-            for (int pp = 0; pp < NPW; ++pp)
-              if (pb + pp < pe) {
-                tmem_ld_32x16(tx + (pb + pp) * 16, rx[pp]);
-                tmem_ld_32x16(ty + (pb + pp) * 16, ry[pp]);
-              }
-            tmem_ld_wait();
-            if (tid == 0) OCTIC_TRACE(1, 4);
-            // both warps of this lane quarter hold their inputs in registers before either overwrites the columns
-            tc_fence_before();
-            named_bar_sync(1 + q4, 64);
-            tc_fence_after();
-            if (tid == 0) OCTIC_TRACE(1, 8);
-#pragma unroll
-            for (int pp = 0; pp < NPW; ++pp)
-              if (pb + pp < pe) {
-                const int col0 = k0 + (pb + pp) * 16;
+            for (int pc = 0; pc < CW / 16; ++pc) {
+              if (pc < np) {
+                // wait::ld retires every outstanding load, so piece pc+1 is complete too; keep two loads in flight by
+                // issuing piece pc+2 right away
+                tmem_ld_wait();
+                if (pc + 2 < np) {
+                  tmem_ld_32x16(tx + (pc + 2) * 16, rx[(pc + 2) % 3]);
+                  tmem_ld_32x16(ty + (pc + 2) * 16, ry[(pc + 2) % 3]);
+                }
+                const int col0 = k0 + pc * 16;
                 uint32_t pkp[8], pkd[8];
                 if (phase == 0) {
                   // padded query columns carry lse = +inf (p = 0) and delta = 0: no explicit mask
-                  bwd_piece<true>(rx[pp], ry[pp], pkp, pkd, scale_log2, lse_sa + col0 * 4, del_sa + col0 * 4, 0.f, 0.f, 16);
-                  tmem_st_32x8(tx + (pb + pp) * 8, pkp);
+                  bwd_piece<true>(rx[pc % 3], ry[pc % 3], pkp, pkd, scale_log2, lse_sa + col0 * 4, del_sa + col0 * 4, 0.f, 0.f, 16);
+                  tmem_st_32x8(tx + pc * 8, pkp);
                 } else {
-                  bwd_piece<false>(rx[pp], ry[pp], pkp, pkd, scale_log2, 0u, 0u, lse_r, del_r, N - col0);
+                  bwd_piece<false>(rx[pc % 3], ry[pc % 3], pkp, pkd, scale_log2, 0u, 0u, lse_r, del_r, N - col0);
                 }
-                tmem_st_32x8(ty + (pb + pp) * 8, pkd);
+                tmem_st_32x8(ty + pc * 8, pkd);
               }
+            }
             tmem_st_wait();
           }
           tc_fence_before();
           if (tid == 0) OCTIC_TRACE(1, 5);
-          mbar_arrive(&bars[BAR_MDONE + buf]);
+          mbar_arrive(&bars[BAR_MDONE + bsel]);
         }
         // ---- flush the accumulators of this tile: TMEM -> bf16 staging -> packed global rows ----
         mbar_wait(&bars[BAR_ACC], pha);
