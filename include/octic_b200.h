@@ -45,6 +45,8 @@ extern "C" {
                                /* optional branch_out_bf16 = acc + bias (saved for the layer-scale gradient)  */
 #define OCTIC_EPI_F32 2        /* out_f32 = acc + bias                                                        */
 #define OCTIC_EPI_GELU_BF16 3  /* out_bf16 = gelu(bf16(acc + bias)); optional branch_out_bf16 = acc + bias    */
+#define OCTIC_EPI_GELU_BWD 4   /* out_bf16 = acc * gelu'(gelu_pre[m, c]) -- the fc2 dgrad with the nn.GELU backward of */
+                               /* deit/vit.py:126-129 fused; optional colsum[c] += sum_m out (the fc1 bias gradient)  */
 
 const char* octic_strerror(int code);
 int octic_version(void);
@@ -89,6 +91,8 @@ typedef struct {
    * c_col + n: the qkv LinearD8 (S = 3) and the proj dgrad (S = 1) emit head-major rows for the attention kernels
    * (reference pack step octic_vits/d8_layers.py:632-641) straight from the GEMM epilogue. */
   int head_H; int head_S; int head_D; int head_off[OCTIC_MAX_GROUPS];
+  const void* gelu_pre;       /* EPI_GELU_BWD: bf16 pre-activation, same shape and row stride (ldo) as out */
+  float* colsum;              /* EPI_GELU_BWD: optional fp32 [>= c_col + n], accumulated with red.add      */
 } octic_gemm_desc;
 
 int octic_gemm_bf16(const octic_gemm_desc* desc, void* stream);

@@ -15,7 +15,7 @@ LIB_PATH = _HERE / "lib" / "liboctic_b200.so"
 
 OCTIC_MAX_GROUPS = 8
 F32, BF16 = 0, 1
-EPI_BF16, EPI_RESID, EPI_F32, EPI_GELU_BF16 = 0, 1, 2, 3
+EPI_BF16, EPI_RESID, EPI_F32, EPI_GELU_BF16, EPI_GELU_BWD = 0, 1, 2, 3, 4
 
 
 class OcticError(RuntimeError):
@@ -41,6 +41,7 @@ class GemmDesc(C.Structure):
         ("branch_out", C.c_void_p), ("ldb", C.c_long),
         ("remap_group", C.c_int), ("remap_extra", C.c_int), ("remap_off", C.c_int),
         ("head_H", C.c_int), ("head_S", C.c_int), ("head_D", C.c_int), ("head_off", C.c_int * OCTIC_MAX_GROUPS),
+        ("gelu_pre", C.c_void_p), ("colsum", C.c_void_p),
     ]
 
 

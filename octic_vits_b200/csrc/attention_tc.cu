@@ -198,7 +198,28 @@ __device__ __forceinline__ void bwd_piece(const uint32_t (&rx)[16], const uint32
 //  forward
 // =====================================================================================================================
 constexpr int kFwdMathThreads = 256;
-constexpr int kFwdThreads = kFwdMathThreads + 32;
+constexpr int kFwdThreads = kFwdMathThreads + 64;   // + control warp + tail-row warp
+constexpr int kTailMax = 8;                         // N mod 128 <= kTailMax: those query rows leave the tensor path
+constexpr int kTailKpl = 16;                        // keys per lane of the tail warp (Rk <= 512)
+__host__ __device__ inline int attn_tail_rows(int N) { return (N >= 128 && (N & 127) <= kTailMax) ? (N & 127) : 0; }
+
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// 16 consecutive columns (atom column a) of row j of a SWIZZLE_32B tile with R rows -> fp32
+__device__ __forceinline__ void lds_row16(uint32_t tile, int R, int a, int j, float (&v)[16]) {
+  const uint32_t addr = tile + a * (R * 32) + j * 32;
+  const uint32_t sw = ((j >> 2) & 1) << 4;
+  const uint4 x = lds_u4(addr + sw), y = lds_u4(addr + (sw ^ 16u));
+  v[0] = bf_lo(x.x); v[1] = bf_hi(x.x); v[2] = bf_lo(x.y); v[3] = bf_hi(x.y);
+  v[4] = bf_lo(x.z); v[5] = bf_hi(x.z); v[6] = bf_lo(x.w); v[7] = bf_hi(x.w);
+  v[8] = bf_lo(y.x); v[9] = bf_hi(y.x); v[10] = bf_lo(y.y); v[11] = bf_hi(y.y);
+  v[12] = bf_lo(y.z); v[13] = bf_hi(y.z); v[14] = bf_lo(y.w); v[15] = bf_hi(y.w);
+}
 
 template <int HD, int GRAN>
 __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmKV,
@@ -206,7 +227,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
                                                                      __nv_bfloat16* __restrict__ o, float* __restrict__ lse,
                                                                      int N, int H, HeadMap m, float scale_log2,
                                                                      const __grid_constant__ ChunkPlan cp,
-                                                                     int kv_box_rows) {
+                                                                     int kv_box_rows,
+                                                                     const __nv_bfloat16* __restrict__ qkv, int n_tail) {
   constexpr int KS = HD / 16, CW = tc_chunk_width(HD), OCOL = 2 * CW, NU = HD / (GRAN / 2);
   constexpr int NPW = (CW / 16 + 1) / 2;        // max 16-column pieces per warp in one job
   constexpr int KS0 = (KS + 1) / 2;             // epilogue: accumulator pieces handled by column-half 0
@@ -224,10 +246,13 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   int* ocb = reinterpret_cast<int*>(xch + 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ocb + NU + (NU & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
+  // tail warp: q row [HD] + reduction scratch [32][17] (16-byte aligned for vector loads)
+  float* tailf = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 15) & ~uintptr_t(15));
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   __nv_bfloat16* orows = o + static_cast<long>(b) * N * m.D;
+  const int Nm = N - n_tail;                                     // query rows handled by the tensor path
 
   if (tid < NU) ocb[tid] = o_col(m, h, tid * (GRAN / 2));
   if (tid == kFwdMathThreads) {
@@ -246,9 +271,100 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs);
-  const int nt = (N + 127) >> 7, nc = cp.n, njobs = 2 * nc;
+  const int nt = (Nm + 127) >> 7, nc = cp.n, njobs = 2 * nc;
 
-  if (warp == 8) {
+  if (warp == 9) {
+    // -------------------------------------------------- tail warp --------------------------------------------------
+    // N = 128 k + (a few) rows (ViT: 256 patches + cls = 257): a third 128-row tensor tile would be 99 % padding, i.e.
+    // a third of all MMA work.  The last n_tail query rows are instead done here on the CUDA cores, from the same K / V
+    // tiles in shared memory, while the tensor pipeline runs the full tiles: lane = key (stride 32), exact softmax.
+    if (n_tail > 0) {
+      float* qf = tailf;
+      float* red = tailf + HD;
+      const int kpl = (Rk + 31) >> 5;
+      mbar_wait(&bars[BAR_K], 0);
+      for (int r = Nm; r < N; ++r) {
+        const __nv_bfloat16* qrow = qkv + (static_cast<long>(b) * N + r) * (3L * m.D) + h * HD;
+        for (int i = lane; i < HD / 2; i += 32) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + 2 * i));
+          qf[2 * i] = f.x * scale_log2;
+          qf[2 * i + 1] = f.y * scale_log2;
+        }
+        __syncwarp();
+        float sc[kTailKpl];
+#pragma unroll
+        for (int i = 0; i < kTailKpl; ++i) sc[i] = 0.f;
+#pragma unroll 1
+        for (int a = 0; a < KS; ++a) {
+          float q16[16];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float4 f = lds_f4(smem_u32(qf) + (a * 16 + u * 4) * 4);
+            q16[4 * u] = f.x; q16[4 * u + 1] = f.y; q16[4 * u + 2] = f.z; q16[4 * u + 3] = f.w;
+          }
+#pragma unroll
+          for (int i = 0; i < kTailKpl; ++i) {
+            const int j = lane + 32 * i;
+            if (i < kpl && j < Rk) {
+              float kv[16];
+              lds_row16(k_addr, Rk, a, j, kv);
+              float acc = sc[i];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc = fmaf(q16[c], kv[c], acc);
+              sc[i] = acc;
+            }
+          }
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < kTailKpl; ++i) {
+          if (lane + 32 * i >= N) sc[i] = -INFINITY;
+          mx = fmaxf(mx, sc[i]);
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o2));
+        float l = 0.f;
+#pragma unroll
+        for (int i = 0; i < kTailKpl; ++i) {
+          sc[i] = exp2f(sc[i] - mx);          // -inf -> 0
+          l += sc[i];
+        }
+#pragma unroll
+        for (int o2 = 16; o2 > 0; o2 >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o2);
+        if (lane == 0 && lse != nullptr) lse[(static_cast<long>(b) * H + h) * N + r] = (mx + log2f(l)) * kLn2;
+        const float inv = 1.0f / l;
+        if (r == Nm) mbar_wait(&bars[BAR_V], 0);
+#pragma unroll 1
+        for (int a = 0; a < KS; ++a) {
+          float acc[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+          for (int i = 0; i < kTailKpl; ++i) {
+            const int j = lane + 32 * i;
+            if (i < kpl && j < Rk) {
+              // P is rounded to bf16 like the tensor path (the reference's SDPA also multiplies a bf16 P with V)
+              const float pj = __bfloat162float(__float2bfloat16(sc[i]));
+              float vv[16];
+              lds_row16(v_addr, Rk, a, j, vv);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc[c] = fmaf(pj, vv[c], acc[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) red[lane * 17 + c] = acc[c];
+          __syncwarp();
+          if (lane < 16) {
+            float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 32; u += 2) { t0 += red[u * 17 + lane]; t1 += red[(u + 1) * 17 + lane]; }
+            orows[static_cast<long>(r) * m.D + o_col(m, h, a * 16 + lane)] = __float2bfloat16((t0 + t1) * inv);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 8) {
     // ------------------------------------------------ control warp ------------------------------------------------
     // The whole warp runs the loops (so addresses and descriptors stay warp-uniform); lane 0 issues TMA / MMA / commit.
     const bool leader = lane == 0;
@@ -332,7 +448,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     const uint32_t ta = t_lane + bsel * CW;
     uint32_t phs = 0u, pho = 0u;
     for (int t = 0; t < nt; ++t) {
-      const bool warp_valid = t * 128 + q4 * 32 < N;
+      const bool warp_valid = t * 128 + q4 * 32 < Nm;
       float mx = -INFINITY, l = 0.f, moff = 0.f;
       for (int j = 0; j < njobs; ++j) {
         const int c = j < nc ? j : j - nc;
@@ -437,12 +553,12 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
       if (warp_valid) {
         const float inv = 1.0f / l;
         acc_half_to_stg<KS>(t_lane + OCOL, hh, inv, Qs + rloc * (HD * 2));
-        if (hh == 0 && lse != nullptr && row < N)
+        if (hh == 0 && lse != nullptr && row < Nm)
           lse[(static_cast<long>(b) * H + h) * N + row] = (mx * scale_log2 + log2f(l)) * kLn2;
       }
       tc_fence_before();
       named_bar_sync(5, kFwdMathThreads);
-      store_tile<HD, GRAN>(Qs, orows + static_cast<long>(t) * 128 * m.D, m.D, min(128, N - t * 128), ocb, nullptr, 0, tid,
+      store_tile<HD, GRAN>(Qs, orows + static_cast<long>(t) * 128 * m.D, m.D, min(128, Nm - t * 128), ocb, nullptr, 0, tid,
                            kFwdMathThreads);
       fence_proxy_async_smem();      // the next Q tile arrives in Qs through the async proxy
       if (tid == 0) OCTIC_TRACE(1, 7);
@@ -461,7 +577,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
 //  backward
 // =====================================================================================================================
 constexpr int kBwdMathThreads = 256;
-constexpr int kBwdThreads = kBwdMathThreads + 32;
+constexpr int kBwdThreads = kBwdMathThreads + 96;   // + control warp + two tail-row warps (as key / as query)
 
 template <int HD, int GRAN>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,
@@ -471,7 +587,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
                                                                      __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
                                                                      float scale, float scale_log2,
                                                                      const __grid_constant__ ChunkPlan cp,
-                                                                     int box_rows) {
+                                                                     int box_rows, int n_tail) {
   constexpr int KS = HD / 16, CW = tc_chunk_width(HD), ACC = 4 * CW, NU = HD / (GRAN / 2);
   constexpr int NPW = (CW / 16 + 1) / 2;        // max 16-column pieces per warp in the math step
   constexpr int KS0 = (KS + 1) / 2;             // epilogue: pieces of the accumulator handled by column-half 0
@@ -494,10 +610,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   int* sm = cb + NU;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + NU + ((2 * NU) & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
+  float* tail_red = reinterpret_cast<float*>(tmem_ptr + 4);      // two tail warps x [32][33] reduction scratch
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
   const long ld3 = 3L * m.D;
+  const int Nm = N - n_tail;                                     // rows (as keys and as queries) of the tensor path
   __nv_bfloat16* drows = dqkv + static_cast<long>(b) * N * ld3;
 
   if (tid < NU) {
@@ -529,10 +647,103 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), do_addr = smem_u32(dOs);
-  const int nt = (N + 127) >> 7, nc = cp.n;
+  const int nt = (Nm + 127) >> 7, nc = cp.n;
   const int jobs_per_phase = nt * nc, G = 2 * jobs_per_phase;
 
-  if (warp == 8) {
+  if (warp >= 9) {
+    // -------------------------------------------------- tail warps --------------------------------------------------
+    // N = 128 k + a few rows (ViT: 257): the last n_tail tokens would cost a whole 128-lane tile in BOTH phases.  They
+    // stay in the column (chunk) dimension of the tensor path; their own rows are done here on the CUDA cores from the
+    // same shared-memory tiles: warp 9 takes them as keys (dK_j, dV_j over all queries), warp 10 as queries (dQ_i over
+    // all keys).  lane = the other token (stride 32).  P and dS are rounded to bf16 like the tensor path's operands.
+    if (n_tail > 0) {
+      const bool as_key = warp == 9;
+      float* red = tail_red + (warp - 9) * (32 * 33);
+      const int kpl = (Rk + 31) >> 5;
+      mbar_wait(&bars[BAR_KQ], 0);
+      mbar_wait(&bars[BAR_VDO], 0);
+      // as key:   fixed row r of K / V, lanes run over rows of Q / dO;   as query: fixed row r of Q / dO, lanes over K / V
+      const uint32_t fix1 = as_key ? k_addr : q_addr, fix2 = as_key ? v_addr : do_addr;
+      const uint32_t run1 = as_key ? q_addr : k_addr, run2 = as_key ? do_addr : v_addr;
+      for (int r = Nm; r < N; ++r) {
+        float sx[kTailKpl], sy[kTailKpl];
+#pragma unroll
+        for (int u = 0; u < kTailKpl; ++u) { sx[u] = 0.f; sy[u] = 0.f; }
+#pragma unroll 1
+        for (int a = 0; a < KS; ++a) {
+          float f1[16], f2[16];
+          lds_row16(fix1, Rk, a, r, f1);
+          lds_row16(fix2, Rk, a, r, f2);
+#pragma unroll
+          for (int u = 0; u < kTailKpl; ++u) {
+            const int i = lane + 32 * u;
+            if (u < kpl && i < Rk) {
+              float g1[16], g2[16];
+              lds_row16(run1, Rk, a, i, g1);
+              lds_row16(run2, Rk, a, i, g2);
+              float ax = sx[u], ay = sy[u];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) { ax = fmaf(f1[c], g1[c], ax); ay = fmaf(f2[c], g2[c], ay); }
+              sx[u] = ax; sy[u] = ay;
+            }
+          }
+        }
+        // sx = q.k, sy = dO.v  ->  sx = P, sy = dS
+        const float lse_r = lse_s[r], del_r = del_s[r];
+#pragma unroll
+        for (int u = 0; u < kTailKpl; ++u) {
+          const int i = lane + 32 * u;
+          float pv = 0.f, dv = 0.f;
+          if (u < kpl && i < N) {
+            const float ls = as_key ? lse_s[i] : lse_r, dl = as_key ? del_s[i] : del_r;
+            pv = exp2f(fmaf(sx[u], scale_log2, -ls));
+            dv = pv * (sy[u] - dl);
+          }
+          sx[u] = __bfloat162float(__float2bfloat16(pv));
+          sy[u] = __bfloat162float(__float2bfloat16(dv));
+        }
+        __nv_bfloat16* drow = drows + static_cast<long>(r) * ld3;
+#pragma unroll 1
+        for (int a = 0; a < KS; ++a) {
+          // as key:   acc1 = sum_i P_i dO_i (dV), acc2 = sum_i dS_i q_i (dK);   as query: acc2 = sum_j dS_j k_j (dQ)
+          float acc1[16], acc2[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { acc1[c] = 0.f; acc2[c] = 0.f; }
+#pragma unroll
+          for (int u = 0; u < kTailKpl; ++u) {
+            const int i = lane + 32 * u;
+            if (u < kpl && i < Rk) {
+              float g1[16];
+              lds_row16(run1, Rk, a, i, g1);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc2[c] = fmaf(sy[u], g1[c], acc2[c]);
+              if (as_key) {
+                float g2[16];
+                lds_row16(run2, Rk, a, i, g2);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc1[c] = fmaf(sx[u], g2[c], acc1[c]);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { red[lane * 33 + c] = acc1[c]; red[lane * 33 + 16 + c] = acc2[c]; }
+          __syncwarp();
+          float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+          for (int u = 0; u < 32; u += 2) { t0 += red[u * 33 + lane]; t1 += red[(u + 1) * 33 + lane]; }
+          const float tot = t0 + t1;
+          // lanes 0..15: acc1 column (dV), lanes 16..31: acc2 column (dK or dQ, scaled by 1/sqrt(hd))
+          const int jc = a * 16 + (lane & 15);
+          int base, smul;
+          qkv_col(m, h, jc & ~1, base, smul);
+          base += jc & 1;
+          if (lane >= 16) drow[base + (as_key ? 1 : 0) * smul] = __float2bfloat16(tot * scale);
+          else if (as_key) drow[base + 2 * smul] = __float2bfloat16(tot);
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 8) {
     // ------------------------------------------------ control warp ------------------------------------------------
     // The whole warp runs the loops (so addresses and descriptors stay warp-uniform); lane 0 issues TMA / MMA / commit.
     const bool leader = lane == 0;
@@ -623,7 +834,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       for (int t = 0; t < nt; ++t) {
         const int row0 = t * 128;
         const int my_row = row0 + q4 * 32 + lane;
-        const bool warp_valid = row0 + q4 * 32 < N;
+        const bool warp_valid = row0 + q4 * 32 < Nm;
         float lse_r = 0.f, del_r = 0.f;
         if (phase == 1) {
           lse_r = my_row < Rk ? lse_s[my_row] : INFINITY;
@@ -687,7 +898,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
         }
         tc_fence_before();
         named_bar_sync(5, kBwdMathThreads);
-        const int nvalid = min(128, N - row0);
+        const int nvalid = min(128, Nm - row0);
         store_tile<HD, GRAN>(stg, drows + static_cast<long>(row0) * ld3, ld3, nvalid, cb, sm, phase == 0 ? 1 : 0, tid,
                              kBwdMathThreads);
         if (phase == 0)
@@ -743,11 +954,11 @@ static int pick_box_rows(int Rk) { return Rk > 256 ? Rk / 2 : Rk; }
 
 static size_t fwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 256 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 1024;
+  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 256 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 16 + (hd + 32 * 17) * 4 + 1024;
 }
 static size_t bwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(4 * Rk + 256) * hd * 2 + 2 * Rk * 4 + (2 * nu + 1) * 4 + 7 * 8 + 16 + 1024;
+  return static_cast<size_t>(4 * Rk + 256) * hd * 2 + 2 * Rk * 4 + (2 * nu + 1) * 4 + 7 * 8 + 16 + 2 * 32 * 33 * 4 + 1024;
 }
 
 bool attn_tc_supported(int N, int hd, bool backward) {
@@ -780,7 +991,8 @@ static int launch_fwd_t(const void* qkv, void* o, float* lse, int B, int N, int 
   if (rc) return rc;
   const float scale_log2 = kLog2e / sqrtf(static_cast<float>(HD));
   attn_fwd_tc_kernel<HD, GRAN><<<B * H, kFwdThreads, smem, s>>>(tmKV, tmQ, static_cast<__nv_bfloat16*>(o), lse, N, H, m,
-                                                                scale_log2, cp, br);
+                                                                scale_log2, cp, br, static_cast<const __nv_bfloat16*>(qkv),
+                                                                attn_tail_rows(N));
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 template <int HD, int GRAN>
@@ -802,7 +1014,7 @@ static int launch_bwd_t(const void* qkv, const void* d_o, const float* lse, cons
   if (rc) return rc;
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   attn_bwd_tc_kernel<HD, GRAN><<<B * H, kBwdThreads, smem, s>>>(tmQKV, tmDO, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
-                                                                N, H, m, scale, kLog2e * scale, cp, br);
+                                                                N, H, m, scale, kLog2e * scale, cp, br, attn_tail_rows(N));
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 

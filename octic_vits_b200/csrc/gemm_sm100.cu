@@ -2,7 +2,10 @@
 // -> fused epilogue.  One persistent CTA per SM, warp-specialised:
 //   warp 0     TMA producer (one lane)
 //   warp 1     MMA issuer (one lane) + TMEM allocation (whole warp)
-//   warps 2-5  epilogue: tcgen05.ld -> registers -> per-warp smem transpose -> coalesced global I/O
+//   warps 2-17 epilogue: tcgen05.ld -> registers -> per-warp smem transpose -> coalesced global I/O
+// gemm_tn_kernel<MODE, 2> runs as CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): each CTA loads its own
+// 128 A rows and HALF of the B tile, so the operand traffic out of L2 per flop drops by a third -- at 128 x 256
+// single-CTA tiles the kernel is bound by L2 -> SM bandwidth, not by the tensor pipe.
 //
 // Two kernels live here:
 //   gemm_tn_kernel     C[m, n] = sum_k A[m, k] * B[n, k]   (both operands K-major).  A "problem" is a list of
@@ -16,13 +19,15 @@
 //                      contraction runs over tokens), split over token ranges, reduced with red.add.f32.
 #include "octic_capi_internal.h"
 #include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace octic {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;           // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 320;          // TN kernel: 2 + 8 epilogue warps
+constexpr int kEpiWarps = 16;              // TN kernel: four epilogue warps per TMEM lane quarter
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kWgradThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;   // 16 KiB
@@ -33,12 +38,12 @@ constexpr int kAccStride = 256;                       // columns between the two
 struct SmemLayout {
   uint32_t a_off, b_off, stg_off, bar_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int stages, int b_stage_bytes) {
+__host__ __device__ inline SmemLayout smem_layout(int stages, int b_stage_bytes, int epi_warps) {
   SmemLayout L;
   L.a_off = 0;
   L.b_off = stages * kAStageBytes;
   L.stg_off = L.b_off + stages * b_stage_bytes;
-  L.bar_off = L.stg_off + 8 * kStagingWords * 4;
+  L.bar_off = L.stg_off + epi_warps * kStagingWords * 4;
   L.total = L.bar_off + (2 * kMaxStages + 4) * 8 + 16;
   return L;
 }
@@ -55,6 +60,19 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(e, x);
 }
 __device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+// d/dx gelu(x) = Phi(x) + x phi(x) with the same erf approximation: one MUFU.EX2 + one MUFU.RCP (reference
+// octic_vits/d8_gelu.py:16-26 states the derivative; the dense fc1 activation is nn.GELU, deit/vit.py:126-129)
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float e = __expf(-0.5f * x * x);
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfv = copysignf(1.0f - poly * t * e, x);
+  return fmaf(x, 0.3989422804014327f * e, 0.5f * (1.0f + erfv));
+}
 __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
@@ -79,7 +97,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // ------------------------------------------------------------------------------------------------------------
 //  TN kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int NCTA>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ GemmParams p) {
@@ -90,8 +108,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.num_stages;
-  const int b_stage_bytes = p.block_n * kBlockK * 2;
-  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+  const int b_rows = p.block_n / NCTA;                    // B rows held by this CTA
+  const int b_stage_bytes = b_rows * kBlockK * 2;
+  const SmemLayout L = smem_layout(stages, b_stage_bytes, kEpiWarps);
+  const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = blockIdx.x / NCTA, ncl = gridDim.x / NCTA;   // this CTA (pair) and the number of them
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -109,21 +130,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 8);   // one arrive per epilogue warp
+      mbar_init(&tempty_bar[s], kEpiWarps * NCTA);   // one arrive per epilogue warp of the pair (leader's barrier)
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == 1) {
+    if (NCTA == 2) tmem_alloc_pair(tmem_ptr, kTmemCols);
+    else tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int total_tiles = p.num_m_blocks * p.tiles_per_m;
+  const int total_tiles = p.num_m_blocks * p.tiles_per_m;     // num_m_blocks counts 128 * NCTA-row blocks
 
   auto decode = [&](int tile, int& m_blk, int& g, int& n_blk) {
-    m_blk = tile / p.tiles_per_m;
-    int j = tile - m_blk * p.tiles_per_m;
+    const int mp = tile / p.tiles_per_m;
+    m_blk = mp * NCTA + rank;                                  // this CTA's own 128-row block
+    int j = tile - mp * p.tiles_per_m;
     g = 0;
 #pragma unroll 1
     for (int i = 1; i < p.num_groups; ++i)
@@ -136,30 +162,37 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cid; tile < total_tiles; tile += ncl) {
         int m_blk, g, n_blk;
         decode(tile, m_blk, g, n_blk);
         const GemmGroup& G = p.g[g];
         const CUtensorMap* tmB = G.b_map ? &tmB1 : &tmB0;
         for (int kb = 0; kb < G.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes + b_stage_bytes);
-          tma_load_2d(smem + L.a_off + stage * kAStageBytes, &tmA, &full_bar[stage], G.a_col + kb * kBlockK,
-                      m_blk * kBlockM);
-          tma_load_2d(smem + L.b_off + stage * b_stage_bytes, tmB, &full_bar[stage], kb * kBlockK,
-                      G.b_row + n_blk * p.block_n);
+          uint8_t* a_dst = smem + L.a_off + stage * kAStageBytes;
+          uint8_t* b_dst = smem + L.b_off + stage * b_stage_bytes;
+          if (NCTA == 2) {
+            // both CTAs' loads complete on the leader's barrier, which expects the bytes of the pair
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kAStageBytes + b_stage_bytes));
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], G.a_col + kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d_pair(b_dst, tmB, &full_bar[stage], kb * kBlockK, G.b_row + n_blk * p.block_n + rank * b_rows);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes + b_stage_bytes);
+            tma_load_2d(a_dst, &tmA, &full_bar[stage], G.a_col + kb * kBlockK, m_blk * kBlockM);
+            tma_load_2d(b_dst, tmB, &full_bar[stage], kb * kBlockK, G.b_row + n_blk * p.block_n);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------- MMA issuer --------------------------------------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 0, 0);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * NCTA, p.block_n, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
         int m_blk, g, n_blk;
         decode(tile, m_blk, g, n_blk);
         const int k_blocks = p.g[g].k_blocks;
@@ -177,43 +210,73 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advancing 16 bf16 (32 B) inside the swizzle atom = +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            if (NCTA == 2) umma_bf16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+          if (NCTA == 2) {
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit_pair(&tfull_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else {
     // --------------------------------------------- epilogue ---------------------------------------------
-    // 8 warps: warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter alternate 32-column chunks.
+    // 16 warps: warp w may touch TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter take every fourth
+    // 32-column chunk (the epilogue is latency bound per warp: more warps, not more work per warp, keep it ahead of
+    // the tensor pipe).
     // A chunk goes TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced global I/O (lane = column).
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int half = ew >> 2;
+    const int half = ew >> 2;                  // 0..3: first chunk of this warp
+    constexpr int kChunkStep = 32 * (kEpiWarps / 4);
     const uint32_t stg = smem_u32(smem + L.stg_off) + ew * kStagingWords * 4;
     // EPI_RESID: the fp32 residual rows of the warp's NEXT 32 x 32 chunk are fetched while the current chunk is
     // processed (and, across tiles, while the MMAs of the next tile run): the epilogue is otherwise paced by one
     // DRAM round trip per 8 rows.  res_ok is warp-uniform.
+    //
+    // Direct path (every full 32-column chunk of an aligned, un-remapped output): the thread keeps its row -- 32
+    // consecutive columns -- in registers and reads / writes global memory with 16-byte accesses straight from there.
+    // No shared-memory transpose: the operand reads of tcgen05.mma plus the TMA fills already use most of the
+    // 128 B/clk of shared-memory bandwidth, which is what bounds this kernel.  The staged path below remains for
+    // head-remapped outputs, column tails and unaligned shapes.
+    const bool direct_ptrs =
+        p.direct != 0 && p.head_H == 0 && p.remap_group == 0 &&
+        (MODE == EPI_RESID
+             ? ((reinterpret_cast<uintptr_t>(p.resid_out) | reinterpret_cast<uintptr_t>(p.resid_in) |
+                 reinterpret_cast<uintptr_t>(p.gamma) | reinterpret_cast<uintptr_t>(p.branch_out)) & 15) == 0 &&
+                   (p.ldr & 3) == 0 && (p.ldb & 7) == 0
+             : MODE == EPI_F32
+                   ? (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 && (p.ldo & 3) == 0
+                   : ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.branch_out) |
+                       reinterpret_cast<uintptr_t>(p.gelu_pre)) & 15) == 0 && (p.ldo & 7) == 0) &&
+        (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+    auto direct_ok = [&](const GemmGroup& G_, int n0_, int c0_) {
+      return direct_ptrs && c0_ + 32 <= min(p.block_n, G_.n - n0_) && ((G_.c_col + n0_ + c0_) & 7) == 0 &&
+             (G_.bias_off < 0 || ((G_.bias_off + n0_ + c0_) & 3) == 0);
+    };
     float res[32];
-    bool res_ok = false;
     auto prefetch_resid = [&](int tile_, int c0_) {
-      res_ok = false;
-      if (MODE != EPI_RESID || p.resid_in == nullptr || p.remap_group != 0 || tile_ >= total_tiles) return;
+      if (MODE != EPI_RESID || p.resid_in == nullptr || tile_ >= total_tiles) return;
       int mb_, g_, nb_;
       decode(tile_, mb_, g_, nb_);
       const GemmGroup& G_ = p.g[g_];
-      const int n0_ = nb_ * p.block_n, row0_ = mb_ * kBlockM + q * 32;
-      if (c0_ + 32 > min(p.block_n, G_.n - n0_) || row0_ + 32 > p.M) return;
-      const float* rin_ = p.resid_in + static_cast<long>(row0_) * p.ldr + G_.c_col + n0_ + c0_ + lane;
+      const int n0_ = nb_ * p.block_n, row_ = mb_ * kBlockM + q * 32 + lane;
+      if (!direct_ok(G_, n0_, c0_) || row_ >= p.M) return;
+      const float4* rin_ = reinterpret_cast<const float4*>(p.resid_in + static_cast<long>(row_) * p.ldr + G_.c_col + n0_ + c0_);
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) res[rr] = rin_[rr * p.ldr];
-      res_ok = true;
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = rin_[j];
+        res[4 * j] = t.x; res[4 * j + 1] = t.y; res[4 * j + 2] = t.z; res[4 * j + 3] = t.w;
+      }
     };
     int it = 0;
-    prefetch_resid(blockIdx.x, half * 32);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    prefetch_resid(cid, half * 32);
+    for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
       int m_blk, g, n_blk;
       decode(tile, m_blk, g, n_blk);
       const GemmGroup& G = p.g[g];
@@ -228,22 +291,142 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const bool has_bias = p.bias != nullptr && G.bias_off >= 0;
 
+      // Direct path: one 32-column chunk, thread = row, global I/O from registers (see above).
+      auto process_direct = [&](const uint32_t (&r)[32], int c0) {
+        const int row = row0 + lane;
+        const bool rv = lane < rmax;
+        const int ocol0 = G.c_col + n0 + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (has_bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + G.bias_off + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(bp + j);
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        }
+        if (MODE == EPI_F32) {
+          if (rv) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long>(row) * p.ldo + ocol0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else if (MODE == EPI_RESID) {
+          uint32_t hb[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hb[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);   // the Linear emits bf16 under autocast
+          if (rv) {
+            if (p.branch_out != nullptr) {
+              uint4* br = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.branch_out) + static_cast<long>(row) * p.ldb + ocol0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) br[j] = make_uint4(hb[4 * j], hb[4 * j + 1], hb[4 * j + 2], hb[4 * j + 3]);
+            }
+            const float sc = p.row_scale != nullptr ? __ldg(p.row_scale + row / p.rows_per_sample) : 1.f;
+            float4* ro = reinterpret_cast<float4*>(p.resid_out + static_cast<long>(row) * p.ldr + ocol0);
+            const float4* gp = reinterpret_cast<const float4*>(p.gamma + ocol0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 gm = make_float4(1.f, 1.f, 1.f, 1.f);
+              if (p.gamma != nullptr) gm = __ldg(gp + j);
+              const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hb[2 * j]));
+              const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hb[2 * j + 1]));
+              float4 o;
+              o.x = (p.resid_in != nullptr ? res[4 * j] : 0.f) + sc * gm.x * a.x;
+              o.y = (p.resid_in != nullptr ? res[4 * j + 1] : 0.f) + sc * gm.y * a.y;
+              o.z = (p.resid_in != nullptr ? res[4 * j + 2] : 0.f) + sc * gm.z * c.x;
+              o.w = (p.resid_in != nullptr ? res[4 * j + 3] : 0.f) + sc * gm.w * c.y;
+              ro[j] = o;
+            }
+          }
+        } else {
+          // bf16 outputs, one 8-column piece (16 bytes) at a time so that only one piece of GELU math is live
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long>(row) * p.ldo + ocol0);
+          uint4* pr = (MODE == EPI_GELU_BF16 && p.branch_out != nullptr)
+                          ? reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.branch_out) + static_cast<long>(row) * p.ldo + ocol0)
+                          : nullptr;
+          uint4 pv[4];
+          if (MODE == EPI_GELU_BWD) {
+            const uint4* pp = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.gelu_pre) + static_cast<long>(row) * p.ldo + ocol0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pv[j] = rv ? __ldg(pp + j) : make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float* t = v + 8 * j;
+            if (MODE == EPI_GELU_BF16) {
+              // the reference rounds the pre-activation to bf16 before nn.GELU under autocast
+              const uint4 h = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+              if (rv && pr != nullptr) pr[j] = h;
+              const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&hw[i]));
+                t[2 * i] = gelu_fast(hf.x);
+                t[2 * i + 1] = gelu_fast(hf.y);
+              }
+            } else if (MODE == EPI_GELU_BWD) {
+              const uint32_t pw[4] = {pv[j].x, pv[j].y, pv[j].z, pv[j].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[i]));
+                t[2 * i] *= gelu_grad_fast(pf.x);
+                t[2 * i + 1] *= gelu_grad_fast(pf.y);
+              }
+            }
+            if (rv) o[j] = make_uint4(pack_bf16x2(t[0], t[1]), pack_bf16x2(t[2], t[3]), pack_bf16x2(t[4], t[5]), pack_bf16x2(t[6], t[7]));
+            if (MODE != EPI_BF16) asm volatile("" ::: "memory");
+          }
+          if (MODE == EPI_GELU_BWD && p.colsum != nullptr) {
+            // column sums over the warp's 32 rows: recursive halving (31 shuffles); lane c ends up with column c
+            if (!rv) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+              const bool up = (lane & w) != 0;
+#pragma unroll
+              for (int j = 0; j < w; ++j) {
+                const float mine = up ? v[j + w] : v[j];
+                const float send = up ? v[j] : v[j + w];
+                v[j] = mine + __shfl_xor_sync(0xffffffffu, send, w);
+              }
+            }
+            // after the halving steps lane l holds column bitrev-free index: bit b of the lane selected the upper half
+            atomicAdd(p.colsum + ocol0 + lane, v[0]);
+          }
+        }
+      };
       // One 32-column chunk: registers (thread = row) -> per-warp smem transpose -> coalesced global I/O.
       auto process_chunk = [&](const uint32_t (&r)[32], int c0) {
         const bool full = (rmax == 32) && (c0 + 32 <= n_valid);
-        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16 || MODE == EPI_GELU_BWD) {
           // Vector path (full chunk, 16-byte aligned bf16 rows, no head remap): rows are staged 36 words apart so both
           // the 16-byte writes (thread = row) and the 16-byte reads (4 lanes per row, 8 columns each) are conflict
           // free; every store instruction then writes 8 rows x 64 B.  ~3x fewer instructions than the 4-byte path.
           const int ocol0 = G.c_col + n0 + c0;
           const bool vec = full && p.head_H == 0 && ((ocol0 | static_cast<int>(p.ldo)) & 7) == 0 &&
                            (reinterpret_cast<uintptr_t>(p.out) & 15) == 0 &&
-                           (MODE != EPI_GELU_BF16 || p.branch_out == nullptr || (reinterpret_cast<uintptr_t>(p.branch_out) & 15) == 0);
+                           (MODE != EPI_GELU_BF16 || p.branch_out == nullptr || (reinterpret_cast<uintptr_t>(p.branch_out) & 15) == 0) &&
+                           (MODE != EPI_GELU_BWD || (reinterpret_cast<uintptr_t>(p.gelu_pre) & 15) == 0);
           if (vec) {
+            const int cq = lane & 3, rsub = lane >> 2;
+            // EPI_GELU_BWD: the pre-activation rows of this chunk are requested before the accumulators are staged
+            uint4 prv[4];
+            if (MODE == EPI_GELU_BWD) {
+              const __nv_bfloat16* prep = reinterpret_cast<const __nv_bfloat16*>(p.gelu_pre) +
+                                          static_cast<long>(row0 + rsub) * p.ldo + ocol0 + cq * 8;
+#pragma unroll
+              for (int h = 0; h < 4; ++h) prv[h] = __ldg(reinterpret_cast<const uint4*>(prep + static_cast<long>(h) * 8 * p.ldo));
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) sts_v4(stg + lane * 144 + j * 16, r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
             __syncwarp();
-            const int cq = lane & 3, rsub = lane >> 2;
+            float cs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs[i] = 0.f;
             float bias8[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) bias8[i] = has_bias ? __ldg(p.bias + G.bias_off + n0 + c0 + cq * 8 + i) : 0.f;
@@ -278,12 +461,39 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                   }
                 }
               }
+              if (MODE == EPI_GELU_BWD) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const uint32_t pw[4] = {prv[h2 + u].x, prv[h2 + u].y, prv[h2 + u].z, prv[h2 + u].w};
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 pf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pw[i]));
+                    v[u][2 * i] *= gelu_grad_fast(pf.x);
+                    v[u][2 * i + 1] *= gelu_grad_fast(pf.y);
+                  }
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) cs[i] += v[u][i];
+                }
+              }
 #pragma unroll
               for (int u = 0; u < 2; ++u) {
                 uint4 o;
                 o.x = pack_bf16x2(v[u][0], v[u][1]); o.y = pack_bf16x2(v[u][2], v[u][3]);
                 o.z = pack_bf16x2(v[u][4], v[u][5]); o.w = pack_bf16x2(v[u][6], v[u][7]);
                 *reinterpret_cast<uint4*>(outv + static_cast<long>(h2 + u) * 8 * p.ldo) = o;
+              }
+            }
+            if (MODE == EPI_GELU_BWD && p.colsum != nullptr) {
+              // column sums of the 32 rows: fold the 8 row lanes (lane = rsub * 4 + cq), one red.add per column
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 4);
+                cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+                cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+              }
+              if (rsub == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) atomicAdd(p.colsum + ocol0 + cq * 8 + i, cs[i]);
               }
             }
             __syncwarp();
@@ -294,7 +504,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) sts_u32(stg + (lane * 33 + j) * 4, r[j]);
         __syncwarp();
 
-        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16 || MODE == EPI_GELU_BWD) {
           // lane -> (row parity, column pair): each store instruction writes 2 rows x 64 B
           const int cp = (lane & 15) * 2;
           const int rsel = lane >> 4;
@@ -318,7 +528,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __nv_bfloat16* pre = (MODE == EPI_GELU_BF16 && p.branch_out != nullptr)
                                    ? reinterpret_cast<__nv_bfloat16*>(p.branch_out) + o0 : nullptr;
           const long step = 2 * p.ldo;
-          if (full) {
+          if (MODE == EPI_GELU_BWD) {
+            // tails and unaligned shapes only (the vector path above takes every full chunk)
+            const __nv_bfloat16* prep = reinterpret_cast<const __nv_bfloat16*>(p.gelu_pre) + o0;
+            float s0 = 0.f, s1 = 0.f;
+            if (cv0) {
+              for (int rr = 0; rr < 16; ++rr) {
+                if (rr * 2 + rsel < rmax) {
+                  const float v0 = lds_f32(rd + rr * 264) * gelu_grad_fast(__bfloat162float(prep[rr * step]));
+                  outp[rr * step] = __float2bfloat16(v0);
+                  s0 += v0;
+                  if (cv1) {
+                    const float v1 = lds_f32(rd + rr * 264 + 4) * gelu_grad_fast(__bfloat162float(prep[rr * step + 1]));
+                    outp[rr * step + 1] = __float2bfloat16(v1);
+                    s1 += v1;
+                  }
+                }
+              }
+            }
+            if (p.colsum != nullptr) {
+              s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+              s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+              if (rsel == 0 && cv0) {
+                atomicAdd(p.colsum + ocol, s0);
+                if (cv1) atomicAdd(p.colsum + ocol + 1, s1);
+              }
+            }
+          } else if (full) {
             // eight row pairs at a time: all shared-memory reads first, then the (independent) math, then the stores,
             // so the GELU chains of different rows overlap instead of running one after the other
 #pragma unroll
@@ -401,13 +637,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int r8 = 0; r8 < 32; r8 += 8) {
                 float base[8];
                 // all loads of a batch before its stores (resid_in may alias resid_out)
-                if (res_ok) {
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) base[i] = res[r8 + i];
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
-                }
+                for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
                 float acc[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = lds_f32(rd + (r8 + i) * 132) + bv;
@@ -457,48 +688,48 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // (tcgen05.ld latency is a few hundred cycles; with K = 160 / 320 the epilogue paces the octic GEMMs).
       if constexpr (MODE == EPI_RESID) {
         uint32_t ra[32];
-        for (int c0 = half * 32; c0 < n_valid; c0 += 64) {
+        for (int c0 = half * 32; c0 < n_valid; c0 += kChunkStep) {
           tmem_ld_32x32(t_addr + c0, ra);
           tmem_ld_wait();
-          // stage the accumulators, then (res[] is consumed inside) fetch the residual rows of the next chunk
-          process_chunk(ra, c0);
-          if (c0 + 64 < n_valid) prefetch_resid(tile, c0 + 64);
-          else prefetch_resid(tile + gridDim.x, half * 32);
+          // (res[] is consumed inside) then fetch the residual rows of the next chunk
+          if (direct_ok(G, n0, c0)) process_direct(ra, c0);
+          else process_chunk(ra, c0);
+          if (c0 + kChunkStep < n_valid) prefetch_resid(tile, c0 + kChunkStep);
+          else prefetch_resid(tile + ncl, half * 32);
         }
-        if (half * 32 >= n_valid) prefetch_resid(tile + gridDim.x, half * 32);
+        if (half * 32 >= n_valid) prefetch_resid(tile + ncl, half * 32);
       } else {
-        uint32_t ra[32], rb[32];
-        int c0 = half * 32;
-        if (c0 < n_valid) tmem_ld_32x32(t_addr + c0, ra);
-        while (c0 < n_valid) {
+        uint32_t ra[32];
+        for (int c0 = half * 32; c0 < n_valid; c0 += kChunkStep) {
+          tmem_ld_32x32(t_addr + c0, ra);
           tmem_ld_wait();
-          if (c0 + 64 < n_valid) tmem_ld_32x32(t_addr + c0 + 64, rb);
-          process_chunk(ra, c0);
-          c0 += 64;
-          if (c0 >= n_valid) break;
-          tmem_ld_wait();
-          if (c0 + 64 < n_valid) tmem_ld_32x32(t_addr + c0 + 64, ra);
-          process_chunk(rb, c0);
-          c0 += 64;
+          if (direct_ok(G, n0, c0)) process_direct(ra, c0);
+          else process_chunk(ra, c0);
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 //  wgrad kernel (MN-major operands, contraction over tokens, split-K with fp32 red.add)
 // ------------------------------------------------------------------------------------------------------------
+template <int NCTA>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
                   const __grid_constant__ WgradParams p) {
@@ -507,8 +738,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.num_stages;
-  const int b_stage_bytes = p.block_n * kBlockK * 2;     // block_n is a multiple of 64 here
-  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+  const int b_cols = p.block_n / NCTA;                    // X columns (N extent) held by this CTA: whole 64-wide atoms
+  const int b_stage_bytes = b_cols * kBlockK * 2;
+  const SmemLayout L = smem_layout(stages, b_stage_bytes, 8);
+  const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int cid = blockIdx.x / NCTA, ncl = gridDim.x / NCTA;
 
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* empty_bar = full_bar + kMaxStages;
@@ -525,20 +759,32 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], 4 * NCTA);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, kTmemCols);
+  if (warp == 1) {
+    if (NCTA == 2) tmem_alloc_pair(tmem_ptr, kTmemCols);
+    else tmem_alloc(tmem_ptr, kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // work item -> (group, m_tile, n_tile, split)
-  auto decode = [&](int item, int& g, int& m_t, int& n_t, int& split) {
-    split = item % p.splits;
-    int j = item / p.splits;
+  // Stream-K: the (tile, k-block) pairs, k-block fastest, form one line of total_tiles * kb_total units that is cut
+  // into gridDim.x / NCTA equal contiguous ranges (one per CTA or CTA pair; a pair's tile has 256 dY features).  A CTA walks its range as segments (one output tile, k-blocks
+  // [kb0, kb1)); every segment ends in a red.add epilogue, so no CTA ever runs a second, mostly empty wave.
+  const int kb_total = (p.T + kBlockK - 1) / kBlockK;
+  const long total_units = static_cast<long>(p.total_tiles) * kb_total;
+  const long u_begin = total_units * cid / ncl;
+  const long u_end = total_units * (cid + 1) / ncl;
+  auto next_seg = [&](long& u, int& g, int& m_t, int& n_t, int& kb0, int& kb1) {
+    int j = static_cast<int>(u / kb_total);
+    kb0 = static_cast<int>(u - static_cast<long>(j) * kb_total);
+    kb1 = static_cast<int>(min(static_cast<long>(kb_total), kb0 + (u_end - u)));
+    u += kb1 - kb0;
     g = 0;
 #pragma unroll 1
     for (int i = 1; i < p.num_groups; ++i)
@@ -547,44 +793,45 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     m_t = j / p.g[g].n_tiles;
     n_t = j - m_t * p.g[g].n_tiles;
   };
-  const int total_items = p.total_tiles * p.splits;
-  const int kb_total = (p.T + kBlockK - 1) / kBlockK;
-  const int kb_per_split = (kb_total + p.splits - 1) / p.splits;
-  const int n_atoms = p.block_n / 64;
+  const int n_atoms = b_cols / 64;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        int g, m_t, n_t, split;
-        decode(item, g, m_t, n_t, split);
+      for (long u = u_begin; u < u_end;) {
+        int g, m_t, n_t, kb0, kb1;
+        next_seg(u, g, m_t, n_t, kb0, kb1);
         const WgradGroup& G = p.g[g];
-        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes + b_stage_bytes);
           uint8_t* a_dst = smem + L.a_off + stage * kAStageBytes;
           uint8_t* b_dst = smem + L.b_off + stage * b_stage_bytes;
+          const int a_col0 = G.dy_col + (m_t * NCTA + rank) * kBlockM;
+          const int b_col0 = G.x_col + n_t * p.block_n + rank * b_cols;
           // each box: 64 features (128 B, swizzled) x 64 tokens = 8 KiB; consecutive boxes = consecutive MN atoms
-          for (int i = 0; i < 2; ++i)
-            tma_load_2d(a_dst + i * 8192, &tmDY, &full_bar[stage], G.dy_col + m_t * kBlockM + i * 64, kb * kBlockK);
-          for (int i = 0; i < n_atoms; ++i)
-            tma_load_2d(b_dst + i * 8192, &tmX, &full_bar[stage], G.x_col + n_t * p.block_n + i * 64, kb * kBlockK);
+          if (NCTA == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kAStageBytes + b_stage_bytes));
+            for (int i = 0; i < 2; ++i) tma_load_2d_pair(a_dst + i * 8192, &tmDY, &full_bar[stage], a_col0 + i * 64, kb * kBlockK);
+            for (int i = 0; i < n_atoms; ++i) tma_load_2d_pair(b_dst + i * 8192, &tmX, &full_bar[stage], b_col0 + i * 64, kb * kBlockK);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kAStageBytes + b_stage_bytes);
+            for (int i = 0; i < 2; ++i) tma_load_2d(a_dst + i * 8192, &tmDY, &full_bar[stage], a_col0 + i * 64, kb * kBlockK);
+            for (int i = 0; i < n_atoms; ++i) tma_load_2d(b_dst + i * 8192, &tmX, &full_bar[stage], b_col0 + i * 64, kb * kBlockK);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kBlockM, p.block_n, 1, 1);
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM * NCTA, p.block_n, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-        int g, m_t, n_t, split;
-        decode(item, g, m_t, n_t, split);
-        const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+      for (long u = u_begin; u < u_end; ++it) {
+        int g, m_t, n_t, kb0, kb1;
+        next_seg(u, g, m_t, n_t, kb0, kb1);
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1);
@@ -600,15 +847,17 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // 16 K-rows x 128 B = 2048 B -> +128 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb > kb0) || (k != 0));
+            if (NCTA == 2) umma_bf16_pair(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb > kb0) || (k != 0));
+            else umma_bf16(d_tmem, da + 128 * k, db + 128 * k, idesc, (kb > kb0) || (k != 0));
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          if (NCTA == 2) {
+            umma_commit_pair(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit_pair(&tfull_bar[as]);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[as]);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1; }
-        }
-        if (kb1 <= kb0) {
-          // empty split (cannot happen with the host's choice of splits, but never leave the epilogue waiting)
-          umma_commit(&tfull_bar[as]);
         }
       }
     }
@@ -616,20 +865,19 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     const int q = warp & 3;
     float* stg = reinterpret_cast<float*>(smem + L.stg_off) + (warp - 2) * kStagingWords;
     int it = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
-      int g, m_t, n_t, split;
-      decode(item, g, m_t, n_t, split);
+    for (long u = u_begin; u < u_end; ++it) {
+      int g, m_t, n_t, kb0, kb1;
+      next_seg(u, g, m_t, n_t, kb0, kb1);
       const WgradGroup& G = p.g[g];
-      const int kb0 = split * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       const int n0 = n_t * p.block_n;
       const int n_valid = min(p.block_n, G.k_in - n0);
-      const int row0 = m_t * kBlockM + q * 32;            // out-feature row inside the group
+      const int row0 = (m_t * NCTA + rank) * kBlockM + q * 32;   // out-feature row inside the group
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
-      if (kb1 > kb0) {
+      {
         for (int c0 = 0; c0 < n_valid; c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32(t_addr + c0, r);
@@ -650,15 +898,20 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(&tempty_bar[as], 0);
+        else mbar_arrive(&tempty_bar[as]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (NCTA == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -707,6 +960,47 @@ static int num_sms() {
 }
 
 constexpr int kMaxDynSmem = 232448;   // 227 KiB
+// Measured on B200 (tools/gpu_s5_e.sh, profiles/r01_gemm_epilogue_policy_s5.txt): the register-direct epilogue issues
+// one 16-byte access per lane to 32 different lines and is bound by L1 line transactions; the staged (coalesced) path
+// wins for every mode, so direct is off by default and kept only as an experiment switch.
+constexpr int kDefaultDirectMask = 0;
+
+template <int MODE, int NCTA>
+static int launch_tn_one(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmB1,
+                         int grid, int smem_bytes, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tn_kernel<MODE, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
+      return OCTIC_ERR_CUDA;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_tn_kernel<MODE, NCTA>, tmA, tmB0, tmB1, p) == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+}
+template <int NCTA>
+static int launch_tn_mode(const GemmParams& p, const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmB1,
+                          int grid, int smem_bytes, cudaStream_t stream) {
+  switch (p.mode) {
+    case EPI_BF16: return launch_tn_one<EPI_BF16, NCTA>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream);
+    case EPI_RESID: return launch_tn_one<EPI_RESID, NCTA>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream);
+    case EPI_F32: return launch_tn_one<EPI_F32, NCTA>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream);
+    case EPI_GELU_BF16: return launch_tn_one<EPI_GELU_BF16, NCTA>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream);
+    case EPI_GELU_BWD: return launch_tn_one<EPI_GELU_BWD, NCTA>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream);
+    default: return OCTIC_ERR_ARG;
+  }
+}
 
 int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   if (d->num_groups < 1 || d->num_groups > OCTIC_MAX_GROUPS) return OCTIC_ERR_ARG;
@@ -717,7 +1011,26 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   p.M = d->M;
   p.num_groups = d->num_groups;
   p.block_n = d->block_n;
-  p.num_m_blocks = (d->M + kBlockM - 1) / kBlockM;
+  // CTA pairs (cta_group::2, M = 256) whenever the B tile splits into two halves of whole 8-row swizzle groups;
+  // OCTIC_GEMM_NCTA=1 forces single CTAs (A/B measurements).
+  static int forced_ncta = -1;
+  if (forced_ncta < 0) {
+    const char* e = getenv("OCTIC_GEMM_NCTA");
+    forced_ncta = (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 0;
+  }
+  static int direct_mask = -1;     // bit MODE set: that epilogue takes the register-direct path (OCTIC_GEMM_DIRECT=mask)
+  if (direct_mask < 0) {
+    const char* e = getenv("OCTIC_GEMM_DIRECT");
+    direct_mask = e != nullptr ? atoi(e) : kDefaultDirectMask;
+  }
+  p.direct = (direct_mask >> d->mode) & 1;
+  // Pairs pay off when the tile's MMA time dominates (dense layers, K >= 512) or the epilogue is the slow head-major
+  // scatter; the irrep groups with K = 160 / 320 (3-5 k-blocks per tile) run faster as single CTAs (same measurement).
+  int kmax = 0;
+  for (int i = 0; i < d->num_groups; ++i) kmax = d->groups[i].k > kmax ? d->groups[i].k : kmax;
+  const bool want_pairs = forced_ncta == 2 || (forced_ncta != 1 && (d->num_groups == 1 || kmax >= 512 || d->head_H > 0));
+  const int ncta = (want_pairs && d->block_n % 16 == 0 && d->block_n >= 32 && d->M > kBlockM && num_sms() >= 2) ? 2 : 1;
+  p.num_m_blocks = (d->M + kBlockM * ncta - 1) / (kBlockM * ncta);
   int tiles = 0;
   for (int i = 0; i < d->num_groups; ++i) {
     const octic_gemm_group& s = d->groups[i];
@@ -744,8 +1057,8 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   p.head_S = d->head_S;
   p.head_D = d->head_D;
   p.tiles_per_m = tiles;
-  const int b_stage_bytes = d->block_n * kBlockK * 2;
-  int stages = (kMaxDynSmem - 1024 - (8 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
+  const int b_stage_bytes = (d->block_n / ncta) * kBlockK * 2;
+  int stages = (kMaxDynSmem - 1024 - (kEpiWarps * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) return OCTIC_ERR_ARG;
   p.num_stages = stages;
@@ -764,42 +1077,56 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   p.remap_group = d->remap_group;
   p.remap_extra = d->remap_extra;
   p.remap_off = d->remap_off;
+  p.gelu_pre = d->gelu_pre;
+  p.colsum = d->colsum;
+  if (p.mode == EPI_GELU_BWD && (p.gelu_pre == nullptr || d->head_H > 0 || d->bias != nullptr)) return OCTIC_ERR_ARG;
   if (p.mode == EPI_RESID && p.resid_out == nullptr) return OCTIC_ERR_ARG;
   if (p.mode != EPI_RESID && p.out == nullptr) return OCTIC_ERR_ARG;
 
   CUtensorMap tmA, tmB0, tmB1;
   int rc = make_map_bf16(&tmA, d->a, d->M, d->a_cols, d->lda, kBlockM);
   if (rc) return rc;
-  rc = make_map_bf16(&tmB0, d->b0, d->b0_rows, d->b0_cols, d->b0_ld, d->block_n);
+  rc = make_map_bf16(&tmB0, d->b0, d->b0_rows, d->b0_cols, d->b0_ld, d->block_n / ncta);
   if (rc) return rc;
   if (d->b1 != nullptr) {
-    rc = make_map_bf16(&tmB1, d->b1, d->b1_rows, d->b1_cols, d->b1_ld, d->block_n);
+    rc = make_map_bf16(&tmB1, d->b1, d->b1_rows, d->b1_cols, d->b1_ld, d->block_n / ncta);
     if (rc) return rc;
   } else {
     tmB1 = tmB0;
   }
-  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+  const SmemLayout L = smem_layout(stages, b_stage_bytes, kEpiWarps);
   const int smem_bytes = L.total + 1024;
   const int total_tiles = p.num_m_blocks * p.tiles_per_m;
-  int grid = num_sms();
+  int grid = num_sms() / ncta;                       // CTAs (ncta = 1) or CTA pairs (ncta = 2)
   if (grid > total_tiles) grid = total_tiles;
+  grid *= ncta;
+  return ncta == 2 ? launch_tn_mode<2>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream)
+                   : launch_tn_mode<1>(p, tmA, tmB0, tmB1, grid, smem_bytes, stream);
+}
+
+template <int NCTA>
+static int launch_wgrad_t(const WgradParams& p, const CUtensorMap& tmDY, const CUtensorMap& tmX, int grid, int smem_bytes,
+                          cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tn_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tn_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tn_kernel<EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
+    if (cudaFuncSetAttribute(gemm_wgrad_kernel<NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess)
       return OCTIC_ERR_CUDA;
     attr_set = true;
   }
-  switch (p.mode) {
-    case EPI_BF16: gemm_tn_kernel<EPI_BF16><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
-    case EPI_RESID: gemm_tn_kernel<EPI_RESID><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
-    case EPI_F32: gemm_tn_kernel<EPI_F32><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
-    case EPI_GELU_BF16: gemm_tn_kernel<EPI_GELU_BF16><<<grid, kGemmThreads, smem_bytes, stream>>>(tmA, tmB0, tmB1, p); break;
-    default: return OCTIC_ERR_ARG;
-  }
-  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kWgradThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NCTA;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel<NCTA>, tmDY, tmX, p) == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
 int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
@@ -811,6 +1138,15 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
   p.T = d->T;
   p.num_groups = d->num_groups;
   p.block_n = d->block_n;
+  // CTA pairs (M = 256 dY features per tile, each CTA holds half of the X columns) when the halves are whole atoms
+  static int forced_ncta = -1;
+  if (forced_ncta < 0) {
+    const char* e = getenv("OCTIC_GEMM_NCTA");
+    forced_ncta = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  bool wide = false;
+  for (int i = 0; i < d->num_groups; ++i) wide = wide || d->groups[i].n_out > kBlockM;
+  const int ncta = (forced_ncta != 1 && d->block_n % 128 == 0 && wide && num_sms() >= 2) ? 2 : 1;
   int tiles = 0;
   for (int i = 0; i < d->num_groups; ++i) {
     const octic_wgrad_group& s = d->groups[i];
@@ -823,25 +1159,20 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
     G.dw = s.dw;
     G.ldw = s.ldw;
     G.n_tiles = (s.k_in + d->block_n - 1) / d->block_n;
-    G.m_tiles = (s.n_out + kBlockM - 1) / kBlockM;
+    G.m_tiles = (s.n_out + kBlockM * ncta - 1) / (kBlockM * ncta);
     G.tile_begin = tiles;
     tiles += G.n_tiles * G.m_tiles;
   }
   p.total_tiles = tiles;
+  // stream-K grid: one CTA (pair) per SM (pair); splits > 0: at most tiles * splits of them; each at least 4 k-blocks
   const int kb_total = (d->T + kBlockK - 1) / kBlockK;
-  int splits = d->splits;
-  if (splits <= 0) {
-    // enough items for ~2 waves, but at least 8 k-blocks per item
-    splits = (2 * num_sms() + tiles - 1) / tiles;
-    int max_splits = kb_total / 8;
-    if (max_splits < 1) max_splits = 1;
-    if (splits > max_splits) splits = max_splits;
-  }
-  if (splits > kb_total) splits = kb_total;
-  // make sure no split is empty
-  while (splits > 1 && (splits - 1) * ((kb_total + splits - 1) / splits) >= kb_total) --splits;
-  p.splits = splits;
-  const int b_stage_bytes = d->block_n * kBlockK * 2;
+  const long total_units = static_cast<long>(tiles) * kb_total;
+  long grid_l = num_sms() / ncta;
+  if (d->splits > 0 && static_cast<long>(tiles) * d->splits < grid_l) grid_l = static_cast<long>(tiles) * d->splits;
+  if (grid_l > (total_units + 3) / 4) grid_l = (total_units + 3) / 4;
+  if (grid_l < 1) grid_l = 1;
+  p.splits = d->splits;
+  const int b_stage_bytes = (d->block_n / ncta) * kBlockK * 2;
   int stages = (kMaxDynSmem - 1024 - (8 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.num_stages = stages;
@@ -851,19 +1182,11 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
   if (rc) return rc;
   rc = make_map_bf16(&tmX, d->x, d->T, d->x_cols, d->ld_x, kBlockK);
   if (rc) return rc;
-  const SmemLayout L = smem_layout(stages, b_stage_bytes);
+  const SmemLayout L = smem_layout(stages, b_stage_bytes, 8);
   const int smem_bytes = L.total + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
-    if (e != cudaSuccess) return OCTIC_ERR_CUDA;
-    attr_set = true;
-  }
-  const int total_items = tiles * splits;
-  int grid = num_sms();
-  if (grid > total_items) grid = total_items;
-  gemm_wgrad_kernel<<<grid, kWgradThreads, smem_bytes, stream>>>(tmDY, tmX, p);
-  return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
+  const int grid = static_cast<int>(grid_l) * ncta;
+  return ncta == 2 ? launch_wgrad_t<2>(p, tmDY, tmX, grid, smem_bytes, stream)
+                   : launch_wgrad_t<1>(p, tmDY, tmX, grid, smem_bytes, stream);
 }
 
 }  // namespace octic

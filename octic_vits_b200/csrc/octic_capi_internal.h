@@ -9,7 +9,8 @@
 
 namespace octic {
 
-enum { EPI_BF16 = OCTIC_EPI_BF16, EPI_RESID = OCTIC_EPI_RESID, EPI_F32 = OCTIC_EPI_F32, EPI_GELU_BF16 = OCTIC_EPI_GELU_BF16 };
+enum { EPI_BF16 = OCTIC_EPI_BF16, EPI_RESID = OCTIC_EPI_RESID, EPI_F32 = OCTIC_EPI_F32, EPI_GELU_BF16 = OCTIC_EPI_GELU_BF16,
+       EPI_GELU_BWD = OCTIC_EPI_GELU_BWD };
 
 struct GemmGroup {
   int a_col, k_blocks, b_map, b_row, n, n_tiles, c_col, bias_off, tile_begin, head_off;
@@ -30,6 +31,9 @@ struct GemmParams {
   long ldb;
   int remap_group, remap_extra, remap_off;
   int head_H, head_S, head_D;
+  const void* gelu_pre;
+  float* colsum;
+  int direct;   // 1: full aligned chunks go registers -> global without the shared-memory transpose
 };
 
 struct WgradGroup {

@@ -12,7 +12,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import ops
-from ._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID, OcticError
+from ._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_GELU_BWD, EPI_RESID, OcticError
 
 # ----------------------------------------------------------------------------------------------------------------
 # packing cache: fp32 parameters -> bf16 GEMM operands, re-packed only when a parameter's version changes
@@ -208,6 +208,51 @@ class LinearResidualFn(torch.autograd.Function):
             ops.linear_dense(dy, pk.w_t, pk.k, pk.n, None, EPI_BF16, out=dx)
         dw = ops.linear_dense_wgrad(dy, x, pk.n, pk.k) if ctx.needs_input_grad[1] else None
         return dx, dw, colsum, dgamma, dout, None, None, None
+
+
+class MlpResidualFn(torch.autograd.Function):
+    """resid_out = resid + row_scale * gamma * bf16(fc2(gelu(fc1(x)))): the whole dense MLP branch of a block
+    (timm Mlp + layer scale + DropPath + residual, deit/vit.py:126-134) as ONE autograd node, so that backward can
+    fuse the nn.GELU derivative and the fc1 bias gradient into the epilogue of the fc2 dgrad GEMM
+    (OCTIC_EPI_GELU_BWD): the gradient w.r.t. the hidden activation never makes a round trip through HBM."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, gamma, resid, row_scale, rows_per_sample):
+        x = _c(x)
+        pk1, pk2 = packed_dense(w1), packed_dense(w2)
+        T = x.shape[0]
+        train = any(ctx.needs_input_grad)
+        h = torch.empty(T, pk1.n, dtype=torch.bfloat16, device=x.device)
+        pre = torch.empty_like(h) if train else None
+        ops.linear_dense(x, pk1.w, pk1.n, pk1.k, b1, EPI_GELU_BF16, out=h, branch_out=pre)
+        need_branch = gamma is not None and ctx.needs_input_grad[5]
+        out = torch.empty_like(resid)
+        branch = torch.empty(T, pk2.n, dtype=torch.bfloat16, device=x.device) if need_branch else None
+        ops.linear_dense(h, pk2.w, pk2.n, pk2.k, b2, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out,
+                         row_scale=row_scale, rows_per_sample=rows_per_sample, branch_out=branch)
+        ctx.save_for_backward(x, pre, h, branch, gamma, row_scale)
+        ctx.pk = (pk1, pk2)
+        ctx.rows_per_sample = rows_per_sample
+        ctx.has_bias = (b1 is not None, b2 is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, pre, h, branch, gamma, row_scale = ctx.saved_tensors
+        pk1, pk2 = ctx.pk
+        dout = _c(dout)
+        dy, dgamma, colsum2 = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
+                                                 want_colsum=ctx.has_bias[1])
+        db1 = torch.zeros(pk1.n, dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
+        dpre = torch.empty_like(pre)
+        ops.linear_dense(dy, pk2.w_t, pk2.k, pk2.n, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre, colsum=db1)
+        dw2 = ops.linear_dense_wgrad(dy, h, pk2.n, pk2.k) if ctx.needs_input_grad[3] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(x.shape[0], pk1.k, dtype=torch.bfloat16, device=x.device)
+            ops.linear_dense(dpre, pk1.w_t, pk1.k, pk1.n, None, EPI_BF16, out=dx)
+        dw1 = ops.linear_dense_wgrad(dpre, x, pk1.n, pk1.k) if ctx.needs_input_grad[1] else None
+        return dx, dw1, db1, dw2, colsum2, dgamma, dout, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -695,8 +695,13 @@ class _DenseBlockBase(nn.Module):
         x2 = OF.LinearResidualFn.apply(_rows(a), self.attn.proj.weight, self.attn.proj.bias, self._gamma(1), xs,
                                        s1, N, (0, 0, 0))
         xn, x2 = OF.LayerNormFn.apply(x2, self.norm2.weight, self.norm2.bias, self.norm2.eps, False, True, True)
-        h = self.mlp.hidden_packed(xn)
-        out = OF.LinearResidualFn.apply(h, self.mlp.fc2.weight, self.mlp.fc2.bias, self._gamma(2), x2, s2, N, (0, 0, 0))
+        if type(self.mlp) is Mlp and isinstance(self.mlp.norm, nn.Identity):
+            out = OF.MlpResidualFn.apply(_as_bf16(xn), self.mlp.fc1.weight, self.mlp.fc1.bias, self.mlp.fc2.weight,
+                                         self.mlp.fc2.bias, self._gamma(2), x2, s2, N)
+        else:
+            h = self.mlp.hidden_packed(xn)
+            out = OF.LinearResidualFn.apply(h, self.mlp.fc2.weight, self.mlp.fc2.bias, self._gamma(2), x2, s2, N,
+                                            (0, 0, 0))
         return out.view(B, N, D)
 
 

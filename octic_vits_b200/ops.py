@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import BF16, EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID, F32, GemmDesc, WgradDesc, call
+from ._lib import BF16, EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_GELU_BWD, EPI_RESID, F32, GemmDesc, WgradDesc, call
 
 
 def _stream() -> C.c_void_p:
@@ -102,7 +102,8 @@ def pack_linear(w: torch.Tensor, need_t: bool = True) -> PackedDense:
 # GEMM front ends
 # ----------------------------------------------------------------------------------------------------------------
 def _epilogue_desc(mode: int, out=None, gamma=None, resid_in=None, resid_out=None, row_scale=None,
-                   rows_per_sample: int = 1, branch_out=None, remap=(0, 0, 0), head=(0, 0)) -> GemmDesc:
+                   rows_per_sample: int = 1, branch_out=None, remap=(0, 0, 0), head=(0, 0), gelu_pre=None,
+                   colsum=None) -> GemmDesc:
     d = GemmDesc()
     d.mode = mode
     if out is not None:
@@ -122,6 +123,11 @@ def _epilogue_desc(mode: int, out=None, gamma=None, resid_in=None, resid_out=Non
         d.ldb = branch_out.stride(0)
     d.remap_group, d.remap_extra, d.remap_off = remap
     d.head_H, d.head_S = head      # (heads, S): EPI_BF16 output rows head-major [S][H][hd] (see octic_b200.h)
+    if mode == EPI_GELU_BWD:
+        if gelu_pre is None or out is None or gelu_pre.stride(0) != out.stride(0) or gelu_pre.dtype != torch.bfloat16:
+            raise _lib.OcticError("EPI_GELU_BWD needs a bf16 pre-activation with the row stride of out")
+        d.gelu_pre = gelu_pre.data_ptr()
+        d.colsum = _ptr(colsum)
     return d
 
 

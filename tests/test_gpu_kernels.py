@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     from octic_vits_b200 import ops
-    from octic_vits_b200._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_RESID
+    from octic_vits_b200._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_GELU_BWD, EPI_RESID
 from octic_vits_b200._lib import OcticError
 from oracle import octic_oracle as O
 
@@ -113,6 +113,26 @@ def test_gemm_gelu_epilogue():
     h = x.float() @ bf(w).float().T + b
     assert_close(pre, h, rtol=1e-2, atol=2e-2)
     assert_close(out, torch.nn.functional.gelu(pre.float()), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("M,K,N", [(777, 256, 512), (300, 192, 1000), (4099, 320, 1280)])
+def test_gemm_gelu_bwd_epilogue(M, K, N):
+    """fc2 dgrad with the nn.GELU derivative and the fc1 bias gradient fused (OCTIC_EPI_GELU_BWD) vs autograd of
+    torch.nn.functional.gelu (deit/vit.py:126-129) on the same bf16 operands."""
+    g = torch.Generator().manual_seed(5 + M)
+    dy = bf(torch.randn(M, K, generator=g)).to(DEV)
+    w = (torch.randn(K, N, generator=g) / math.sqrt(K)).to(DEV)          # fc2 weight [out=K, hidden=N]
+    pre = bf(torch.randn(M, N, generator=g) * 1.5).to(DEV)
+    pk = ops.pack_linear(w)                                               # w_t = [N, roundup64(K)]
+    dpre = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    colsum = torch.zeros(N, dtype=torch.float32, device=DEV)
+    ops.linear_dense(dy, pk.w_t, N, K, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre, colsum=colsum)
+    p32 = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(p32).backward(dy.float() @ bf(w).float())
+    assert_close(dpre, p32.grad, rtol=1e-2, atol=2e-2)
+    assert_close(colsum, p32.grad.sum(0), rtol=1e-3, atol=2e-2 * math.sqrt(M))
+    with pytest.raises(OcticError):
+        ops.linear_dense(dy, pk.w_t, N, K, None, EPI_GELU_BWD, out=dpre)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,16 @@
+#!/usr/bin/env bash
+# direct epilogue + wgrad pairs: tests, per-op microbench (pairs vs single CTAs), event table, bench
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+( timeout 300 python -m pytest tests/test_gpu_kernels.py -q -m gpu -x -k "gemm" 2>&1 | tail -15 ) > gpurun_out/pytest_gemm.log 2>&1
+cat gpurun_out/pytest_gemm.log
+( time timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -15 ) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
+timeout 300 python tools/microbench_ops.py --batch 128 --only d8_,dense_ > gpurun_out/mb_pairs.txt 2>&1
+cat gpurun_out/mb_pairs.txt
+OCTIC_GEMM_NCTA=1 timeout 300 python tools/microbench_ops.py --batch 128 --only d8_,dense_ > gpurun_out/mb_single.txt 2>&1
+cat gpurun_out/mb_single.txt
+timeout 300 python tools/profile_step.py --batch 128 --events > gpurun_out/events_b128.txt 2>&1
+cat gpurun_out/events_b128.txt
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+cat gpurun_out/bench.json; tail -3 gpurun_out/bench.err

@@ -14,7 +14,7 @@ import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 from octic_vits_b200 import ops  # noqa: E402
-from octic_vits_b200._lib import EPI_BF16, EPI_GELU_BF16, EPI_RESID  # noqa: E402
+from octic_vits_b200._lib import EPI_BF16, EPI_GELU_BF16, EPI_GELU_BWD, EPI_RESID  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=64)
@@ -59,6 +59,7 @@ out3 = torch.empty(T, 3 * D, dtype=bf, device=dev)
 out4 = torch.empty(T, 4 * D, dtype=bf, device=dev)
 out1 = torch.empty(T, D, dtype=bf, device=dev)
 res_out = torch.empty(T, D, device=dev)
+colsum4 = torch.zeros(4 * D, device=dev)
 branch = torch.empty(T, D, dtype=bf, device=dev)
 _, stats8 = ops.layernorm_fwd(x32, alpha, beta, 1e-5, True)
 _, stats2 = ops.layernorm_fwd(x32, alpha, alpha, 1e-6, False)
@@ -94,6 +95,16 @@ CASES = {
     "dense_fc2_resid": (lambda: ops.linear_dense(h4, d2.w, D, 4 * D, None, EPI_RESID, gamma=gamma, resid_in=x32,
                                                  resid_out=res_out, branch_out=branch), T * D * 18, 2.0 * T * D * 4 * D),
     "dense_fc1_wgrad": (lambda: ops.linear_dense_wgrad(g4, xb, 4 * D, D), T * D * 10, 2.0 * T * D * 4 * D),
+    "dense_fc2_wgrad": (lambda: ops.linear_dense_wgrad(dyb, h4, D, 4 * D), T * D * 10, 2.0 * T * D * 4 * D),
+    "dense_qkv_wgrad": (lambda: ops.linear_dense_wgrad(qkv, xb, 3 * D, D), T * D * 8, 2.0 * T * D * 3 * D),
+    "dense_proj_wgrad": (lambda: ops.linear_dense_wgrad(dyb, xb, D, D), T * D * 4, 2.0 * T * D * D),
+    "dense_proj_plain": (lambda: ops.linear_dense(xb, dp.w, D, D, None, EPI_BF16, out=out1), T * D * 4, 2.0 * T * D * D),
+    "dense_fc2_dgrad_geluBwd": (lambda: ops.linear_dense(dyb, d2.w_t, 4 * D, D, None, EPI_GELU_BWD, out=out4, gelu_pre=h4,
+                                                         colsum=colsum4), T * D * 18, 2.0 * T * D * 4 * D),
+    "dense_fc1_dgrad": (lambda: ops.linear_dense(g4, d1.w_t, D, 4 * D, None, EPI_BF16, out=out1), T * D * 10, 2.0 * T * D * 4 * D),
+    "d8_qkv_headmajor": (lambda: ops.linear_d8(xb, pk_qkv, None, EPI_BF16, out=out3, head=(H, 3)), T * D * 8, oct_f * 3 * D),
+    "d8_fc2_dgrad": (lambda: ops.linear_d8_dgrad(dyb, pk_fc2), T * D * 10, oct_f * 4 * D),
+    "d8_qkv_wgrad": (lambda: ops.linear_d8_wgrad(qkv, xb, D, 3 * D), T * D * 8, oct_f * 3 * D),
 }
 
 only = [s for s in args.only.split(",") if s]
