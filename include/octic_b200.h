@@ -142,6 +142,12 @@ int octic_linear_d8_wgrad(const void* dy, const void* x, int T, int Din, int Dou
 
 /* Dense nn.Linear helpers (deit/vit.py:29-33): pack fp32 [N, K] -> bf16 [N, roundup64(K)] and its transpose. */
 int octic_linear_pack_weights(const float* w, int N, int K, void* w_packed, void* w_t_packed, void* stream);
+/* Transposed packs of diag(gamma) W (dgrad operand of the gamma-folded layer-scale backward, see
+ * octic_layerscale_wgrad_finalize): gamma fp32 [N] (dense) or the packed [Dout] vector (octic, alpha_E repeated). */
+int octic_linear_pack_weights_scaled(const float* w, const float* gamma, int N, int K, void* w_t_packed, void* stream);
+int octic_linear_d8_pack_weights_scaled(const float* wA1, const float* wA2, const float* wB1, const float* wB2,
+                                        const float* wE, const float* gamma, int Din, int Dout, void* w1d_t, void* wE_t,
+                                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * D8 GELU (octic_vits/d8_gelu.py:103-196 fwd, :209-331 bwd, :456-482 autograd wrapper; maths
@@ -161,19 +167,21 @@ int octic_gelu_bwd(const void* g, const void* x, void* gin, long n_rows, int n_c
  * column order (alpha_E repeated for both E rows); beta fp32 [C] or NULL; y bf16 or fp32 [T, D];
  * stats fp32 [T, 8] = (mean A1,A2,B1,B2,E0,E1, rstd, unused) or NULL.
  * bwd: dx_out = dx_in (or 0 if NULL) + LN^T(dy); dalpha[D], dbeta[C] accumulate (pre-zeroed by the caller).
+ * Optional by-products for the residual branch that produced x (NULL = off): dx_bf16 [T, D] (row stride lddx) =
+ * bf16(dx_out), dx_colsum fp32 [D] += sum_t dx_out (pre-zeroed).
  * --------------------------------------------------------------------------------------------------------- */
 int octic_layernorm_d8_fwd(const float* x, long ldx, const float* alpha, const float* beta, float eps, void* y,
                            long ldy, int y_dtype, float* stats, long T, int D, void* stream);
 int octic_layernorm_d8_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
                            const float* alpha, const float* dx_in, float* dx_out, long lddx, float* dalpha,
-                           float* dbeta, long T, int D, void* stream);
+                           float* dbeta, long T, int D, void* dx_bf16, float* dx_colsum, void* stream);
 
 /* nn.LayerNorm(eps) of the dense half (octic_vits/model.py:95,140; deit/vit.py:110,124). stats fp32 [T,2]. */
 int octic_layernorm_fwd(const float* x, long ldx, const float* w, const float* b, float eps, void* y, long ldy,
                         int y_dtype, float* stats, long T, int D, void* stream);
 int octic_layernorm_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
                         const float* w, const float* dx_in, float* dx_out, long lddx, float* dw, float* db, long T,
-                        int D, void* stream);
+                        int D, void* dx_bf16, float* dx_colsum, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Layer-scale + DropPath + residual, backward half (forward is the EPI_RESID GEMM epilogue).
@@ -183,6 +191,20 @@ int octic_layernorm_bwd(const void* dy, long lddy, int dy_dtype, const float* x,
 int octic_layerscale_bwd(const float* dres, long lddres, const void* branch, long ldbr, const float* gamma,
                          const float* row_scale, int rows_per_sample, void* dy, long lddy, float* dgamma,
                          float* colsum, long T, int D, void* stream);
+
+/* Gamma-folded variant without DropPath (the branch output is NOT saved in forward).  With g = bf16(dres) and
+ * cs = colsum(dres) (by-products of the layer-norm backward above):  dx = g (diag(gamma) W)  [dgrad with the *_scaled
+ * packs],  dW_raw = g^T x  [ordinary wgrad into a zeroed buffer], and this call finishes, per weight row n:
+ *   dgamma[n] += <W[n,:], dW_raw[n,:]> + bias[n] cs[n]   (= sum_t dres[t,n] branch[t,n], the autograd gradient of
+ *   gamma_1/2 in octic_vits/d8_layers.py:698-707),   dW[n,:] = gamma[n] dW_raw[n,:] (in place),   dbias[n] = gamma[n] cs[n].
+ * Up to 8 weight matrices (segments) per call: the five irrep weights of a LinearD8, or one nn.Linear. */
+typedef struct {
+  float* dw; const float* w; int N; int K;   /* fp32 [N, K], contiguous                         */
+  const float* gamma;                        /* fp32 [N]                                        */
+  const float* bias; const float* cs;        /* fp32 [N] or NULL                                */
+  float* dgamma; float* dbias;               /* fp32 [N] or NULL; dgamma accumulates            */
+} octic_lsfin_seg;
+int octic_layerscale_wgrad_finalize(const octic_lsfin_seg* segs, int nseg, void* stream);
 
 /* column sums of a bf16 matrix: out[c] += sum_t x[t, c] (bias gradients). */
 int octic_colsum_bf16(const void* x, long ldx, long T, int n_cols, float* out, void* stream);

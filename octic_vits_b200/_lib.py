@@ -59,6 +59,11 @@ class WgradDesc(C.Structure):
     ]
 
 
+class LsFinSeg(C.Structure):
+    _fields_ = [("dw", C.c_void_p), ("w", C.c_void_p), ("N", C.c_int), ("K", C.c_int), ("gamma", C.c_void_p),
+                ("bias", C.c_void_p), ("cs", C.c_void_p), ("dgamma", C.c_void_p), ("dbias", C.c_void_p)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
 
 # name -> argtypes; every function returns int.  Keep in sync with include/octic_b200.h (tests check that every
@@ -71,13 +76,16 @@ SIGNATURES = {
     "octic_linear_d8_dgrad": [_P, _I, _I, _I, _P, _P, _P, _I, _P],
     "octic_linear_d8_wgrad": [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P],
     "octic_linear_pack_weights": [_P, _I, _I, _P, _P, _P],
+    "octic_linear_pack_weights_scaled": [_P, _P, _I, _I, _P, _P],
+    "octic_linear_d8_pack_weights_scaled": [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
+    "octic_layerscale_wgrad_finalize": [C.POINTER(LsFinSeg), _I, _P],
     "octic_gelu_d8_fwd": [_P, _L, _P, _L, _L, _I, _I, _P],
     "octic_gelu_d8_bwd": [_P, _L, _P, _L, _P, _L, _L, _I, _I, _P, _P],
     "octic_gelu_bwd": [_P, _P, _P, _L, _I, _P, _P],
     "octic_layernorm_d8_fwd": [_P, _L, _P, _P, _F, _P, _L, _I, _P, _L, _I, _P],
-    "octic_layernorm_d8_bwd": [_P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _I, _P],
+    "octic_layernorm_d8_bwd": [_P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _I, _P, _P, _P],
     "octic_layernorm_fwd": [_P, _L, _P, _P, _F, _P, _L, _I, _P, _L, _I, _P],
-    "octic_layernorm_bwd": [_P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _I, _P],
+    "octic_layernorm_bwd": [_P, _L, _I, _P, _L, _P, _P, _P, _P, _L, _P, _P, _L, _I, _P, _P, _P],
     "octic_layerscale_bwd": [_P, _L, _P, _L, _P, _P, _I, _P, _L, _P, _P, _L, _I, _P],
     "octic_colsum_bf16": [_P, _L, _L, _I, _P, _P],
     "octic_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
@@ -122,7 +130,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_attention_bwd": 2}   # bwd: delta + main (legacy: +1)
+KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_linear_d8_pack_weights_scaled": 5, "octic_attention_bwd": 2}   # bwd: delta + main (legacy: +1)
 
 
 class _Stats:

@@ -17,14 +17,17 @@ int pick_block_n(const int* ns, int count) {
 }
 
 // fp32 [N, K] -> bf16 [N, ldp] (zero padded to ldp columns) and bf16 transpose [K, ldt] (zero padded).
+// row_scale (optional, fp32 [N]) multiplies row n before rounding: diag(gamma) W of the gamma-folded layer-scale backward.
 __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, __nv_bfloat16* __restrict__ dst,
-                                   long ldp, int Kp, __nv_bfloat16* __restrict__ dst_t, long ldt, int Np) {
+                                   long ldp, int Kp, __nv_bfloat16* __restrict__ dst_t, long ldt, int Np,
+                                   const float* __restrict__ row_scale) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
   for (int i = ty; i < 32; i += 8) {
     const int n = n0 + i, k = k0 + tx;
     float v = (n < N && k < K) ? w[static_cast<long>(n) * K + k] : 0.f;
+    if (row_scale != nullptr && n < N) v *= row_scale[n];
     tile[i][tx] = v;
     if (dst != nullptr && n < N && k < Kp) dst[static_cast<long>(n) * ldp + k] = __float2bfloat16(v);
   }
@@ -38,10 +41,10 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int N, int K, __
 }
 
 static int pack_one(const float* w, int N, int K, __nv_bfloat16* dst, long ldp, __nv_bfloat16* dst_t, long ldt,
-                    cudaStream_t s) {
+                    cudaStream_t s, const float* row_scale = nullptr) {
   const int Kp = roundup64(K), Np = roundup64(N);
   dim3 grid((Kp + 31) / 32, (Np + 31) / 32), block(32, 8);
-  pack_weight_kernel<<<grid, block, 0, s>>>(w, N, K, dst, ldp, Kp, dst_t, ldt, Np);
+  pack_weight_kernel<<<grid, block, 0, s>>>(w, N, K, dst, ldp, Kp, dst_t, ldt, Np, row_scale);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
@@ -99,6 +102,28 @@ int octic_linear_d8_pack_weights(const float* wA1, const float* wA2, const float
   }
   return pack_one(wE, 2 * Co, 2 * Ci, static_cast<__nv_bfloat16*>(wE_packed), ldE,
                   static_cast<__nv_bfloat16*>(wE_t), ldEt, s);
+}
+
+int octic_linear_d8_pack_weights_scaled(const float* wA1, const float* wA2, const float* wB1, const float* wB2,
+                                        const float* wE, const float* gamma, int Din, int Dout, void* w1d_t, void* wE_t,
+                                        void* stream) {
+  if (Din % 8 || Dout % 8 || !wA1 || !wA2 || !wB1 || !wB2 || !wE || !gamma || !w1d_t || !wE_t) return OCTIC_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int Ci = Din / 8, Co = Dout / 8;
+  const long ld1t = roundup64(Co), ldEt = roundup64(2 * Co);
+  const float* w[4] = {wA1, wA2, wB1, wB2};
+  for (int g = 0; g < 4; ++g) {
+    int rc = pack_one(w[g], Co, Ci, nullptr, 0, static_cast<__nv_bfloat16*>(w1d_t) + static_cast<long>(g) * Ci * ld1t, ld1t, s,
+                      gamma + g * Co);
+    if (rc) return rc;
+  }
+  return pack_one(wE, 2 * Co, 2 * Ci, nullptr, 0, static_cast<__nv_bfloat16*>(wE_t), ldEt, s, gamma + 4 * Co);
+}
+
+int octic_linear_pack_weights_scaled(const float* w, const float* gamma, int N, int K, void* w_t_packed, void* stream) {
+  if (!w || !gamma || !w_t_packed || N <= 0 || K <= 0) return OCTIC_ERR_ARG;
+  return pack_one(w, N, K, nullptr, 0, static_cast<__nv_bfloat16*>(w_t_packed), roundup64(N),
+                  static_cast<cudaStream_t>(stream), gamma);
 }
 
 int octic_linear_pack_weights(const float* w, int N, int K, void* w_packed, void* w_t_packed, void* stream) {

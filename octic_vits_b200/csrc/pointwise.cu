@@ -542,7 +542,8 @@ __global__ void __maxnreg__(96) layernorm_bwd_kernel(const TDY* __restrict__ dy,
                                                              const float* __restrict__ dx_in, float* __restrict__ dx_out,
                                                              long lddx, float* __restrict__ dalpha,
                                                              float* __restrict__ dbeta, long T_rows, int D,
-                                                             int tokens_per_block) {
+                                                             int tokens_per_block, __nv_bfloat16* __restrict__ dx_bf16,
+                                                             float* __restrict__ dx_colsum) {
   constexpr int NSEG = D8 ? 6 : 1;
   constexpr int NRED = NSEG + 1;                     // Q + per-segment sums
   __shared__ float part[16][kLnG * NRED];            // per-warp partials
@@ -559,6 +560,7 @@ __global__ void __maxnreg__(96) layernorm_bwd_kernel(const TDY* __restrict__ dy,
   float a4[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) Vec<float, 4>::load(alpha + col, a4);
   float acc_a[4] = {0.f, 0.f, 0.f, 0.f}, acc_b[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc_c[4] = {0.f, 0.f, 0.f, 0.f};             // column sums of dx (bias gradient of the layer below)
 
   (void)tokens_per_block;
   const long t1 = T_rows;
@@ -639,6 +641,12 @@ __global__ void __maxnreg__(96) layernorm_bwd_kernel(const TDY* __restrict__ dy,
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[i] += din[u][i];
         Vec<float, 4>::store(dx_out + t * lddx + col, o);
+        if (dx_bf16 != nullptr) {
+          // bf16 copy of the residual-stream gradient: the A operand of the dgrad / wgrad GEMMs of the branch below
+          Vec<__nv_bfloat16, 4>::store(dx_bf16 + t * lddx + col, o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc_c[i] += o[i];
+        }
       }
     }
   }
@@ -647,6 +655,65 @@ __global__ void __maxnreg__(96) layernorm_bwd_kernel(const TDY* __restrict__ dy,
     for (int i = 0; i < 4; ++i) {
       if (dalpha != nullptr) atomicAdd(dalpha + col + i, acc_a[i]);
       if (dbeta != nullptr && (!D8 || col < C)) atomicAdd(dbeta + col + i, acc_b[i]);
+      if (dx_colsum != nullptr) atomicAdd(dx_colsum + col + i, acc_c[i]);
+    }
+  }
+}
+
+// Gamma-folded layer-scale backward, last step (see functional.py "gamma-folded backward"): the wgrad GEMM produced
+// dW_raw = bf16(dres)^T x; here, one warp per weight row n:
+//   dgamma[n] += <W[n, :], dW_raw[n, :]> + bias[n] * cs[n]      (= sum_t dres[t, n] * branch[t, n])
+//   dW[n, :]   = gamma[n] * dW_raw[n, :]   (in place),   dbias[n] = gamma[n] * cs[n]
+struct LsFinSeg {
+  float* dw; const float* w; int N, K; const float* gamma; const float* bias; const float* cs; float* dgamma; float* dbias;
+};
+struct LsFinParams { int nseg; int row_begin[9]; LsFinSeg seg[8]; };
+__global__ void __launch_bounds__(128) layerscale_finalize_kernel(const __grid_constant__ LsFinParams p) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int row = warp; row < p.row_begin[p.nseg]; row += nwarps) {
+    int sg = 0;
+    for (int i = 1; i < p.nseg; ++i) sg = row >= p.row_begin[i] ? i : sg;
+    const LsFinSeg& S = p.seg[sg];
+    const int n = row - p.row_begin[sg];
+    float* dwr = S.dw + static_cast<long>(n) * S.K;
+    const float* wr = S.w + static_cast<long>(n) * S.K;
+    const float g = S.gamma[n];
+    float dot = 0.f;
+    if ((S.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(dwr) | reinterpret_cast<uintptr_t>(wr)) & 15) == 0) {
+      // four float4 column groups in flight per lane
+      const int k4 = S.K >> 2;
+      float4* d4 = reinterpret_cast<float4*>(dwr);
+      const float4* w4 = reinterpret_cast<const float4*>(wr);
+      for (int k0 = lane; k0 < k4; k0 += 128) {
+        float4 dv[4], wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 32 * u;
+          if (k < k4) { dv[u] = d4[k]; wv[u] = w4[k]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 32 * u;
+          if (k < k4) {
+            dot = fmaf(wv[u].x, dv[u].x, fmaf(wv[u].y, dv[u].y, fmaf(wv[u].z, dv[u].z, fmaf(wv[u].w, dv[u].w, dot))));
+            d4[k] = make_float4(g * dv[u].x, g * dv[u].y, g * dv[u].z, g * dv[u].w);
+          }
+        }
+      }
+    } else {
+      for (int k = lane; k < S.K; k += 32) {
+        const float d = dwr[k];
+        dot = fmaf(wr[k], d, dot);
+        dwr[k] = g * d;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) {
+      const float c = S.cs != nullptr ? S.cs[n] : 0.f;
+      if (S.dgamma != nullptr) S.dgamma[n] += dot + (S.bias != nullptr ? S.bias[n] * c : 0.f);
+      if (S.dbias != nullptr) S.dbias[n] = g * c;
     }
   }
 }
@@ -975,7 +1042,7 @@ static int ln_fwd_common(bool d8, const float* x, long ldx, const float* alpha, 
 
 static int ln_bwd_common(bool d8, const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
                          const float* alpha, const float* dx_in, float* dx_out, long lddx, float* dalpha, float* dbeta,
-                         long T, int D, void* stream) {
+                         long T, int D, void* dx_bf16, float* dx_colsum, void* stream) {
   if (!dy || !x || !stats || !alpha || !dx_out || T < 0 || D <= 0) return OCTIC_ERR_ARG;
   if (d8 ? (D % 32 != 0) : (D % 4 != 0)) return OCTIC_ERR_ARG;
   if ((ldx % 4) || (lddy % 4) || (lddx % 4) || !aligned16(x) || !aligned16(dy) || !aligned16(dx_out) ||
@@ -991,12 +1058,12 @@ static int ln_bwd_common(bool d8, const void* dy, long lddy, int dy_dtype, const
   const int grid = static_cast<int>(groups < 148L * per_sm ? groups : 148L * per_sm);
   if (dy_dtype == OCTIC_BF16) {
     const __nv_bfloat16* d = static_cast<const __nv_bfloat16*>(dy);
-    if (d8) layernorm_bwd_kernel<__nv_bfloat16, true><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
-    else layernorm_bwd_kernel<__nv_bfloat16, false><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
+    if (d8) layernorm_bwd_kernel<__nv_bfloat16, true><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block, static_cast<__nv_bfloat16*>(dx_bf16), dx_colsum);
+    else layernorm_bwd_kernel<__nv_bfloat16, false><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block, static_cast<__nv_bfloat16*>(dx_bf16), dx_colsum);
   } else if (dy_dtype == OCTIC_F32) {
     const float* d = static_cast<const float*>(dy);
-    if (d8) layernorm_bwd_kernel<float, true><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
-    else layernorm_bwd_kernel<float, false><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block);
+    if (d8) layernorm_bwd_kernel<float, true><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block, static_cast<__nv_bfloat16*>(dx_bf16), dx_colsum);
+    else layernorm_bwd_kernel<float, false><<<grid, nthreads, 0, s>>>(d, lddy, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, tokens_per_block, static_cast<__nv_bfloat16*>(dx_bf16), dx_colsum);
   } else {
     return OCTIC_ERR_ARG;
   }
@@ -1009,8 +1076,9 @@ int octic_layernorm_d8_fwd(const float* x, long ldx, const float* alpha, const f
 }
 int octic_layernorm_d8_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
                            const float* alpha, const float* dx_in, float* dx_out, long lddx, float* dalpha,
-                           float* dbeta, long T, int D, void* stream) {
-  return ln_bwd_common(true, dy, lddy, dy_dtype, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, stream);
+                           float* dbeta, long T, int D, void* dx_bf16, float* dx_colsum, void* stream) {
+  return ln_bwd_common(true, dy, lddy, dy_dtype, x, ldx, stats, alpha, dx_in, dx_out, lddx, dalpha, dbeta, T, D, dx_bf16,
+                       dx_colsum, stream);
 }
 int octic_layernorm_fwd(const float* x, long ldx, const float* w, const float* b, float eps, void* y, long ldy,
                         int y_dtype, float* stats, long T, int D, void* stream) {
@@ -1018,8 +1086,29 @@ int octic_layernorm_fwd(const float* x, long ldx, const float* w, const float* b
 }
 int octic_layernorm_bwd(const void* dy, long lddy, int dy_dtype, const float* x, long ldx, const float* stats,
                         const float* w, const float* dx_in, float* dx_out, long lddx, float* dw, float* db, long T,
-                        int D, void* stream) {
-  return ln_bwd_common(false, dy, lddy, dy_dtype, x, ldx, stats, w, dx_in, dx_out, lddx, dw, db, T, D, stream);
+                        int D, void* dx_bf16, float* dx_colsum, void* stream) {
+  return ln_bwd_common(false, dy, lddy, dy_dtype, x, ldx, stats, w, dx_in, dx_out, lddx, dw, db, T, D, dx_bf16, dx_colsum,
+                       stream);
+}
+
+int octic_layerscale_wgrad_finalize(const octic_lsfin_seg* segs, int nseg, void* stream) {
+  if (segs == nullptr || nseg < 1 || nseg > 8) return OCTIC_ERR_ARG;
+  LsFinParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = nseg;
+  int rows = 0;
+  for (int i = 0; i < nseg; ++i) {
+    if (!segs[i].dw || !segs[i].w || !segs[i].gamma || segs[i].N <= 0 || segs[i].K <= 0) return OCTIC_ERR_ARG;
+    p.row_begin[i] = rows;
+    rows += segs[i].N;
+    LsFinSeg& S = p.seg[i];
+    S.dw = segs[i].dw; S.w = segs[i].w; S.N = segs[i].N; S.K = segs[i].K; S.gamma = segs[i].gamma;
+    S.bias = segs[i].bias; S.cs = segs[i].cs; S.dgamma = segs[i].dgamma; S.dbias = segs[i].dbias;
+  }
+  p.row_begin[nseg] = rows;
+  const int grid = (rows + 3) / 4 < 148 * 16 ? (rows + 3) / 4 : 148 * 16;
+  layerscale_finalize_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return last_err();
 }
 
 int octic_layerscale_bwd(const float* dres, long lddres, const void* branch, long ldbr, const float* gamma,

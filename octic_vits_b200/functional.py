@@ -55,6 +55,46 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# gamma-folded backward of  x + gamma * Linear(a)  (layer scale without DropPath; octic_vits/d8_layers.py:698-707,
+# deit/vit.py:131-134).  The reference's autograd needs the branch output (saved in forward) for dgamma and makes a
+# pass over [T, D] to form dy = bf16(gamma * dres).  Here nothing is saved and no pass is made:
+#   * the layer-norm backward that PRODUCES dres also emits g = bf16(dres) and cs = colsum(dres) (two more outputs of
+#     a kernel that already holds the row in registers) and parks them in `_aux_slot`;
+#   * dgrad:  dx = g (diag(gamma) W)          -- the gamma-scaled transposed packs
+#   * wgrad:  dW_raw = g^T a, then one small kernel per layer: dgamma = <W, dW_raw>_rows + b * cs, dW = gamma * dW_raw,
+#     db = gamma * cs   (exact: sum_t dres * branch = sum_t dres * (a W^T + b)).
+# With DropPath (row_scale) or FOLD_GAMMA = False the branch-saving path (octic_layerscale_bwd) is used.
+# ----------------------------------------------------------------------------------------------------------------
+FOLD_GAMMA = True
+_aux_slot = None     # (data_ptr, shape, bf16 copy, column sums) of the most recent layer-norm backward output
+
+
+def _park_aux(dx: torch.Tensor, dxb: torch.Tensor, dxs: torch.Tensor) -> None:
+    global _aux_slot
+    _aux_slot = (dx.data_ptr(), tuple(dx.shape), dxb, dxs, dx)   # dx itself is held so that its storage cannot be reused
+
+
+def _take_aux(dres: torch.Tensor):
+    """(bf16(dres), colsum(dres)): from the producer when it is the tensor parked last, else one streaming pass."""
+    global _aux_slot
+    slot, _aux_slot = _aux_slot, None
+    if slot is not None and slot[0] == dres.data_ptr() and slot[1] == tuple(dres.shape):
+        return slot[2], slot[3]
+    g, _, cs = ops.layerscale_bwd(dres, None, None, None, 1, want_colsum=True)
+    return g, cs
+
+
+def packed_d8_scaled_t(weights, gamma, gamma_src):
+    """cached on the weight parameters and the parameters gamma was assembled from (gamma itself is a derived tensor)"""
+    key = tuple(weights) + tuple(gamma_src if gamma_src is not None else (gamma,))
+    return _cached(key, lambda: ops.pack_linear_d8_scaled_t(*[w.detach() for w in weights], gamma.detach().contiguous()))
+
+
+def packed_dense_scaled_t(weight, gamma):
+    return _cached((weight, gamma), lambda: ops.pack_linear_scaled_t(weight.detach().contiguous(), gamma.detach().contiguous()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # LinearD8  (reference octic_vits/d8_layers.py:104-127)
 # ----------------------------------------------------------------------------------------------------------------
 class LinearD8Fn(torch.autograd.Function):
@@ -93,15 +133,18 @@ class LinearD8ResidualFn(torch.autograd.Function):
     (reference d8_layers.py:698-707, 759-776, 205-212, 249-282)."""
 
     @staticmethod
-    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, gamma, resid, row_scale, rows_per_sample, dgrad_heads: int = 0):
+    def forward(ctx, x, wA1, wA2, wB1, wB2, wE, bias, gamma, resid, row_scale, rows_per_sample, dgrad_heads: int = 0,
+                gamma_src=None):
         x = _c(x)
         pk = packed_d8((wA1, wA2, wB1, wB2, wE))
-        need_branch = gamma is not None and ctx.needs_input_grad[7]
+        ctx.fold = FOLD_GAMMA and gamma is not None and row_scale is None and any(ctx.needs_input_grad)
+        need_branch = gamma is not None and ctx.needs_input_grad[7] and not ctx.fold
+        ctx.gamma_src = gamma_src
         out = torch.empty_like(resid)
         branch = torch.empty(x.shape[0], pk.dout, dtype=torch.bfloat16, device=x.device) if need_branch else None
         ops.linear_d8(x, pk, bias, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out, row_scale=row_scale,
                       rows_per_sample=rows_per_sample, branch_out=branch)
-        ctx.save_for_backward(x, branch, gamma, row_scale)
+        ctx.save_for_backward(x, branch, gamma, row_scale, wA1, wA2, wB1, wB2, wE, bias)
         ctx.pk = pk
         ctx.rows_per_sample = rows_per_sample
         ctx.has_bias = bias is not None
@@ -110,15 +153,33 @@ class LinearD8ResidualFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, branch, gamma, row_scale = ctx.saved_tensors
+        x, branch, gamma, row_scale, wA1, wA2, wB1, wB2, wE, bias = ctx.saved_tensors
         pk = ctx.pk
         dout = _c(dout)
+        if ctx.fold:
+            g, cs = _take_aux(dout)
+            co = pk.dout // 8
+            ws = (wA1, wA2, wB1, wB2, wE)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = ops.linear_d8_dgrad(g, packed_d8_scaled_t(ws, gamma, ctx.gamma_src), ctx.dgrad_heads)
+            dws = ops.linear_d8_wgrad(g, x, pk.din, pk.dout)
+            dgamma = torch.zeros_like(gamma)
+            db = torch.empty(co, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            gam = gamma.detach()
+            segs = [(dws[i], ws[i].detach(), gam[i * co:(i + 1) * co], bias if i == 0 else None,
+                     cs[:co] if (i == 0 and ctx.has_bias) else None, dgamma[i * co:(i + 1) * co],
+                     db if i == 0 else None) for i in range(4)]
+            # both E rows share W_E and alpha_E: the whole gradient lands on the first copy of alpha_E in the packed vector
+            segs.append((dws[4], wE.detach(), gam[4 * co:6 * co], None, None, dgamma[4 * co:6 * co], None))
+            ops.layerscale_wgrad_finalize(segs)
+            return (dx, *dws, db, dgamma, dout, None, None, None, None)
         dy, dgamma, colsum = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
                                                 want_colsum=ctx.has_bias)
         dx = ops.linear_d8_dgrad(dy, pk, ctx.dgrad_heads) if ctx.needs_input_grad[0] else None
         dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
         db = colsum[: pk.dout // 8] if ctx.has_bias else None
-        return (dx, *dws, db, dgamma, dout, None, None, None)
+        return (dx, *dws, db, dgamma, dout, None, None, None, None)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -176,22 +237,32 @@ class LinearResidualFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, resid, row_scale, rows_per_sample, remap):
         x = _c(x)
         pk = packed_dense(weight)
-        need_branch = gamma is not None and ctx.needs_input_grad[3]
+        ctx.fold = (FOLD_GAMMA and gamma is not None and row_scale is None and remap == (0, 0, 0)
+                    and isinstance(gamma, torch.nn.Parameter) and any(ctx.needs_input_grad))
+        need_branch = gamma is not None and ctx.needs_input_grad[3] and not ctx.fold
         out = torch.empty_like(resid)
         if remap != (0, 0, 0):
             out.copy_(resid)        # rows the GEMM does not touch (cls tokens) must carry over
         branch = torch.empty(resid.shape[0], pk.n, dtype=torch.bfloat16, device=x.device) if need_branch else None
         ops.linear_dense(x, pk.w, pk.n, pk.k, bias, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out,
                          row_scale=row_scale, rows_per_sample=rows_per_sample, branch_out=branch, remap=remap)
-        ctx.save_for_backward(x, branch, gamma, row_scale)
+        ctx.save_for_backward(x, branch, gamma, row_scale, weight, bias)
         ctx.pk, ctx.rows_per_sample, ctx.has_bias, ctx.remap = pk, rows_per_sample, bias is not None, remap
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, branch, gamma, row_scale = ctx.saved_tensors
+        x, branch, gamma, row_scale, weight, bias = ctx.saved_tensors
         pk = ctx.pk
         dout = _c(dout)
+        if ctx.fold:
+            g, cs = _take_aux(dout)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(x.shape[0], pk.k, dtype=torch.bfloat16, device=x.device)
+                ops.linear_dense(g, packed_dense_scaled_t(weight, gamma), pk.k, pk.n, None, EPI_BF16, out=dx)
+            dw, dgamma, db = _dense_fold_wgrad(g, x, weight, gamma, bias, cs, pk.n, pk.k)
+            return dx, dw, db, dgamma, dout, None, None, None
         if ctx.remap != (0, 0, 0):
             grp, extra, off = ctx.remap
             # gather the rows the GEMM wrote: [M/grp, grp + extra, D] -> rows off..off+grp of every group
@@ -210,6 +281,15 @@ class LinearResidualFn(torch.autograd.Function):
         return dx, dw, colsum, dgamma, dout, None, None, None
 
 
+def _dense_fold_wgrad(g, a, weight, gamma, bias, cs, n, k):
+    """wgrad + finalize of the gamma-folded backward for one nn.Linear: returns (dW, dgamma, dbias)."""
+    dw = ops.linear_dense_wgrad(g, a, n, k)
+    dgamma = torch.zeros_like(gamma)
+    db = torch.empty(n, dtype=torch.float32, device=g.device) if bias is not None else None
+    ops.layerscale_wgrad_finalize([(dw, weight.detach(), gamma.detach(), bias, cs if bias is not None else None, dgamma, db)])
+    return dw, dgamma, db
+
+
 class MlpResidualFn(torch.autograd.Function):
     """resid_out = resid + row_scale * gamma * bf16(fc2(gelu(fc1(x)))): the whole dense MLP branch of a block
     (timm Mlp + layer scale + DropPath + residual, deit/vit.py:126-134) as ONE autograd node, so that backward can
@@ -225,12 +305,14 @@ class MlpResidualFn(torch.autograd.Function):
         h = torch.empty(T, pk1.n, dtype=torch.bfloat16, device=x.device)
         pre = torch.empty_like(h) if train else None
         ops.linear_dense(x, pk1.w, pk1.n, pk1.k, b1, EPI_GELU_BF16, out=h, branch_out=pre)
-        need_branch = gamma is not None and ctx.needs_input_grad[5]
+        ctx.fold = (FOLD_GAMMA and gamma is not None and row_scale is None and isinstance(gamma, torch.nn.Parameter)
+                    and train)
+        need_branch = gamma is not None and ctx.needs_input_grad[5] and not ctx.fold
         out = torch.empty_like(resid)
         branch = torch.empty(T, pk2.n, dtype=torch.bfloat16, device=x.device) if need_branch else None
         ops.linear_dense(h, pk2.w, pk2.n, pk2.k, b2, EPI_RESID, gamma=gamma, resid_in=resid, resid_out=out,
                          row_scale=row_scale, rows_per_sample=rows_per_sample, branch_out=branch)
-        ctx.save_for_backward(x, pre, h, branch, gamma, row_scale)
+        ctx.save_for_backward(x, pre, h, branch, gamma, row_scale, w2, b2)
         ctx.pk = (pk1, pk2)
         ctx.rows_per_sample = rows_per_sample
         ctx.has_bias = (b1 is not None, b2 is not None)
@@ -238,15 +320,21 @@ class MlpResidualFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, pre, h, branch, gamma, row_scale = ctx.saved_tensors
+        x, pre, h, branch, gamma, row_scale, w2, b2 = ctx.saved_tensors
         pk1, pk2 = ctx.pk
         dout = _c(dout)
-        dy, dgamma, colsum2 = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
-                                                 want_colsum=ctx.has_bias[1])
         db1 = torch.zeros(pk1.n, dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
         dpre = torch.empty_like(pre)
-        ops.linear_dense(dy, pk2.w_t, pk2.k, pk2.n, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre, colsum=db1)
-        dw2 = ops.linear_dense_wgrad(dy, h, pk2.n, pk2.k) if ctx.needs_input_grad[3] else None
+        if ctx.fold:
+            g, cs = _take_aux(dout)
+            ops.linear_dense(g, packed_dense_scaled_t(w2, gamma), pk2.k, pk2.n, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre,
+                             colsum=db1)
+            dw2, dgamma, colsum2 = _dense_fold_wgrad(g, h, w2, gamma, b2, cs, pk2.n, pk2.k)
+        else:
+            dy, dgamma, colsum2 = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
+                                                     want_colsum=ctx.has_bias[1])
+            ops.linear_dense(dy, pk2.w_t, pk2.k, pk2.n, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre, colsum=db1)
+            dw2 = ops.linear_dense_wgrad(dy, h, pk2.n, pk2.k) if ctx.needs_input_grad[3] else None
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape[0], pk1.k, dtype=torch.bfloat16, device=x.device)
@@ -286,7 +374,12 @@ class LayerNormFn(torch.autograd.Function):
         dy = _c(dy)
         if dskip is not None:
             dskip = _c(dskip)
-        dx, dalpha, dbeta = ops.layernorm_bwd(dy, x, stats, alpha, ctx.d8, dx_in=dskip)
+        if FOLD_GAMMA and ctx.passthrough and dskip is not None:
+            # x is the output of a residual branch: hand its backward the bf16 copy and the column sums of dx
+            dx, dalpha, dbeta, dxb, dxs = ops.layernorm_bwd(dy, x, stats, alpha, ctx.d8, dx_in=dskip, want_aux=True)
+            _park_aux(dx, dxb, dxs)
+        else:
+            dx, dalpha, dbeta = ops.layernorm_bwd(dy, x, stats, alpha, ctx.d8, dx_in=dskip)
         return dx, dalpha, (dbeta if ctx.has_beta else None), None, None, None, None
 
 

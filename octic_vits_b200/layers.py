@@ -309,8 +309,9 @@ def _branch_residual(lin: LinearD8, a: Tensor, scale_mod, x: Tensor, row_scale: 
     """x + row_scale * gamma * lin(a) with everything after the GEMM fused into its epilogue."""
     B, N, D = x.shape
     gamma = scale_mod.packed_alpha() if scale_mod is not None else None
+    gamma_src = tuple(scale_mod.parameters()) if scale_mod is not None else None
     out = OF.LinearD8ResidualFn.apply(_as_bf16(_rows(a)), *lin.weights(), lin.lin_A1.bias, gamma, _rows(x), row_scale, N,
-                                      dgrad_heads)
+                                      dgrad_heads, gamma_src)
     return out.view(B, N, D)
 
 

@@ -79,6 +79,25 @@ def pack_linear_d8(wA1, wA2, wB1, wB2, wE, need_t: bool = True) -> PackedD8:
     return PackedD8(w1d, wEp, w1d_t, wE_t, 8 * ci, 8 * co)
 
 
+def pack_linear_d8_scaled_t(wA1, wA2, wB1, wB2, wE, gamma: torch.Tensor) -> PackedD8:
+    """Transposed packs of diag(gamma) W only (gamma = packed [Dout] vector): dgrad operand of the gamma-folded
+    layer-scale backward.  The forward fields of the result are None."""
+    co, ci = wA1.shape
+    dev = wA1.device
+    w1d_t = torch.empty(4 * ci, roundup64(co), dtype=torch.bfloat16, device=dev)
+    wE_t = torch.empty(2 * ci, roundup64(2 * co), dtype=torch.bfloat16, device=dev)
+    call("octic_linear_d8_pack_weights_scaled", wA1.data_ptr(), wA2.data_ptr(), wB1.data_ptr(), wB2.data_ptr(),
+         wE.data_ptr(), gamma.data_ptr(), 8 * ci, 8 * co, w1d_t.data_ptr(), wE_t.data_ptr(), _stream())
+    return PackedD8(None, None, w1d_t, wE_t, 8 * ci, 8 * co)
+
+
+def pack_linear_scaled_t(w: torch.Tensor, gamma: torch.Tensor) -> torch.Tensor:
+    n, k = w.shape
+    wt = torch.empty(k, roundup64(n), dtype=torch.bfloat16, device=w.device)
+    call("octic_linear_pack_weights_scaled", w.data_ptr(), gamma.data_ptr(), n, k, wt.data_ptr(), _stream())
+    return wt
+
+
 @dataclass
 class PackedDense:
     w: torch.Tensor        # [N, roundup64(K)]
@@ -256,17 +275,32 @@ def layernorm_fwd(x: torch.Tensor, alpha: torch.Tensor, beta: Optional[torch.Ten
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, alpha: torch.Tensor, d8: bool,
-                  dx_in: Optional[torch.Tensor] = None):
-    """returns (dx [= dx_in + LN^T dy], dalpha [D], dbeta [C or D])"""
+                  dx_in: Optional[torch.Tensor] = None, want_aux: bool = False):
+    """returns (dx [= dx_in + LN^T dy], dalpha [D], dbeta [C or D]) and, with want_aux, (bf16(dx), colsum(dx) [D])"""
     T, D = x.shape
     dx = torch.empty(T, D, dtype=torch.float32, device=x.device)
     nb = D // 8 if d8 else D
-    flat = torch.zeros(D + nb, dtype=torch.float32, device=x.device)
-    dalpha, dbeta = flat[:D], flat[D:]
+    flat = torch.zeros(D + nb + (D if want_aux else 0), dtype=torch.float32, device=x.device)
+    dalpha, dbeta = flat[:D], flat[D:D + nb]
+    dxb = torch.empty(T, D, dtype=torch.bfloat16, device=x.device) if want_aux else None
+    dxs = flat[D + nb:] if want_aux else None
     call("octic_layernorm_d8_bwd" if d8 else "octic_layernorm_bwd", dy.data_ptr(), dy.stride(0), _dt(dy),
          x.data_ptr(), x.stride(0), stats.data_ptr(), alpha.data_ptr(), _ptr(dx_in), dx.data_ptr(), dx.stride(0),
-         dalpha.data_ptr(), dbeta.data_ptr(), T, D, _stream())
+         dalpha.data_ptr(), dbeta.data_ptr(), T, D, _ptr(dxb), _ptr(dxs), _stream())
+    if want_aux:
+        return dx, dalpha, dbeta, dxb, dxs
     return dx, dalpha, dbeta
+
+
+def layerscale_wgrad_finalize(segs) -> None:
+    """segs: list of (dw, w, gamma, bias, cs, dgamma, dbias) -- see octic_layerscale_wgrad_finalize in octic_b200.h."""
+    arr = (_lib.LsFinSeg * len(segs))()
+    for a, (dw, w, gamma, bias, cs, dgamma, dbias) in zip(arr, segs):
+        if not (dw.is_contiguous() and w.is_contiguous() and dw.shape == w.shape):
+            raise _lib.OcticError("finalize: dw / w must be contiguous and of equal shape")
+        a.dw, a.w, a.N, a.K = dw.data_ptr(), w.data_ptr(), w.shape[0], w.shape[1]
+        a.gamma, a.bias, a.cs, a.dgamma, a.dbias = gamma.data_ptr(), _ptr(bias), _ptr(cs), _ptr(dgamma), _ptr(dbias)
+    call("octic_layerscale_wgrad_finalize", arr, len(segs), _stream())
 
 
 def layerscale_bwd(dres: torch.Tensor, branch: Optional[torch.Tensor], gamma: Optional[torch.Tensor],

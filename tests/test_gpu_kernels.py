@@ -294,6 +294,13 @@ def test_layernorm_plain(T, D):
     assert_close(db, br.grad, rtol=1e-4, atol=2e-3)
     dxb, _, _ = ops.layernorm_bwd(bf(dy), x, stats, w, d8=False)
     assert_close(dxb, xin.grad, rtol=2e-2, atol=2e-2)
+    # by-products for the gamma-folded layer-scale backward: bf16 copy and column sums of dx (incl. the skip gradient)
+    extra = torch.randn(T, D, device=DEV)
+    dx2, dw2, db2, g16, cs = ops.layernorm_bwd(dy, x, stats, w, d8=False, dx_in=extra, want_aux=True)
+    assert_close(dx2, xin.grad + extra, rtol=1e-4, atol=1e-4)
+    assert_close(dw2, wr.grad, rtol=1e-4, atol=2e-3)
+    assert torch.equal(g16, bf(dx2))
+    assert_close(cs, dx2.sum(0), rtol=1e-4, atol=2e-3 * math.sqrt(T))
 
 
 def test_layerscale_bwd():
@@ -311,6 +318,57 @@ def test_layerscale_bwd():
     dy2, dg2, cs2 = ops.layerscale_bwd(dres, None, None, None, 1, want_colsum=False)
     assert dg2 is None and cs2 is None
     assert_close(dy2, dres, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("dense", [True, False])
+def test_gamma_folded_layerscale_backward(dense):
+    """x + gamma * Linear(a) without DropPath: the gamma-folded backward (scaled dgrad packs + raw wgrad + finalize, no
+    saved branch) against torch autograd of the same bf16-operand computation (reference octic_vits/d8_layers.py:698-707,
+    deit/vit.py:131-134)."""
+    from octic_vits_b200 import functional as OF
+    g = torch.Generator().manual_seed(11)
+    T, D = 771, 256
+    a = bf(torch.randn(T, D, generator=g)).to(DEV)
+    resid = torch.randn(T, D, generator=g).to(DEV)
+    dres = torch.randn(T, D, generator=g).to(DEV)
+    if dense:
+        w = torch.nn.Parameter((torch.randn(D, D, generator=g) / math.sqrt(D)).to(DEV))
+        b = torch.nn.Parameter(torch.randn(D, generator=g).to(DEV))
+        gamma = torch.nn.Parameter((0.5 + torch.rand(D, generator=g)).to(DEV))
+        ar = a.clone().requires_grad_(True)
+        out = OF.LinearResidualFn.apply(ar, w, b, gamma, resid, None, 1, (0, 0, 0))
+        out.backward(dres)
+        got = dict(dx=ar.grad, dw=w.grad, db=b.grad, dgamma=gamma.grad)
+        a32 = a.float().requires_grad_(True)
+        w32, b32, g32 = (t.detach().clone().requires_grad_(True) for t in (w, b, gamma))
+        branch = (a32 @ bf(w32).float().T + b32)
+        (resid + g32 * branch).backward(dres)
+        want = dict(dx=a32.grad, dw=w32.grad, db=b32.grad, dgamma=g32.grad)
+    else:
+        C = D // 8
+        wd = d8_weights(D, D, seed=5)
+        names = ["A1", "A2", "B1", "B2", "E"]
+        ws = [torch.nn.Parameter(wd[f"lin_{n}.weight"]) for n in names]
+        b = torch.nn.Parameter(wd["lin_A1.bias"])
+        alphas = [torch.nn.Parameter((0.5 + torch.rand(C if n != "E" else 2 * C, generator=g)).to(DEV)) for n in names]
+        gamma = torch.cat(alphas + [alphas[4]])
+        ar = a.clone().requires_grad_(True)
+        out = OF.LinearD8ResidualFn.apply(ar, *ws, b, gamma, resid, None, 1, 0, tuple(alphas))
+        out.backward(dres)
+        got = dict(dx=ar.grad, db=b.grad, **{f"dw{n}": w_.grad for n, w_ in zip(names, ws)},
+                   **{f"dg{n}": a_.grad for n, a_ in zip(names, alphas)})
+        a32 = a.float().requires_grad_(True)
+        wr = {f"lin_{n}.weight": bf(w_.detach()).float().requires_grad_(True) for n, w_ in zip(names, ws)}
+        wr["lin_A1.bias"] = b.detach().clone().requires_grad_(True)
+        al = [a_.detach().clone().requires_grad_(True) for a_ in alphas]
+        branch = O.pack_rows(O.linear_d8(O.unpack_rows(a32.reshape(1, T, D)), wr, "")).reshape(T, D)
+        (resid + torch.cat(al + [al[4]]) * branch).backward(dres)
+        want = dict(dx=a32.grad, db=wr["lin_A1.bias"].grad, **{f"dw{n}": wr[f"lin_{n}.weight"].grad for n in names},
+                    **{f"dg{n}": a_.grad for n, a_ in zip(names, al)})
+    scale = math.sqrt(T)
+    for k in want:
+        tol = 3e-2 if k == "dx" else 2e-2 * scale
+        assert_close(got[k].float(), want[k], rtol=2e-2, atol=tol)
 
 
 def test_colsum_and_cast():
