@@ -170,7 +170,7 @@ def run_ours(args):
     B = args.batch
     model = create_model(MODEL["name"], num_classes=MODEL["classes"], drop_path_rate=args.drop_path).to(dev).train()
     # one flat fp32 gradient buffer: .grad tensors are views, the all-reduce is a single NCCL call over NVLink
-    from octic_vits_b200.parallel import FlatGrads
+    from octic_vits_b200.parallel import FlatGrads, GraphedTrainStep
     fg = FlatGrads(model.parameters())
     flat = fg.flat
 
@@ -179,13 +179,17 @@ def run_ours(args):
     img_host = torch.randn(B, 3, MODEL["img"], MODEL["img"]).pin_memory()
     tgt_host = torch.randint(0, MODEL["classes"], (B,)).pin_memory()
 
-    def step(img, tgt):
+    def eager_step(img, tgt):
         flat.zero_()
         logits = model(img)
         loss = torch.nn.functional.cross_entropy(logits, tgt)
         loss.backward()
         fg.all_reduce()
         return loss
+
+    # public-API step: fwd + loss + bwd captured in a CUDA graph (parallel.GraphedTrainStep), all-reduce after the replay
+    gstep = GraphedTrainStep(model, fg, img_dev.shape, warmup=args.warmup, use_graph=not args.no_graph)
+    step = gstep if gstep.graphed else eager_step
 
     def barrier():
         if world > 1:
@@ -214,24 +218,29 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    _lib.STATS.reset()
     ms_dev = timed(lambda: step(img_dev, tgt_dev), args.steps)
-    launches = _lib.STATS.kernel_launches
     clocks = sampler.stop() if rank == 0 else None
+    # launches of our kernels inside the timed region: counted on one eager step (a graph replay launches the same nodes)
+    _lib.STATS.reset()
+    eager_step(img_dev, tgt_dev)
+    torch.cuda.synchronize()
+    launches = _lib.STATS.kernel_launches * args.steps
 
     # dominant kernel: the tcgen05 grouped GEMM.  Time every launch of it with CUDA events on the launching stream
     # during extra (untimed-for-the-headline) steps, so the headline number carries no event overhead.
     _lib.STATS.reset()
     _lib.STATS.profile_prefixes = ("octic_gemm_bf16", "octic_linear_d8_fwd", "octic_linear_d8_dgrad")
-    step(img_dev, tgt_dev)
+    eager_step(img_dev, tgt_dev)
     torch.cuda.synchronize()
     gemm_ms, gemm_flops, gemm_calls = _lib.STATS.collect()
     _lib.STATS.profile_prefixes = ()
 
     def e2e_step():
+        if gstep.graphed:
+            return gstep(img_host, tgt_host).item()      # H2D copies into the graph's static inputs, replay, loss D2H
         img = img_host.to(dev, non_blocking=True)
         tgt = tgt_host.to(dev, non_blocking=True)
-        return step(img, tgt).item()
+        return eager_step(img, tgt).item()
     e2e_step()
     ms_e2e = timed(e2e_step, max(2, args.steps // 2))
 
@@ -251,6 +260,7 @@ def run_ours(args):
                                    "DeiT-III training step: fwd + bwd" + (" + NCCL grad all-reduce" if world > 1 else ""),
                        "img": MODEL["img"], "batch_per_gpu": B, "global_batch": world * B, "tokens_per_image": 257,
                        "drop_path": args.drop_path, "parallelism": f"dp{world}", "optimizer_step": False,
+                       "cuda_graph": bool(gstep.graphed),
                        "l2": "activations per step (>50 GB) exceed the 126 MB L2; no explicit flush"},
             "model_tflops": ips * flops_img / 1e12,
             "tc_util_vs_sustained_peak": ips * flops_img / 1e12 / (world * peaks["tf_sustained"]),
@@ -280,6 +290,7 @@ def main():
     ap.add_argument("--drop-path", type=float, default=0.0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the captured CUDA graph")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
