@@ -109,13 +109,16 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(leader_smem_u32(leader_bar)), "r"(x), "r"(y)
       : "memory");
 }
-// arrive on the barrier at this shared-memory offset in CTA `rank` of the cluster
+// arrive on the barrier at this shared-memory offset in CTA `rank` of the cluster.  Default semantics (release at CTA
+// scope) on purpose: .release.cluster compiles to MEMBAR.ALL.GPU, which made every epilogue warp wait for all of its
+// outstanding global stores before it could hand the TMEM stage back (33 % of the stall samples of the pair kernels,
+// profiles/r01_ncu_s5.md).  The hand-off only orders tcgen05.ld (tcgen05.wait::ld + fence::before_thread_sync).
 __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
   asm volatile(
       "{\n\t"
       ".reg .b32 ra;\n\t"
       "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
       "}\n" ::"r"(smem_u32(bar)), "r"(rank)
       : "memory");
 }
