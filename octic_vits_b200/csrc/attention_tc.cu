@@ -114,11 +114,43 @@ __device__ __forceinline__ void store_tile(const uint8_t* stg, __nv_bfloat16* ds
   const int u = tid % NU, r0 = tid / NU;
   if (r0 >= rpi) return;
   const int col = cb[u] + (sm != nullptr ? s * sm[u] : 0);
-  for (int r = r0; r < nvalid; r += rpi) {
-    const uint8_t* sp = stg + r * (HD * 2) + u * GRAN;
-    __nv_bfloat16* gp = dst + static_cast<long>(r) * ld + col;
-    if (GRAN == 16) *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
-    else *reinterpret_cast<uint32_t*>(gp) = *reinterpret_cast<const uint32_t*>(sp);
+  // a thread keeps its column unit and walks the rows: shared-memory address and global pointer advance by constants,
+  // four rows are loaded before they are stored (the 4-byte scatter of the octic layouts is instruction bound)
+  uint32_t sa = smem_u32(stg) + r0 * (HD * 2) + u * GRAN;
+  uint8_t* gp = reinterpret_cast<uint8_t*>(dst + static_cast<long>(r0) * ld + col);
+  const uint32_t sstep = rpi * (HD * 2);
+  const long gstep = static_cast<long>(rpi) * ld * 2;
+  int r = r0;
+  if (GRAN == 16) {
+    for (; r + 3 * rpi < nvalid; r += 4 * rpi) {
+      uint4 v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w) : "r"(sa + i * sstep));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(gp + i * gstep) = v[i];
+      sa += 4 * sstep; gp += 4 * gstep;
+    }
+    for (; r < nvalid; r += rpi) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sa));
+      *reinterpret_cast<uint4*>(gp) = v;
+      sa += sstep; gp += gstep;
+    }
+  } else {
+    for (; r + 3 * rpi < nvalid; r += 4 * rpi) {
+      uint32_t v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v[i]) : "r"(sa + i * sstep));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) *reinterpret_cast<uint32_t*>(gp + i * gstep) = v[i];
+      sa += 4 * sstep; gp += 4 * gstep;
+    }
+    for (; r < nvalid; r += rpi) {
+      uint32_t v;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sa));
+      *reinterpret_cast<uint32_t*>(gp) = v;
+      sa += sstep; gp += gstep;
+    }
   }
 }
 

@@ -62,6 +62,8 @@ class GraphedTrainStep:
         loss = step(images, targets)                             # copies into the static inputs, replays, all-reduces
 
     Inputs may live on the host (pinned) or on the device; gradients land in `fg.flat` (the parameters' .grad views).
+    Input pipeline: `stage(images, targets)` starts the host -> device copy of a batch on a copy stream (it overlaps the
+    step that is still running) and `run()` consumes the staged batch; `step(images, targets)` = stage + run.
     The gradient all-reduce stays outside the graph: it is a single NCCL call per step.  If capture is impossible
     (e.g. an op that synchronises), `graphed` is False and every call runs the eager step instead.
     """
@@ -73,6 +75,11 @@ class GraphedTrainStep:
         dev = flat_grads.flat.device
         self.img = torch.zeros(tuple(image_shape), device=dev)
         self.tgt = torch.zeros(image_shape[0], dtype=target_dtype, device=dev)
+        self._stage_img, self._stage_tgt = torch.zeros_like(self.img), torch.zeros_like(self.tgt)
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staged = torch.cuda.Event()
+        self._consumed = torch.cuda.Event()
+        self._consumed.record()
         self.graph, self.loss, self.graphed = None, None, False
         if not use_graph:
             return
@@ -98,9 +105,29 @@ class GraphedTrainStep:
         loss.backward()
         return loss
 
+    def stage(self, images: torch.Tensor, targets: torch.Tensor) -> None:
+        """Start copying a batch into the staging buffers on the copy stream (after the previous batch was consumed)."""
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed)
+            self._stage_img.copy_(images, non_blocking=True)
+            self._stage_tgt.copy_(targets, non_blocking=True)
+            self._staged.record()
+
+    def run(self) -> torch.Tensor:
+        """One step on the staged batch (device -> device copy into the graph's static inputs, replay, all-reduce)."""
+        cur = torch.cuda.current_stream(self.img.device)
+        cur.wait_event(self._staged)
+        self.img.copy_(self._stage_img, non_blocking=True)
+        self.tgt.copy_(self._stage_tgt, non_blocking=True)
+        self._consumed.record(cur)
+        return self._launch()
+
     def __call__(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         self.img.copy_(images, non_blocking=True)
         self.tgt.copy_(targets, non_blocking=True)
+        return self._launch()
+
+    def _launch(self) -> torch.Tensor:
         if self.graphed:
             self.graph.replay()
             loss = self.loss

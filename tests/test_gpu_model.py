@@ -271,5 +271,9 @@ def test_graphed_train_step_matches_eager():
     # wgrad accumulates with fp32 red.add in a non-deterministic order: equal up to summation order
     assert rel_err(grads_g, fg.flat) < 1e-4
     # a second replay with new inputs changes the result (the static inputs are really read)
-    loss_g2 = float(step(torch.randn_like(img), tgt))
+    img2 = torch.randn_like(img)
+    loss_g2 = float(step(img2, tgt))
     assert loss_g2 != loss_g
+    # staged input pipeline (pinned host batch -> copy stream -> static inputs) gives the same step
+    step.stage(img2.cpu().pin_memory(), tgt.cpu().pin_memory())
+    assert abs(float(step.run()) - loss_g2) <= 1e-5 * max(1.0, abs(loss_g2))

@@ -1,0 +1,11 @@
+#!/usr/bin/env bash
+# final checks of the session: all tests, attention microbench (leaner store_tile), bench (staged e2e), event table
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+( time timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -6 ) > gpurun_out/pytest_gpu.log 2>&1
+cat gpurun_out/pytest_gpu.log
+timeout 120 python tools/microbench_ops.py --batch 128 --only attn_ 2>&1 | tail -3
+timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err
+cat gpurun_out/bench.json; tail -2 gpurun_out/bench.err | cut -c1-300
+timeout 300 python tools/profile_step.py --batch 128 --events > gpurun_out/events_b128.txt 2>&1
+cat gpurun_out/events_b128.txt
