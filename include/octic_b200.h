@@ -203,6 +203,7 @@ typedef struct {
   const float* gamma;                        /* fp32 [N]                                        */
   const float* bias; const float* cs;        /* fp32 [N] or NULL                                */
   float* dgamma; float* dbias;               /* fp32 [N] or NULL; dgamma accumulates            */
+  float* dw_acc;                             /* optional fp32 [N, K]: dw_acc += gamma dW_raw (the parameter's .grad), dw untouched */
 } octic_lsfin_seg;
 int octic_layerscale_wgrad_finalize(const octic_lsfin_seg* segs, int nseg, void* stream);
 

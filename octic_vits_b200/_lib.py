@@ -61,7 +61,8 @@ class WgradDesc(C.Structure):
 
 class LsFinSeg(C.Structure):
     _fields_ = [("dw", C.c_void_p), ("w", C.c_void_p), ("N", C.c_int), ("K", C.c_int), ("gamma", C.c_void_p),
-                ("bias", C.c_void_p), ("cs", C.c_void_p), ("dgamma", C.c_void_p), ("dbias", C.c_void_p)]
+                ("bias", C.c_void_p), ("cs", C.c_void_p), ("dgamma", C.c_void_p), ("dbias", C.c_void_p),
+                ("dw_acc", C.c_void_p)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float

@@ -666,6 +666,7 @@ __global__ void __maxnreg__(96) layernorm_bwd_kernel(const TDY* __restrict__ dy,
 //   dW[n, :]   = gamma[n] * dW_raw[n, :]   (in place),   dbias[n] = gamma[n] * cs[n]
 struct LsFinSeg {
   float* dw; const float* w; int N, K; const float* gamma; const float* bias; const float* cs; float* dgamma; float* dbias;
+  float* dw_acc;   // optional: dw_acc += gamma * dW_raw (gradient accumulation fused), dW_raw left untouched
 };
 struct LsFinParams { int nseg; int row_begin[9]; LsFinSeg seg[8]; };
 __global__ void __launch_bounds__(128) layerscale_finalize_kernel(const __grid_constant__ LsFinParams p) {
@@ -677,10 +678,11 @@ __global__ void __launch_bounds__(128) layerscale_finalize_kernel(const __grid_c
     const LsFinSeg& S = p.seg[sg];
     const int n = row - p.row_begin[sg];
     float* dwr = S.dw + static_cast<long>(n) * S.K;
+    float* accr = S.dw_acc != nullptr ? S.dw_acc + static_cast<long>(n) * S.K : nullptr;
     const float* wr = S.w + static_cast<long>(n) * S.K;
     const float g = S.gamma[n];
     float dot = 0.f;
-    if ((S.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(dwr) | reinterpret_cast<uintptr_t>(wr)) & 15) == 0) {
+    if ((S.K & 3) == 0 && ((reinterpret_cast<uintptr_t>(dwr) | reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(accr)) & 15) == 0) {
       // four float4 column groups in flight per lane
       const int k4 = S.K >> 2;
       float4* d4 = reinterpret_cast<float4*>(dwr);
@@ -697,7 +699,13 @@ __global__ void __launch_bounds__(128) layerscale_finalize_kernel(const __grid_c
           const int k = k0 + 32 * u;
           if (k < k4) {
             dot = fmaf(wv[u].x, dv[u].x, fmaf(wv[u].y, dv[u].y, fmaf(wv[u].z, dv[u].z, fmaf(wv[u].w, dv[u].w, dot))));
-            d4[k] = make_float4(g * dv[u].x, g * dv[u].y, g * dv[u].z, g * dv[u].w);
+            if (accr != nullptr) {
+              float4* a4 = reinterpret_cast<float4*>(accr) + k;
+              const float4 a = *a4;
+              *a4 = make_float4(fmaf(g, dv[u].x, a.x), fmaf(g, dv[u].y, a.y), fmaf(g, dv[u].z, a.z), fmaf(g, dv[u].w, a.w));
+            } else {
+              d4[k] = make_float4(g * dv[u].x, g * dv[u].y, g * dv[u].z, g * dv[u].w);
+            }
           }
         }
       }
@@ -705,7 +713,8 @@ __global__ void __launch_bounds__(128) layerscale_finalize_kernel(const __grid_c
       for (int k = lane; k < S.K; k += 32) {
         const float d = dwr[k];
         dot = fmaf(wr[k], d, dot);
-        dwr[k] = g * d;
+        if (accr != nullptr) accr[k] = fmaf(g, d, accr[k]);
+        else dwr[k] = g * d;
       }
     }
 #pragma unroll
@@ -1104,6 +1113,7 @@ int octic_layerscale_wgrad_finalize(const octic_lsfin_seg* segs, int nseg, void*
     LsFinSeg& S = p.seg[i];
     S.dw = segs[i].dw; S.w = segs[i].w; S.N = segs[i].N; S.K = segs[i].K; S.gamma = segs[i].gamma;
     S.bias = segs[i].bias; S.cs = segs[i].cs; S.dgamma = segs[i].dgamma; S.dbias = segs[i].dbias;
+    S.dw_acc = segs[i].dw_acc;
   }
   p.row_begin[nseg] = rows;
   const int grid = (rows + 3) / 4 < 148 * 16 ? (rows + 3) / 4 : 148 * 16;

@@ -66,7 +66,20 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 # With DropPath (row_scale) or FOLD_GAMMA = False the branch-saving path (octic_layerscale_bwd) is used.
 # ----------------------------------------------------------------------------------------------------------------
 FOLD_GAMMA = True
+# Weight gradients go straight into an existing fp32 `.grad` (the wgrad kernels accumulate with red.add anyway) and the
+# Function returns None for that parameter: no zero fill, no autograd accumulation kernel.  Opt-in (parallel.FlatGrads
+# switches it on): tensor hooks on those parameters do not see the gradient.
+ACCUMULATE_INTO_GRAD = False
 _aux_slot = None     # (data_ptr, shape, bf16 copy, column sums) of the most recent layer-norm backward output
+
+
+def _grad_target(p):
+    if not ACCUMULATE_INTO_GRAD or not isinstance(p, torch.nn.Parameter):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
 
 
 def _park_aux(dx: torch.Tensor, dxb: torch.Tensor, dxs: torch.Tensor) -> None:
@@ -114,6 +127,7 @@ class LinearD8Fn(torch.autograd.Function):
         ctx.pk = pk
         ctx.has_bias = bias is not None
         ctx.dgrad_heads = dgrad_heads
+        ctx.wparams = (wA1, wA2, wB1, wB2, wE)
         return y
 
     @staticmethod
@@ -122,7 +136,13 @@ class LinearD8Fn(torch.autograd.Function):
         pk = ctx.pk
         dy = _c(dy)
         dx = ops.linear_d8_dgrad(dy, pk, ctx.dgrad_heads) if ctx.needs_input_grad[0] else None
-        dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
+        dws = (None,) * 5
+        if any(ctx.needs_input_grad[1:6]):
+            tg = [_grad_target(w) for w in ctx.wparams]
+            if all(t is not None for t in tg):
+                ops.linear_d8_wgrad(dy, x, pk.din, pk.dout, targets=tg)
+            else:
+                dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout)
         db = ops.colsum_bf16(dy, pk.dout // 8) if (ctx.has_bias and ctx.needs_input_grad[6]) else None
         return (dx, *dws, db, None, None)
 
@@ -149,11 +169,14 @@ class LinearD8ResidualFn(torch.autograd.Function):
         ctx.rows_per_sample = rows_per_sample
         ctx.has_bias = bias is not None
         ctx.dgrad_heads = dgrad_heads
+        ctx.wparams = (wA1, wA2, wB1, wB2, wE)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, branch, gamma, row_scale, wA1, wA2, wB1, wB2, wE, bias = ctx.saved_tensors
+        tg = [_grad_target(w) for w in ctx.wparams]
+        fused = all(t is not None for t in tg)
         pk = ctx.pk
         dout = _c(dout)
         if ctx.fold:
@@ -169,15 +192,23 @@ class LinearD8ResidualFn(torch.autograd.Function):
             gam = gamma.detach()
             segs = [(dws[i], ws[i].detach(), gam[i * co:(i + 1) * co], bias if i == 0 else None,
                      cs[:co] if (i == 0 and ctx.has_bias) else None, dgamma[i * co:(i + 1) * co],
-                     db if i == 0 else None) for i in range(4)]
+                     db if i == 0 else None, tg[i] if fused else None) for i in range(4)]
             # both E rows share W_E and alpha_E: the whole gradient lands on the first copy of alpha_E in the packed vector
-            segs.append((dws[4], wE.detach(), gam[4 * co:6 * co], None, None, dgamma[4 * co:6 * co], None))
+            segs.append((dws[4], wE.detach(), gam[4 * co:6 * co], None, None, dgamma[4 * co:6 * co], None,
+                         tg[4] if fused else None))
             ops.layerscale_wgrad_finalize(segs)
+            if fused:
+                dws = (None,) * 5
             return (dx, *dws, db, dgamma, dout, None, None, None, None)
         dy, dgamma, colsum = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
                                                 want_colsum=ctx.has_bias)
         dx = ops.linear_d8_dgrad(dy, pk, ctx.dgrad_heads) if ctx.needs_input_grad[0] else None
-        dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout) if any(ctx.needs_input_grad[1:6]) else (None,) * 5
+        dws = (None,) * 5
+        if any(ctx.needs_input_grad[1:6]):
+            if fused:
+                ops.linear_d8_wgrad(dy, x, pk.din, pk.dout, targets=tg)
+            else:
+                dws = ops.linear_d8_wgrad(dy, x, pk.din, pk.dout)
         db = colsum[: pk.dout // 8] if ctx.has_bias else None
         return (dx, *dws, db, dgamma, dout, None, None, None, None)
 
@@ -202,6 +233,7 @@ class LinearFn(torch.autograd.Function):
             ops.linear_dense(x, pk.w, n, k, bias, EPI_F32 if out_f32 else EPI_BF16, out=y)
         ctx.save_for_backward(x, pre)
         ctx.pk, ctx.gelu, ctx.has_bias = pk, gelu, bias is not None
+        ctx.wparam = weight
         return y
 
     @staticmethod
@@ -225,7 +257,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape[0], k, dtype=torch.bfloat16, device=x.device)
             ops.linear_dense(dy, pk.w_t, k, n, None, EPI_BF16, out=dx)
-        dw = ops.linear_dense_wgrad(dy, x, n, k) if ctx.needs_input_grad[1] else None
+        dw = _dense_wgrad(dy, x, n, k, ctx.wparam) if ctx.needs_input_grad[1] else None
         return dx, dw, db, None, None
 
 
@@ -248,6 +280,7 @@ class LinearResidualFn(torch.autograd.Function):
                          row_scale=row_scale, rows_per_sample=rows_per_sample, branch_out=branch, remap=remap)
         ctx.save_for_backward(x, branch, gamma, row_scale, weight, bias)
         ctx.pk, ctx.rows_per_sample, ctx.has_bias, ctx.remap = pk, rows_per_sample, bias is not None, remap
+        ctx.wparam = weight
         return out
 
     @staticmethod
@@ -261,7 +294,7 @@ class LinearResidualFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = torch.empty(x.shape[0], pk.k, dtype=torch.bfloat16, device=x.device)
                 ops.linear_dense(g, packed_dense_scaled_t(weight, gamma), pk.k, pk.n, None, EPI_BF16, out=dx)
-            dw, dgamma, db = _dense_fold_wgrad(g, x, weight, gamma, bias, cs, pk.n, pk.k)
+            dw, dgamma, db = _dense_fold_wgrad(g, x, weight, gamma, bias, cs, pk.n, pk.k, ctx.wparam)
             return dx, dw, db, dgamma, dout, None, None, None
         if ctx.remap != (0, 0, 0):
             grp, extra, off = ctx.remap
@@ -277,17 +310,29 @@ class LinearResidualFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape[0], pk.k, dtype=torch.bfloat16, device=x.device)
             ops.linear_dense(dy, pk.w_t, pk.k, pk.n, None, EPI_BF16, out=dx)
-        dw = ops.linear_dense_wgrad(dy, x, pk.n, pk.k) if ctx.needs_input_grad[1] else None
+        dw = _dense_wgrad(dy, x, pk.n, pk.k, ctx.wparam) if ctx.needs_input_grad[1] else None
         return dx, dw, colsum, dgamma, dout, None, None, None
 
 
-def _dense_fold_wgrad(g, a, weight, gamma, bias, cs, n, k):
-    """wgrad + finalize of the gamma-folded backward for one nn.Linear: returns (dW, dgamma, dbias)."""
+def _dense_fold_wgrad(g, a, weight, gamma, bias, cs, n, k, wparam=None):
+    """wgrad + finalize of the gamma-folded backward for one nn.Linear: returns (dW or None if accumulated into
+    wparam.grad, dgamma, dbias)."""
     dw = ops.linear_dense_wgrad(g, a, n, k)
     dgamma = torch.zeros_like(gamma)
     db = torch.empty(n, dtype=torch.float32, device=g.device) if bias is not None else None
-    ops.layerscale_wgrad_finalize([(dw, weight.detach(), gamma.detach(), bias, cs if bias is not None else None, dgamma, db)])
-    return dw, dgamma, db
+    tg = _grad_target(wparam)
+    ops.layerscale_wgrad_finalize([(dw, weight.detach(), gamma.detach(), bias, cs if bias is not None else None, dgamma, db,
+                                    tg)])
+    return (None if tg is not None else dw), dgamma, db
+
+
+def _dense_wgrad(dy, a, n, k, wparam):
+    """plain dense wgrad: accumulated into wparam.grad (returns None) or into a fresh buffer (returned)."""
+    tg = _grad_target(wparam)
+    if tg is not None:
+        ops.linear_dense_wgrad(dy, a, n, k, dw=tg)
+        return None
+    return ops.linear_dense_wgrad(dy, a, n, k)
 
 
 class MlpResidualFn(torch.autograd.Function):
@@ -316,6 +361,7 @@ class MlpResidualFn(torch.autograd.Function):
         ctx.pk = (pk1, pk2)
         ctx.rows_per_sample = rows_per_sample
         ctx.has_bias = (b1 is not None, b2 is not None)
+        ctx.wparams = (w1, w2)
         return out
 
     @staticmethod
@@ -329,17 +375,17 @@ class MlpResidualFn(torch.autograd.Function):
             g, cs = _take_aux(dout)
             ops.linear_dense(g, packed_dense_scaled_t(w2, gamma), pk2.k, pk2.n, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre,
                              colsum=db1)
-            dw2, dgamma, colsum2 = _dense_fold_wgrad(g, h, w2, gamma, b2, cs, pk2.n, pk2.k)
+            dw2, dgamma, colsum2 = _dense_fold_wgrad(g, h, w2, gamma, b2, cs, pk2.n, pk2.k, ctx.wparams[1])
         else:
             dy, dgamma, colsum2 = ops.layerscale_bwd(dout, branch, gamma, row_scale, ctx.rows_per_sample,
                                                      want_colsum=ctx.has_bias[1])
             ops.linear_dense(dy, pk2.w_t, pk2.k, pk2.n, None, EPI_GELU_BWD, out=dpre, gelu_pre=pre, colsum=db1)
-            dw2 = ops.linear_dense_wgrad(dy, h, pk2.n, pk2.k) if ctx.needs_input_grad[3] else None
+            dw2 = _dense_wgrad(dy, h, pk2.n, pk2.k, ctx.wparams[1]) if ctx.needs_input_grad[3] else None
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(x.shape[0], pk1.k, dtype=torch.bfloat16, device=x.device)
             ops.linear_dense(dpre, pk1.w_t, pk1.k, pk1.n, None, EPI_BF16, out=dx)
-        dw1 = ops.linear_dense_wgrad(dpre, x, pk1.n, pk1.k) if ctx.needs_input_grad[1] else None
+        dw1 = _dense_wgrad(dpre, x, pk1.n, pk1.k, ctx.wparams[0]) if ctx.needs_input_grad[1] else None
         return dx, dw1, db1, dw2, colsum2, dgamma, dout, None, None
 
 

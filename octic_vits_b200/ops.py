@@ -181,13 +181,18 @@ def linear_d8_dgrad(dy: torch.Tensor, pk: PackedD8, head_H: int = 0) -> torch.Te
     return dx
 
 
-def linear_d8_wgrad(dy: torch.Tensor, x: torch.Tensor, din: int, dout: int):
+def linear_d8_wgrad(dy: torch.Tensor, x: torch.Tensor, din: int, dout: int, targets=None):
+    """dW_* (+)= dy^T x per irrep.  targets: five fp32 tensors to accumulate into (the parameters' .grad) instead of a
+    fresh zeroed buffer."""
     _req(dy, torch.bfloat16, "dy")
     _req(x, torch.bfloat16, "x")
     ci, co = din // 8, dout // 8
-    flat = torch.zeros(8 * co * ci, dtype=torch.float32, device=x.device)      # one fill for all five gradients
-    dws = [flat[i * co * ci:(i + 1) * co * ci].view(co, ci) for i in range(4)]
-    dwE = flat[4 * co * ci:].view(2 * co, 2 * ci)
+    if targets is not None:
+        dws, dwE = list(targets[:4]), targets[4]
+    else:
+        flat = torch.zeros(8 * co * ci, dtype=torch.float32, device=x.device)      # one fill for all five gradients
+        dws = [flat[i * co * ci:(i + 1) * co * ci].view(co, ci) for i in range(4)]
+        dwE = flat[4 * co * ci:].view(2 * co, 2 * ci)
     call("octic_linear_d8_wgrad", dy.data_ptr(), x.data_ptr(), x.shape[0], din, dout, dws[0].data_ptr(),
          dws[1].data_ptr(), dws[2].data_ptr(), dws[3].data_ptr(), dwE.data_ptr(), _stream(),
          flops=2.0 * x.shape[0] * din * dout * 3 / 16)
@@ -293,9 +298,10 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, alpha:
 
 
 def layerscale_wgrad_finalize(segs) -> None:
-    """segs: list of (dw, w, gamma, bias, cs, dgamma, dbias) -- see octic_layerscale_wgrad_finalize in octic_b200.h."""
+    """segs: list of (dw, w, gamma, bias, cs, dgamma, dbias, dw_acc) -- see octic_layerscale_wgrad_finalize in octic_b200.h."""
     arr = (_lib.LsFinSeg * len(segs))()
-    for a, (dw, w, gamma, bias, cs, dgamma, dbias) in zip(arr, segs):
+    for a, (dw, w, gamma, bias, cs, dgamma, dbias, dw_acc) in zip(arr, segs):
+        a.dw_acc = _ptr(dw_acc)
         if not (dw.is_contiguous() and w.is_contiguous() and dw.shape == w.shape):
             raise _lib.OcticError("finalize: dw / w must be contiguous and of equal shape")
         a.dw, a.w, a.N, a.K = dw.data_ptr(), w.data_ptr(), w.shape[0], w.shape[1]

@@ -27,7 +27,7 @@ class FlatGrads:
         fg.zero(); loss.backward(); fg.all_reduce()      # grads are now the mean over ranks
     """
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], fuse_accumulation: bool = True):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -37,6 +37,10 @@ class FlatGrads:
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        if fuse_accumulation:
+            # the wgrad kernels add straight into these views (no zero fill + autograd accumulation kernel per weight)
+            from . import functional as OF
+            OF.ACCUMULATE_INTO_GRAD = True
 
     def zero(self) -> None:
         self.flat.zero_()

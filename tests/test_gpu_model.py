@@ -274,6 +274,18 @@ def test_graphed_train_step_matches_eager():
     img2 = torch.randn_like(img)
     loss_g2 = float(step(img2, tgt))
     assert loss_g2 != loss_g
+    # fused gradient accumulation (wgrad kernels add straight into the flat .grad views; FlatGrads switched it on)
+    # against plain autograd accumulation
+    from octic_vits_b200 import functional as OF
+    assert OF.ACCUMULATE_INTO_GRAD
+    OF.ACCUMULATE_INTO_GRAD = False
+    try:
+        float(eager(img2, tgt))
+        plain = fg.flat.clone()
+    finally:
+        OF.ACCUMULATE_INTO_GRAD = True
+    float(eager(img2, tgt))
+    assert rel_err(fg.flat, plain) < 1e-4
     # staged input pipeline (pinned host batch -> copy stream -> static inputs) gives the same step
     step.stage(img2.cpu().pin_memory(), tgt.cpu().pin_memory())
     assert abs(float(step.run()) - loss_g2) <= 1e-5 * max(1.0, abs(loss_g2))
