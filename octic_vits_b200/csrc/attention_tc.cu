@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     tma_prefetch_desc(&tmQ);
     mbar_init(&bars[BAR_K], 1); mbar_init(&bars[BAR_V], 1); mbar_init(&bars[BAR_Q], 1);
     mbar_init(&bars[BAR_SFULL], 1); mbar_init(&bars[BAR_SFULL + 1], 1);
-    mbar_init(&bars[BAR_SDONE], kFwdMathThreads / 2); mbar_init(&bars[BAR_SDONE + 1], kFwdMathThreads / 2);
+    mbar_init(&bars[BAR_SDONE], kFwdMathThreads); mbar_init(&bars[BAR_SDONE + 1], kFwdMathThreads);
     mbar_init(&bars[BAR_OFULL], 1);
     mbar_init(&bars[BAR_QFREE], kFwdMathThreads);
     fence_mbar_init();
@@ -424,13 +424,18 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
         umma_commit(&bars[BAR_SFULL + buf]);
       }
     };
+    // P of K-step kk: warp set 0 wrote the first half of the pieces at columns kk * 8, set 1 the second half at the
+    // start of its own column range (see the math warps)
     auto issue_pv = [&](int c, int buf, bool first, bool last) {   // O (+)= P_c V_c, P read from TMEM
-      const int nk = cp.w[c] >> 4;
+      const int nk = cp.w[c] >> 4, hsplit = (nk + 1) >> 1;
       const uint32_t a = tb + buf * CW, vb = v_lo + cp.off[c] * 2;
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < CW / 16; ++kk)
-          if (kk < nk) umma_ts_lohi(tb + OCOL, a + kk * 8, vb + kk * 32, kDescHiSw32, idesc_pv, !(first && kk == 0));
+          if (kk < nk) {
+            const uint32_t ak = kk < hsplit ? kk * 8 : hsplit * 16 + (kk - hsplit) * 8;
+            umma_ts_lohi(tb + OCOL, a + ak, vb + kk * 32, kDescHiSw32, idesc_pv, !(first && kk == 0));
+          }
         if (last) umma_commit(&bars[BAR_OFULL]);
       }
     };
@@ -468,108 +473,94 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     }
   } else {
     // -------------------------------------------------- math warps --------------------------------------------------
-    // Warp (q4, bsel) owns TMEM lane quarter q4 of S buffer bsel: it handles the jobs j with (j & 1) == bsel.  Pass 1
-    // loads the whole chunk (row max); pass 2 streams 16-column pieces (load of piece p+1 in flight while piece p is
-    // exponentiated) and writes P in place -- hazard free inside one warp, since output piece p lands on columns of
-    // input piece p/2.  Row max / row sum are combined between the two warps of a quarter once per tile; for the
-    // output accumulator the pair splits the columns (hh = bsel).
+    // Warp (q4, bsel) works on TMEM lane quarter q4 of EVERY job: set bsel = 0 takes the first half of the chunk's
+    // 16-column pieces, set 1 the second half (half the math latency per job; the other buffer's job keeps the tensor
+    // pipe busy).  Pass 1: row max.  Pass 2: p = exp2(.), bf16 P written at the start of the set's own column range --
+    // output piece q lands on columns of the set's input piece q/2, already consumed, so the sets need no barrier.
+    // Row max / row sum are combined between the two warps of a quarter once per tile; for the output accumulator the
+    // pair splits the columns (hh = bsel).
     const int q4 = warp & 3, bsel = warp >> 2, hh = bsel;
     const int rloc = q4 * 32 + lane;                   // row inside the tile
     OCTIC_TRACE_DECL;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-    const uint32_t ta = t_lane + bsel * CW;
-    uint32_t phs = 0u, pho = 0u;
+    uint32_t pho = 0u;
+    int gj = 0;                                        // running job index (buffer = gj & 1, phase = (gj >> 1) & 1)
     for (int t = 0; t < nt; ++t) {
       const bool warp_valid = t * 128 + q4 * 32 < Nm;
       float mx = -INFINITY, l = 0.f, moff = 0.f;
-      for (int j = 0; j < njobs; ++j) {
+      for (int j = 0; j < njobs; ++j, ++gj) {
         const int c = j < nc ? j : j - nc;
         if (j == nc && warp_valid) {
-          // all pass-1 jobs of both warps are done: combine the two partial row maxima
+          // all pass-1 jobs are done: combine the two partial row maxima
           xch[bsel * 128 + rloc] = mx;
           named_bar_sync(1 + q4, 64);
           mx = fmaxf(mx, xch[(bsel ^ 1) * 128 + rloc]);
           moff = mx * scale_log2;
         }
-        if ((j & 1) != bsel) continue;
-        mbar_wait(&bars[BAR_SFULL + bsel], phs);
-        phs ^= 1u;
+        const int buf = j & 1;
+        mbar_wait(&bars[BAR_SFULL + buf], (gj >> 1) & 1);
         tc_fence_after();
         if (tid == 0) OCTIC_TRACE(1, 3);
         if (warp_valid) {
           const int w = cp.w[c], k0 = cp.off[c];
-          const int np = w >> 4;
-          // Pieces are fetched in batches of up to PB (one TMEM round trip of ~300 cycles per batch instead of per
-          // piece).  In pass 2 the in-place P write of batch [b0, b1) lands on S columns of pieces < b1: all loaded.
-          constexpr int PB = 2;
+          const int np = w >> 4, hsplit = (np + 1) >> 1;
+          const int p0 = bsel ? hsplit : 0, cnt = bsel ? np - hsplit : hsplit;     // this set's pieces [p0, p0 + cnt)
+          const uint32_t ta = t_lane + buf * CW + p0 * 16;                          // the set's inputs / outputs start here
+          constexpr int QMAX = (CW / 16 + 1) / 2;
+          // all of the set's pieces are fetched with one TMEM round trip
+          uint32_t r[QMAX][16];
+#pragma unroll
+          for (int q = 0; q < QMAX; ++q)
+            if (q < cnt) tmem_ld_32x16(ta + q * 16, r[q]);
+          tmem_ld_wait();
           if (j < nc) {
             float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-            for (int b0 = 0; b0 < CW / 16; b0 += PB) {
-              if (b0 < np) {
-                uint32_t r[PB][16];
+            for (int q = 0; q < QMAX; ++q)
+              if (q < cnt) {
+                const int nvalid = N - (k0 + (p0 + q) * 16);
+                float v[16];
 #pragma unroll
-                for (int u = 0; u < PB; ++u)
-                  if (b0 + u < CW / 16 && b0 + u < np) tmem_ld_32x16(ta + (b0 + u) * 16, r[u]);
-                tmem_ld_wait();
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[q][i]);
+                if (nvalid < 16) {
 #pragma unroll
-                for (int u = 0; u < PB; ++u)
-                  if (b0 + u < CW / 16 && b0 + u < np) {
-                    const int nvalid = N - (k0 + (b0 + u) * 16);
-                    float v[16];
+                  for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
+                }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[u][i]);
-                    if (nvalid < 16) {
-#pragma unroll
-                      for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
-                    }
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                      m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
-                    }
-                  }
+                for (int i = 0; i < 16; i += 4) {
+                  m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
+                }
               }
-            }
             mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           } else {
             float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
-            for (int b0 = 0; b0 < CW / 16; b0 += PB) {
-              if (b0 < np) {
-                uint32_t r[PB][16];
+            for (int q = 0; q < QMAX; ++q)
+              if (q < cnt) {
+                const int nvalid = N - (k0 + (p0 + q) * 16);
+                float e[16];
 #pragma unroll
-                for (int u = 0; u < PB; ++u)
-                  if (b0 + u < CW / 16 && b0 + u < np) tmem_ld_32x16(ta + (b0 + u) * 16, r[u]);
-                tmem_ld_wait();
+                for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[q][i]), scale_log2, -moff));
+                if (nvalid < 16) {
 #pragma unroll
-                for (int u = 0; u < PB; ++u)
-                  if (b0 + u < CW / 16 && b0 + u < np) {
-                    const int nvalid = N - (k0 + (b0 + u) * 16);
-                    float e[16];
+                  for (int i = 0; i < 16; ++i) e[i] = i < nvalid ? e[i] : 0.f;
+                }
+                uint32_t pk[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[u][i]), scale_log2, -moff));
-                    if (nvalid < 16) {
-#pragma unroll
-                      for (int i = 0; i < 16; ++i) e[i] = i < nvalid ? e[i] : 0.f;
-                    }
-                    uint32_t pk[8];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                      l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
-                      pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
-                      pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
-                    }
-                    tmem_st_32x8(ta + (b0 + u) * 8, pk);
-                  }
+                for (int i = 0; i < 16; i += 4) {
+                  l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
+                  pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
+                  pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
+                }
+                tmem_st_32x8(ta + q * 8, pk);
               }
-            }
             l += (l0 + l1) + (l2 + l3);
             tmem_st_wait();
           }
         }
         tc_fence_before();
         if (tid == 0) OCTIC_TRACE(1, 5);
-        mbar_arrive(&bars[BAR_SDONE + bsel]);
+        mbar_arrive(&bars[BAR_SDONE + buf]);
       }
       if (warp_valid) {
         // total row sum = both warps of the quarter (written before, read after the pair barrier)
@@ -660,7 +651,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     tma_prefetch_desc(&tmDO);
     mbar_init(&bars[BAR_KQ], 1); mbar_init(&bars[BAR_VDO], 1);
     mbar_init(&bars[BAR_LFULL], 1); mbar_init(&bars[BAR_LFULL + 1], 1);
-    mbar_init(&bars[BAR_MDONE], kBwdMathThreads / 2); mbar_init(&bars[BAR_MDONE + 1], kBwdMathThreads / 2);
+    mbar_init(&bars[BAR_MDONE], kBwdMathThreads); mbar_init(&bars[BAR_MDONE + 1], kBwdMathThreads);
     mbar_init(&bars[BAR_ACC], 1);
     fence_mbar_init();
   }
@@ -814,13 +805,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       }
     };
     // second level: acc (+)= (bf16 in TMEM at a_col) * B[chunk rows] (MN-major)
+    // The bf16 A operand of K-step kk (written by the math warps): the first half of the pieces (warp set 0) sits at
+    // columns kk * 8, the second half (warp set 1) at the start of that set's own column range, h * 16 + (kk - h) * 8.
     auto issue_l2 = [&](uint32_t acc_col, uint32_t a_col, uint32_t bm, int c, bool first) {
-      const int nk = cp.w[c] >> 4;
+      const int nk = cp.w[c] >> 4, hsplit = (nk + 1) >> 1;
       const uint32_t bb = bm + cp.off[c] * 2;
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < CW / 16; ++kk)
-          if (kk < nk) umma_ts_lohi(tb + acc_col, tb + a_col + kk * 8, bb + kk * 32, kDescHiSw32, idesc_l2, !(first && kk == 0));
+          if (kk < nk) {
+            const uint32_t ak = kk < hsplit ? kk * 8 : hsplit * 16 + (kk - hsplit) * 8;
+            umma_ts_lohi(tb + acc_col, tb + a_col + ak, bb + kk * 32, kDescHiSw32, idesc_l2, !(first && kk == 0));
+          }
       }
     };
 
@@ -849,18 +845,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     }
   } else {
     // -------------------------------------------------- math warps --------------------------------------------------
-    // Warp (q4, bsel) owns TMEM lane quarter q4 of first-level buffer bsel: it handles every job g with (g & 1) == bsel
-    // and streams the job's 16-column pieces (load of piece p+1 in flight while piece p is computed).  Writing the
-    // bf16 outputs in place is hazard free inside one warp: output piece p lands on columns of input piece p/2, which
-    // the warp has already consumed.  The two warps of a quarter sit on the same SM sub-partition and cover each
-    // other's TMEM round trips.  For the accumulator flush (once per tile) the pair splits the columns (hh = bsel).
+    // Warp (q4, bsel) works on TMEM lane quarter q4 of EVERY job: set bsel = 0 takes the first half of the job's
+    // 16-column pieces, set 1 the second half, so a job's math latency is half of what one warp per job gives and the
+    // dependent chain math(g) -> second-level MMAs(g) + first-level MMAs(g+2) -> math(g+2) shortens accordingly (the
+    // other buffer's job g+1 fills the tensor pipe meanwhile).  Each set streams its pieces (load of piece p+1 in flight
+    // while piece p is computed) and writes the bf16 outputs at the start of ITS OWN column range: output piece q lands
+    // on columns of the set's input piece q/2, which it has already consumed -- no barrier between the sets.
+    // For the accumulator flush (once per tile) the pair splits the columns (hh = bsel).
     const int q4 = warp & 3, bsel = warp >> 2, hh = bsel;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
     uint8_t* my_stg = stg + (q4 * 32 + lane) * (HD * 2);
     const uint32_t lse_sa = smem_u32(lse_s), del_sa = smem_u32(del_s);
-    const uint32_t tx = t_lane + bsel * 2 * CW, ty = tx + CW;
     OCTIC_TRACE_DECL;
-    uint32_t phl = 0u, pha = 0u;
+    uint32_t pha = 0u;
     int g = 0;
     for (int phase = 0; phase < 2; ++phase) {
       for (int t = 0; t < nt; ++t) {
@@ -873,50 +870,54 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
           del_r = my_row < Rk ? del_s[my_row] : 0.f;
         }
         for (int c = 0; c < nc; ++c, ++g) {
-          if ((g & 1) != bsel) continue;
-          mbar_wait(&bars[BAR_LFULL + bsel], phl);
-          phl ^= 1u;
+          const int buf = g & 1;
+          const uint32_t tx = t_lane + buf * 2 * CW, ty = tx + CW;
+          mbar_wait(&bars[BAR_LFULL + buf], (g >> 1) & 1);
           tc_fence_after();
           if (tid == 0) OCTIC_TRACE(1, 3);
           if (warp_valid) {
             const int w = cp.w[c], k0 = cp.off[c];
-            const int np = w >> 4;
-            // three register sets: the loads of pieces p+1 and p+2 are in flight while piece p is computed (a TMEM
+            const int np = w >> 4, hsplit = (np + 1) >> 1;
+            const int p0 = bsel ? hsplit : 0, cnt = bsel ? np - hsplit : hsplit;     // this set's pieces [p0, p0 + cnt)
+            const uint32_t ix = tx + p0 * 16, iy = ty + p0 * 16;                      // inputs / outputs of the set start here
+            // three register sets: the loads of pieces q+1 and q+2 are in flight while piece q is computed (a TMEM
             // round trip costs ~300 cycles, a piece of math ~150)
             uint32_t rx[3][16], ry[3][16];
-            tmem_ld_32x16(tx, rx[0]);
-            tmem_ld_32x16(ty, ry[0]);
-            if (1 < np) {
-              tmem_ld_32x16(tx + 16, rx[1]);
-              tmem_ld_32x16(ty + 16, ry[1]);
+            if (0 < cnt) {
+              tmem_ld_32x16(ix, rx[0]);
+              tmem_ld_32x16(iy, ry[0]);
+            }
+            if (1 < cnt) {
+              tmem_ld_32x16(ix + 16, rx[1]);
+              tmem_ld_32x16(iy + 16, ry[1]);
             }
 #pragma unroll
-            for (int pc = 0; pc < CW / 16; ++pc) {
-              if (pc < np) {
-                // wait::ld retires every outstanding load, so piece pc+1 is complete too; keep two loads in flight by
-                // issuing piece pc+2 right away
+            for (int q = 0; q < (CW / 16 + 1) / 2; ++q) {
+              if (q < cnt) {
+                // wait::ld retires every outstanding load, so piece q+1 is complete too; keep two loads in flight by
+                // issuing piece q+2 right away
                 tmem_ld_wait();
-                if (pc + 2 < np) {
-                  tmem_ld_32x16(tx + (pc + 2) * 16, rx[(pc + 2) % 3]);
-                  tmem_ld_32x16(ty + (pc + 2) * 16, ry[(pc + 2) % 3]);
+                if (q + 2 < cnt) {
+                  tmem_ld_32x16(ix + (q + 2) * 16, rx[(q + 2) % 3]);
+                  tmem_ld_32x16(iy + (q + 2) * 16, ry[(q + 2) % 3]);
                 }
-                const int col0 = k0 + pc * 16;
+                const int col0 = k0 + (p0 + q) * 16;
                 uint32_t pkp[8], pkd[8];
                 if (phase == 0) {
                   // padded query columns carry lse = +inf (p = 0) and delta = 0: no explicit mask
-                  bwd_piece<true>(rx[pc % 3], ry[pc % 3], pkp, pkd, scale_log2, lse_sa + col0 * 4, del_sa + col0 * 4, 0.f, 0.f, 16);
-                  tmem_st_32x8(tx + pc * 8, pkp);
+                  bwd_piece<true>(rx[q % 3], ry[q % 3], pkp, pkd, scale_log2, lse_sa + col0 * 4, del_sa + col0 * 4, 0.f, 0.f, 16);
+                  tmem_st_32x8(ix + q * 8, pkp);
                 } else {
-                  bwd_piece<false>(rx[pc % 3], ry[pc % 3], pkp, pkd, scale_log2, 0u, 0u, lse_r, del_r, N - col0);
+                  bwd_piece<false>(rx[q % 3], ry[q % 3], pkp, pkd, scale_log2, 0u, 0u, lse_r, del_r, N - col0);
                 }
-                tmem_st_32x8(ty + pc * 8, pkd);
+                tmem_st_32x8(iy + q * 8, pkd);
               }
             }
             tmem_st_wait();
           }
           tc_fence_before();
           if (tid == 0) OCTIC_TRACE(1, 5);
-          mbar_arrive(&bars[BAR_MDONE + bsel]);
+          mbar_arrive(&bars[BAR_MDONE + buf]);
         }
         // ---- flush the accumulators of this tile: TMEM -> bf16 staging -> packed global rows ----
         mbar_wait(&bars[BAR_ACC], pha);

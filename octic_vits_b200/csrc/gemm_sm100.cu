@@ -259,14 +259,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       return direct_ptrs && c0_ + 32 <= min(p.block_n, G_.n - n0_) && ((G_.c_col + n0_ + c0_) & 7) == 0 &&
              (G_.bias_off < 0 || ((G_.bias_off + n0_ + c0_) & 3) == 0);
     };
+    // EPI_RESID: the fp32 residual values of the warp's NEXT 32 x 32 chunk are fetched while the current chunk is
+    // processed (and, across tiles, while the MMAs of the next tile run): the epilogue is otherwise paced by one DRAM
+    // round trip per 8 rows (ncu: 22 % of the stall samples on the FFMAs that consume the loads).  Staged path:
+    // lane = column, res[rr] = row rr (res_ok is warp-uniform); direct path: thread = row, res[] = its 32 columns.
     float res[32];
+    bool res_ok = false;
     auto prefetch_resid = [&](int tile_, int c0_) {
+      res_ok = false;
       if (MODE != EPI_RESID || p.resid_in == nullptr || tile_ >= total_tiles) return;
       int mb_, g_, nb_;
       decode(tile_, mb_, g_, nb_);
       const GemmGroup& G_ = p.g[g_];
       const int n0_ = nb_ * p.block_n, row_ = mb_ * kBlockM + q * 32 + lane;
-      if (!direct_ok(G_, n0_, c0_) || row_ >= p.M) return;
+      if (!direct_ok(G_, n0_, c0_)) {
+        const int row0_ = mb_ * kBlockM + q * 32;
+        if (p.remap_group != 0 || c0_ + 32 > min(p.block_n, G_.n - n0_) || row0_ + 32 > p.M) return;
+        const float* rin_ = p.resid_in + static_cast<long>(row0_) * p.ldr + G_.c_col + n0_ + c0_ + lane;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr) res[rr] = rin_[rr * p.ldr];
+        res_ok = true;
+        return;
+      }
+      if (row_ >= p.M) return;
       const float4* rin_ = reinterpret_cast<const float4*>(p.resid_in + static_cast<long>(row_) * p.ldr + G_.c_col + n0_ + c0_);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -637,8 +652,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int r8 = 0; r8 < 32; r8 += 8) {
                 float base[8];
                 // all loads of a batch before its stores (resid_in may alias resid_out)
+                if (res_ok) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
+                  for (int i = 0; i < 8; ++i) base[i] = res[r8 + i];
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) base[i] = rin != nullptr ? rin[(r8 + i) * p.ldr] : 0.f;
+                }
                 float acc[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = lds_f32(rd + (r8 + i) * 132) + bv;
@@ -777,8 +797,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   //   * whole tiles first: in round r CTA c takes tile r * ncl + c over the FULL token range.  All CTAs then sweep the
   //     tokens in lock step, so every dY / X column block is fetched from DRAM once and shared through L2 (a pure
   //     stream-K line made every CTA stream its own token range: 2.4 GB of DRAM reads for 0.42 GB of operands).
-  //   * the remaining total_tiles mod ncl tiles: their (tile, k-block) pairs, k-block fastest, form one line that is
-  //     cut into ncl equal contiguous ranges, so no CTA runs a mostly empty last wave.
+  //   * the remaining total_tiles mod ncl tiles: either p.rem_splits > 0 -- every tile is cut into rem_splits equal token
+  //     ranges, one (tile, range) item per CTA, CTAs of one range neighbours (again lock step: used when the items fill
+  //     >= 3/4 of the CTAs, the case of the irrep groups whose few tiles would otherwise each stream the operands from
+  //     DRAM on their own) -- or their (tile, k-block) pairs, k-block fastest, form one line that is cut into ncl
+  //     equal contiguous ranges, so no CTA runs a mostly empty last wave.
   // Every segment (one tile, k-blocks [kb0, kb1)) ends in a red.add epilogue.
   const int kb_total = (p.T + kBlockK - 1) / kBlockK;
   const int full_rounds = p.total_tiles / ncl;
@@ -793,6 +816,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       kb0 = 0;
       kb1 = kb_total;
       ++round;
+    } else if (p.rem_splits > 0) {
+      if (u != r_begin || cid >= rem_tiles * p.rem_splits) return false;     // one item per CTA
+      u = r_begin + 1;
+      const int part = cid / rem_tiles, len = (kb_total + p.rem_splits - 1) / p.rem_splits;
+      j = full_rounds * ncl + (cid - part * rem_tiles);
+      kb0 = part * len;
+      kb1 = min(kb_total, kb0 + len);
+      if (kb1 <= kb0) return false;
     } else if (u < r_end) {
       const int jr = static_cast<int>(u / kb_total);
       j = full_rounds * ncl + jr;
@@ -1205,6 +1236,11 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
   if (grid_l > (total_units + 3) / 4) grid_l = (total_units + 3) / 4;
   if (grid_l < 1) grid_l = 1;
   p.splits = d->splits;
+  {
+    const int ncl = static_cast<int>(grid_l), rem = tiles % ncl;
+    const int s_al = rem > 0 ? ncl / rem : 0;
+    p.rem_splits = (d->splits <= 0 && s_al >= 2 && 4 * rem * s_al >= 3 * ncl && kb_total >= 8 * s_al) ? s_al : 0;
+  }
   const int b_stage_bytes = (d->block_n / ncta) * kBlockK * 2;
   int stages = (kMaxDynSmem - 1024 - (8 * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;

@@ -42,7 +42,7 @@ struct WgradGroup {
   long ldw;
 };
 struct WgradParams {
-  int T, num_groups, block_n, total_tiles, splits, num_stages;
+  int T, num_groups, block_n, total_tiles, splits, num_stages, rem_splits;
   WgradGroup g[OCTIC_MAX_GROUPS];
 };
 
