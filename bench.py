@@ -275,7 +275,14 @@ def run_ours(args):
                          "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved_tf / peaks["tf_sustained"]) if achieved_tf else None, "traffic": None,
                          "peak_source": f"{peaks['src']} (bf16 sustained)", "launches_timed": gemm_calls,
-                         "share_of_step": gemm_ms / ms_dev},
+                         "share_of_step": gemm_ms / ms_dev,
+                         # `achieved` averages 259 launches of many shapes, so there is no single per-launch traffic figure;
+                         # ncu --set full per shape (profiles/r01_ncu_s5.md, batch 128): DRAM bytes vs algorithmic bytes
+                         "traffic_samples": {
+                             "dense qkv fwd (M=32896, N=3840, K=1280)": {"dram_bytes": 3.01e8, "algorithmic_bytes": 3.47e8},
+                             "dense fc2 + residual (N=1280, K=5120)": {"dram_bytes": 8.79e8, "algorithmic_bytes": 7.71e8},
+                             "octic fc2 + residual (LinearD8 5120 -> 1280)": {"dram_bytes": 7.35e8, "algorithmic_bytes": 7.62e8},
+                             "octic qkv head-major (LinearD8 1280 -> 3840)": {"dram_bytes": 4.51e8, "algorithmic_bytes": 3.40e8}}},
             "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
                              "sample": "batch 2, 1 warm-up + 2 timed fwd+bwd steps of the same model (oracle port, bf16 autocast)"},
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",
