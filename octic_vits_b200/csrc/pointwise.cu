@@ -3,12 +3,11 @@
 // 16-byte accesses; per-token reductions are warp-shuffle, column (parameter-gradient) reductions are
 // register accumulators + one red.add per column per CTA.
 #include "octic_capi_internal.h"
+#include "gelu_math.cuh"
 
 namespace octic {
 
 constexpr float kSqrt2Over4 = 0.35355339059327376f;
-constexpr float kInvSqrt2 = 0.70710678118654752f;
-constexpr float kInvSqrt2Pi = 0.39894228040143268f;
 
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. below fp32 GELU's own rounding for |x| < 4):
 // one MUFU.RCP + one MUFU.EX2 + 6 FMA instead of erff's ~30 instructions (the D8 GELU needs 8 erf per channel)
@@ -68,6 +67,36 @@ __device__ __forceinline__ void r2i(const float (&x)[8], float (&y)[8]) {
   y[7] = kSqrt2Over4 * (gme + cma);
 }
 
+// same butterflies as i2r / r2i above on channel pairs; `s` is the output scale (sqrt2/4, or sqrt2/8 when the
+// 0.5 of the GELU is folded in)
+__device__ __forceinline__ void i2r_2(const f2 (&x)[8], f2 (&y)[8], f2 s) {
+  const f2 a = add2(x[0], x[1]), b = sub2(x[0], x[1]), c = add2(x[2], x[3]), d = sub2(x[2], x[3]);
+  const f2 e = add2(x[4], x[5]), f = sub2(x[4], x[5]), g = add2(x[6], x[7]), h = sub2(x[6], x[7]);
+  const f2 apc = add2(a, c), amc = sub2(a, c), bpd = add2(b, d), bmd = sub2(b, d);
+  const f2 eph = add2(e, h), emh = sub2(e, h), fpg = add2(f, g), fmg = sub2(f, g);
+  y[0] = mul2(s, add2(apc, eph));
+  y[1] = mul2(s, add2(amc, fmg));
+  y[2] = mul2(s, sub2(apc, eph));
+  y[3] = mul2(s, sub2(amc, fmg));
+  y[4] = mul2(s, sub2(bpd, fpg));
+  y[5] = mul2(s, sub2(bmd, emh));
+  y[6] = mul2(s, add2(bpd, fpg));
+  y[7] = mul2(s, add2(bmd, emh));
+}
+__device__ __forceinline__ void r2i_2(const f2 (&x)[8], f2 (&y)[8], f2 s) {
+  const f2 a = add2(x[0], x[1]), b = sub2(x[0], x[1]), c = add2(x[2], x[3]), d = sub2(x[2], x[3]);
+  const f2 e = add2(x[4], x[5]), f = sub2(x[4], x[5]), g = add2(x[6], x[7]), h = sub2(x[6], x[7]);
+  const f2 apc = add2(a, c), cma = sub2(c, a), bpd = add2(b, d), bmd = sub2(b, d);
+  const f2 epg = add2(e, g), gme = sub2(g, e), fph = add2(f, h), fmh = sub2(f, h);
+  y[0] = mul2(s, add2(apc, epg));
+  y[1] = mul2(s, sub2(apc, epg));
+  y[2] = mul2(s, add2(bpd, fph));
+  y[3] = mul2(s, sub2(bpd, fph));
+  y[4] = mul2(s, sub2(gme, cma));
+  y[5] = mul2(s, add2(bmd, fmh));
+  y[6] = mul2(s, sub2(bmd, fmh));
+  y[7] = mul2(s, add2(gme, cma));
+}
 // ----------------------------------------------- vector I/O -----------------------------------------------
 template <typename T, int V> struct Vec;
 template <> struct Vec<float, 4> {
@@ -143,17 +172,32 @@ __global__ void __launch_bounds__(256) gelu_d8_fwd_kernel(const T* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 8; ++k) Vec<T, V>::load(x + t * ldx + kCompOff[k] * C + c, in[k]);
     float out[8][V];
+    if constexpr ((V & 1) == 0) {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float a[8], r[8];
+      for (int v = 0; v < V; v += 2) {
+        f2 a[8], r[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) a[k] = in[k][v];
-      i2r(a, r);
+        for (int k = 0; k < 8; ++k) a[k] = mk2(in[k][v], in[k][v + 1]);
+        i2r_2(a, r, sp2(kSqrt2Over4));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] = gelu_f(r[k]);
-      r2i(r, a);
+        for (int k = 0; k < 8; ++k) r[k] = gelu_x2_2(r[k]);
+        r2i_2(r, a, sp2(0.5f * kSqrt2Over4));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) out[k][v] = a[k];
+        for (int k = 0; k < 8; ++k) un2(a[k], out[k][v], out[k][v + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        float a[8], r[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = in[k][v];
+        i2r(a, r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r[k] = gelu_f(r[k]);
+        r2i(r, a);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k][v] = a[k];
+      }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) Vec<T, V>::store(y + t * ldy + kCompOff[k] * C + c, out[k]);
@@ -176,18 +220,21 @@ __global__ void __launch_bounds__(256) gelu_d8_bwd_kernel(const T* __restrict__ 
       Vec<T, V>::load(g + t * ldg + kCompOff[k] * C + c, gg[k]);
     }
     float out[8][V];
+    // (the packed-pair form that speeds up the forward kernel by 16 % made this one slower: 232 -> 281 us, measured)
+    {
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float a[8], u[8], b[8], gu[8];
+      for (int v = 0; v < V; ++v) {
+        float a[8], u[8], b[8], gu[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { a[k] = xin[k][v]; b[k] = gg[k][v]; }
-      i2r(a, u);
-      i2r(b, gu);   // R2I = I2R^T, so the cotangent is pulled back with I2R (octic_vits/d8_gelu.py:283-321)
+        for (int k = 0; k < 8; ++k) { a[k] = xin[k][v]; b[k] = gg[k][v]; }
+        i2r(a, u);
+        i2r(b, gu);   // R2I = I2R^T, so the cotangent is pulled back with I2R (octic_vits/d8_gelu.py:283-321)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = gelu_grad_f(u[k]) * gu[k];
-      r2i(u, a);
+        for (int k = 0; k < 8; ++k) u[k] = gelu_grad_f(u[k]) * gu[k];
+        r2i(u, a);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) out[k][v] = a[k];
+        for (int k = 0; k < 8; ++k) out[k][v] = a[k];
+      }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) Vec<T, V>::store(gin + t * ldgin + kCompOff[k] * C + c, out[k]);
