@@ -797,10 +797,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       const uint32_t idesc = make_idesc_bf16(128, cp.w[c], 0, 0);
       const uint32_t d = tb + buf * 2 * CW;
       if (elect_one()) {
+        // the K-steps of X and Y alternate: consecutive MMAs into the SAME accumulator serialise on its latency (an
+        // N = 80 MMA is ~40 cycles of work), two independent accumulation chains keep the pipe busy
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) umma_ss_lohi(d, a1 + ks * mstep, b1 + ks * mstep, kDescHiSw32, idesc, ks != 0);
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) umma_ss_lohi(d + CW, a2 + ks * mstep, b2 + ks * mstep, kDescHiSw32, idesc, ks != 0);
+        for (int ks = 0; ks < KS; ++ks) {
+          umma_ss_lohi(d, a1 + ks * mstep, b1 + ks * mstep, kDescHiSw32, idesc, ks != 0);
+          umma_ss_lohi(d + CW, a2 + ks * mstep, b2 + ks * mstep, kDescHiSw32, idesc, ks != 0);
+        }
         umma_commit(&bars[BAR_LFULL + buf]);
       }
     };
@@ -820,6 +823,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       }
     };
 
+    // phase 0: dV += P^T dO and dK += dS^T Q as two interleaved accumulation chains
+    auto issue_l2_pair = [&](uint32_t acc0, uint32_t a_col0, uint32_t bm0, uint32_t acc1, uint32_t a_col1, uint32_t bm1, int c,
+                             bool first) {
+      const int nk = cp.w[c] >> 4, hsplit = (nk + 1) >> 1;
+      const uint32_t bb0 = bm0 + cp.off[c] * 2, bb1 = bm1 + cp.off[c] * 2;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < CW / 16; ++kk)
+          if (kk < nk) {
+            const uint32_t ak = kk < hsplit ? kk * 8 : hsplit * 16 + (kk - hsplit) * 8;
+            umma_ts_lohi(tb + acc0, tb + a_col0 + ak, bb0 + kk * 32, kDescHiSw32, idesc_l2, !(first && kk == 0));
+            umma_ts_lohi(tb + acc1, tb + a_col1 + ak, bb1 + kk * 32, kDescHiSw32, idesc_l2, !(first && kk == 0));
+          }
+      }
+    };
+
     mbar_wait(&bars[BAR_KQ], 0);
     mbar_wait(&bars[BAR_VDO], 0);
     tc_fence_after();
@@ -834,8 +853,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       if (leader) OCTIC_TRACE(0, 1);
       const uint32_t xcol = buf * 2 * CW, ycol = xcol + CW;
       if (phase == 0) {
-        issue_l2(ACC + HD, xcol, dom, c, c == 0);    // dV += P^T dO
-        issue_l2(ACC, ycol, qm, c, c == 0);          // dK += dS^T Q
+        issue_l2_pair(ACC + HD, xcol, dom, ACC, ycol, qm, c, c == 0);    // dV += P^T dO, dK += dS^T Q
       } else {
         issue_l2(ACC, ycol, km, c, c == 0);          // dQ += dS K
       }
