@@ -180,6 +180,7 @@ def run_ours(args):
     tgt_host = torch.randint(0, MODEL["classes"], (B,)).pin_memory()
 
     def eager_step(img, tgt):
+        ops.begin_step()
         flat.zero_()
         logits = model(img)
         loss = torch.nn.functional.cross_entropy(logits, tgt)

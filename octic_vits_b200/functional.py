@@ -187,7 +187,7 @@ class LinearD8ResidualFn(torch.autograd.Function):
             if ctx.needs_input_grad[0]:
                 dx = ops.linear_d8_dgrad(g, packed_d8_scaled_t(ws, gamma, ctx.gamma_src), ctx.dgrad_heads)
             dws = ops.linear_d8_wgrad(g, x, pk.din, pk.dout)
-            dgamma = torch.zeros_like(gamma)
+            dgamma = ops.zeros_f32(gamma.numel(), gamma.device).view_as(gamma)
             db = torch.empty(co, dtype=torch.float32, device=x.device) if ctx.has_bias else None
             gam = gamma.detach()
             segs = [(dws[i], ws[i].detach(), gam[i * co:(i + 1) * co], bias if i == 0 else None,
@@ -248,7 +248,7 @@ class LinearFn(torch.autograd.Function):
             dy = torch.nn.functional.pad(dy, (0, 8 - n % 8))
         db = None
         if ctx.gelu:
-            colsum = torch.zeros(n, dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+            colsum = ops.zeros_f32(n, dy.device) if ctx.has_bias else None
             dy = ops.gelu_bwd(dy, pre, colsum)
             db = colsum
         elif ctx.has_bias and ctx.needs_input_grad[2]:
@@ -318,7 +318,7 @@ def _dense_fold_wgrad(g, a, weight, gamma, bias, cs, n, k, wparam=None):
     """wgrad + finalize of the gamma-folded backward for one nn.Linear: returns (dW or None if accumulated into
     wparam.grad, dgamma, dbias)."""
     dw = ops.linear_dense_wgrad(g, a, n, k)
-    dgamma = torch.zeros_like(gamma)
+    dgamma = ops.zeros_f32(gamma.numel(), gamma.device).view_as(gamma)
     db = torch.empty(n, dtype=torch.float32, device=g.device) if bias is not None else None
     tg = _grad_target(wparam)
     ops.layerscale_wgrad_finalize([(dw, weight.detach(), gamma.detach(), bias, cs if bias is not None else None, dgamma, db,
@@ -369,7 +369,7 @@ class MlpResidualFn(torch.autograd.Function):
         x, pre, h, branch, gamma, row_scale, w2, b2 = ctx.saved_tensors
         pk1, pk2 = ctx.pk
         dout = _c(dout)
-        db1 = torch.zeros(pk1.n, dtype=torch.float32, device=x.device) if ctx.has_bias[0] else None
+        db1 = ops.zeros_f32(pk1.n, x.device) if ctx.has_bias[0] else None
         dpre = torch.empty_like(pre)
         if ctx.fold:
             g, cs = _take_aux(dout)

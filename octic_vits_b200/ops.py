@@ -47,6 +47,51 @@ def roundup64(x: int) -> int:
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# zeroed fp32 scratch (targets of red.add accumulation: weight-gradient temporaries, LayerNorm / bias column sums).
+# A training step asks for ~330 of them; inside a step bracketed by begin_step() they are slices of ONE buffer that is
+# zero-filled once (its size is the previous step's demand), instead of one fill kernel each.
+# ----------------------------------------------------------------------------------------------------------------
+class _ZeroPool:
+    def __init__(self):
+        self.active, self.buf, self.off, self.demand, self.last_demand = False, None, 0, 0, 0
+
+    def begin_step(self) -> None:
+        self.active = True
+        if self.demand > 0:
+            self.last_demand = self.demand          # what the previous step asked for
+        self.demand, self.off, self.buf = 0, 0, None
+
+    def end(self) -> None:
+        self.active, self.buf = False, None
+
+    def take(self, n: int, device) -> torch.Tensor:
+        n_al = (n + 63) // 64 * 64                       # slices stay 256-byte aligned
+        self.demand += n_al
+        if not self.active or self.last_demand == 0:
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        if self.buf is None:
+            self.buf = torch.zeros(self.last_demand, dtype=torch.float32, device=device)
+            self.off = 0
+        if self.buf.device != torch.device(device) or self.off + n_al > self.buf.numel():
+            return torch.zeros(n, dtype=torch.float32, device=device)
+        out = self.buf[self.off:self.off + n]
+        self.off += n_al
+        return out
+
+
+ZERO_POOL = _ZeroPool()
+
+
+def begin_step() -> None:
+    """Call at the start of every training step (parallel.GraphedTrainStep does): see _ZeroPool."""
+    ZERO_POOL.begin_step()
+
+
+def zeros_f32(n: int, device) -> torch.Tensor:
+    return ZERO_POOL.take(int(n), device)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # weights
 # ----------------------------------------------------------------------------------------------------------------
 @dataclass
@@ -190,7 +235,7 @@ def linear_d8_wgrad(dy: torch.Tensor, x: torch.Tensor, din: int, dout: int, targ
     if targets is not None:
         dws, dwE = list(targets[:4]), targets[4]
     else:
-        flat = torch.zeros(8 * co * ci, dtype=torch.float32, device=x.device)      # one fill for all five gradients
+        flat = zeros_f32(8 * co * ci, x.device)      # one fill for all five gradients
         dws = [flat[i * co * ci:(i + 1) * co * ci].view(co, ci) for i in range(4)]
         dwE = flat[4 * co * ci:].view(2 * co, 2 * ci)
     call("octic_linear_d8_wgrad", dy.data_ptr(), x.data_ptr(), x.shape[0], din, dout, dws[0].data_ptr(),
@@ -223,7 +268,7 @@ def linear_dense_wgrad(dy: torch.Tensor, x: torch.Tensor, n: int, k: int, dw: Op
     _req(dy, torch.bfloat16, "dy")
     _req(x, torch.bfloat16, "x")
     if dw is None:
-        dw = torch.zeros(n, k, dtype=torch.float32, device=x.device)
+        dw = zeros_f32(n * k, x.device).view(n, k)
     d = WgradDesc()
     d.dy, d.ld_dy, d.dy_cols = dy.data_ptr(), dy.stride(0), dy.shape[1]
     d.x, d.ld_x, d.x_cols = x.data_ptr(), x.stride(0), x.shape[1]
@@ -285,7 +330,7 @@ def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, stats: torch.Tensor, alpha:
     T, D = x.shape
     dx = torch.empty(T, D, dtype=torch.float32, device=x.device)
     nb = D // 8 if d8 else D
-    flat = torch.zeros(D + nb + (D if want_aux else 0), dtype=torch.float32, device=x.device)
+    flat = zeros_f32(D + nb + (D if want_aux else 0), x.device)
     dalpha, dbeta = flat[:D], flat[D:D + nb]
     dxb = torch.empty(T, D, dtype=torch.bfloat16, device=x.device) if want_aux else None
     dxs = flat[D + nb:] if want_aux else None
@@ -315,7 +360,7 @@ def layerscale_bwd(dres: torch.Tensor, branch: Optional[torch.Tensor], gamma: Op
     _req(dres, torch.float32, "dres")
     T, D = dres.shape
     dy = torch.empty(T, D, dtype=torch.bfloat16, device=dres.device)
-    flat = torch.zeros(2 * D, dtype=torch.float32, device=dres.device)
+    flat = zeros_f32(2 * D, dres.device)
     dgamma = flat[:D] if branch is not None else None
     colsum = flat[D:] if want_colsum else None
     call("octic_layerscale_bwd", dres.data_ptr(), dres.stride(0), _ptr(branch),
@@ -327,7 +372,7 @@ def layerscale_bwd(dres: torch.Tensor, branch: Optional[torch.Tensor], gamma: Op
 def colsum_bf16(x: torch.Tensor, n_cols: Optional[int] = None) -> torch.Tensor:
     _req(x, torch.bfloat16, "x")
     n_cols = x.shape[1] if n_cols is None else n_cols
-    out = torch.zeros(n_cols, dtype=torch.float32, device=x.device)
+    out = zeros_f32(n_cols, x.device)
     call("octic_colsum_bf16", x.data_ptr(), x.stride(0), x.shape[0], n_cols, out.data_ptr(), _stream())
     return out
 

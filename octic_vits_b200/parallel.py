@@ -47,9 +47,12 @@ class FlatGrads:
 
     def all_reduce(self, average: bool = True) -> None:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat)
-            if average:
-                self.flat.div_(dist.get_world_size())
+            if average and dist.get_backend() == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)      # the division happens inside the NCCL kernel
+            else:
+                dist.all_reduce(self.flat)
+                if average:
+                    self.flat.div_(dist.get_world_size())
 
     def nbytes(self) -> int:
         return self.flat.numel() * 4
@@ -104,6 +107,8 @@ class GraphedTrainStep:
             torch.cuda.synchronize(dev)
 
     def _eager(self) -> torch.Tensor:
+        from . import ops
+        ops.begin_step()                  # one zero fill for all red.add scratch of the step
         self.fg.flat.zero_()
         loss = self.loss_fn(self.model(self.img), self.tgt)
         loss.backward()
