@@ -289,3 +289,48 @@ def test_graphed_train_step_matches_eager():
     # staged input pipeline (pinned host batch -> copy stream -> static inputs) gives the same step
     step.stage(img2.cpu().pin_memory(), tgt.cpu().pin_memory())
     assert abs(float(step.run()) - loss_g2) <= 1e-5 * max(1.0, abs(loss_g2))
+
+
+def test_headline_model_equivariance_report(capsys):
+    """BASELINE.json metric 'D8 equiv error' on the HEADLINE model: hybrid octic ViT-H/14 (DeiT-III init, layer scale
+    1e-4 as shipped, and an O(1)-weights variant), bf16 GPU path, 224 px.  Equivariance of the 16-block octic trunk under
+    all 8 elements of D8 (experiments/test_equivariance.py:145-161 logic) and invariance of the logits of the invariant
+    ViT-H/14.  The numbers are printed (and written to gpurun_out/equivariance_h14.json when that directory exists) so
+    that every GPU test run records them; bounds: 2e-2 relative L2 (bf16 path; the reference's fp32 level is 1.1e-6
+    max-abs)."""
+    import json
+    import os
+    torch.manual_seed(0)
+    report = {}
+    img = torch.randn(2, 3, 224, 224, device=DEV)
+    for tag, randomize in (("default_init", False), ("o1_weights", True)):
+        hyb = create_model("hybrid_deit_huge_patch14", num_classes=1000).to(DEV).eval()
+        if randomize:
+            _randomize(hyb, seed=5)
+        worst_rel, worst_abs = 0.0, 0.0
+        with torch.no_grad():
+            base = tuple(t.float() for t in L.OF.unpack_five(hyb.forward_trunk_packed(img)))
+            scale = max(float(t.abs().max()) for t in base)
+            for g in O.GROUP:
+                moved = L.OF.unpack_five(hyb.forward_trunk_packed(O.image_action(g, img).contiguous()))
+                want = O.token_action(g, base, has_cls=True)
+                for a, b in zip(moved, want):
+                    worst_rel = max(worst_rel, rel_err(a, b))
+                    worst_abs = max(worst_abs, float((a.float() - b).abs().max()))
+        report[f"trunk_equivariance_{tag}"] = {"rel_l2_max_over_group": worst_rel, "max_abs": worst_abs, "max_abs_of_output": scale}
+        del hyb
+        assert worst_rel < 2e-2, report
+    inv = OcticVisionTransformer(img_size=224, patch_size=14, embed_dim=1280, depth=32, num_heads=16, num_classes=1000,
+                                 qkv_bias=True, invariant=True, standard_block_layers=L.Layer_scale_init_Block,
+                                 octic_block_layers=L.Layer_scale_init_BlockD8).to(DEV).eval()
+    _randomize(inv, seed=6)
+    with torch.no_grad():
+        base_logits = inv(img).float()
+        worst = max(rel_err(inv(O.image_action(g, img).contiguous()), base_logits) for g in O.GROUP)
+    report["logit_invariance_o1_weights"] = {"rel_l2_max_over_group": worst, "max_abs_of_output": float(base_logits.abs().max())}
+    assert worst < 2e-2, report
+    with capsys.disabled():
+        print("\nD8 equivariance report (hybrid / invariant ViT-H/14, bf16 GPU path):", json.dumps(report))
+    if os.path.isdir("gpurun_out"):
+        with open("gpurun_out/equivariance_h14.json", "w") as f:
+            json.dump(report, f, indent=1)
