@@ -1133,6 +1133,17 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   const int b_stage_bytes = (d->block_n / ncta) * kBlockK * 2;
   int stages = (kMaxDynSmem - 1024 - (kEpiWarps * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  static int stage_cap = -1;      // OCTIC_GEMM_STAGES=n caps the TMA ring depth (pipeline-depth experiments)
+  if (stage_cap < 0) {
+    const char* e = getenv("OCTIC_GEMM_STAGES");
+    stage_cap = e != nullptr ? atoi(e) : 0;
+  }
+  if (stage_cap >= 2 && stages > stage_cap) stages = stage_cap;
+  // Epilogue-paced small-K launches (head-major scatter; irrep groups with the fp32 residual epilogue) run FASTER with a
+  // shallow ring: a producer that runs far ahead only competes with the epilogue's own global traffic (measured,
+  // tools/gpu_s5_st.sh: qkv head-major 269 -> 214 us, octic proj + residual 152 -> 127 us at 2 stages; K >= 640 and the
+  // plain epilogues want the deep ring).
+  if (stage_cap == 0 && (d->head_H > 0 || (d->mode == EPI_RESID && kmax <= 320)) && stages > 2) stages = 2;
   if (stages < 2) return OCTIC_ERR_ARG;
   p.num_stages = stages;
   p.mode = d->mode;
