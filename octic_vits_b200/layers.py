@@ -684,13 +684,19 @@ class _DenseBlockBase(nn.Module):
     def _dp(self, i):
         raise NotImplementedError
 
-    def forward(self, x):
-        """fp32 [B, N, D] -> fp32 [B, N, D]; 7 kernels: LN, qkv, attention, proj+ls+dp+res, LN, fc1+GELU, fc2+ls+dp+res."""
+    def _drop_scales(self, batch: int, device, nested: bool = False):
+        """per-sample residual factors (mask / keep) of the two branches, None when stochastic depth is inactive"""
+        s1 = self._dp(1).sample(batch, device) if isinstance(self._dp(1), DropPathD8) else None
+        s2 = self._dp(2).sample(batch, device) if isinstance(self._dp(2), DropPathD8) else None
+        return s1, s2
+
+    def forward(self, x, nested: bool = False):
+        """fp32 [B, N, D] -> fp32 [B, N, D]; 7 kernels: LN, qkv, attention, proj+ls+dp+res, LN, fc1+GELU, fc2+ls+dp+res.
+        `nested`: the input is one element of a crop list (only the DINOv2 block's stochastic-depth rule cares)."""
         OF.require_cuda(x)
         x = _as_f32(x)
         B, N, D = x.shape
-        s1 = self._dp(1).sample(B, x.device) if isinstance(self._dp(1), DropPathD8) else None
-        s2 = self._dp(2).sample(B, x.device) if isinstance(self._dp(2), DropPathD8) else None
+        s1, s2 = self._drop_scales(B, x.device, nested)
         xn, xs = OF.LayerNormFn.apply(_rows(x), self.norm1.weight, self.norm1.bias, self.norm1.eps, False, True, True)
         a = self.attn.core_packed(xn.view(B, N, D))
         x2 = OF.LinearResidualFn.apply(_rows(a), self.attn.proj.weight, self.attn.proj.bias, self._gamma(1), xs,

@@ -68,9 +68,9 @@ class OcticVisionTransformer(nn.Module):
         self.octic_equi_break_layer = octic_equi_break_layer
         self.invariant = invariant
         self.num_register_tokens = num_register_tokens
-        if num_register_tokens > 0:
+        if num_register_tokens > 0 and type(self) is OcticVisionTransformer:
             # the reference's base-class register path indexes range(8) over a 5-tuple and cannot run
-            # (SURVEY.md Appendix A.5); only the DINOv2 subclass supports registers.
+            # (SURVEY.md Appendix A.5); only the DINOv2 subclass (dinov2_models.py) supports registers.
             raise NotImplementedError("register tokens are only supported by the DINOv2 wrapper in the reference")
 
         if self.invariant:
@@ -84,6 +84,11 @@ class OcticVisionTransformer(nn.Module):
             self.cls_token = nn.ParameterList(
                 [nn.Parameter(torch.zeros(1, 1, embed_dim // 8), requires_grad=(i == 0)) for i in range(4)] +
                 [nn.Parameter(torch.zeros(1, 1, 2, embed_dim // 4), requires_grad=False)])
+        assert num_register_tokens >= 0
+        if num_register_tokens > 0:     # reference model.py:106-110 (kept for the state-dict key order of subclasses)
+            self.register_tokens = nn.ParameterList(
+                [nn.Parameter(torch.zeros(1, num_register_tokens, embed_dim // 8), requires_grad=(i == 0))
+                 for i in range(8)])
         self.pos_embed = nn.ParameterList([
             nn.Parameter(torch.empty(img_size // patch_size // 2, img_size // patch_size // 2, embed_dim // 8))
             for _ in range(6)])

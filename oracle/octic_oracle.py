@@ -351,6 +351,56 @@ def octic_vit_forward(img: Tensor, w: Dict[str, Tensor], *, patch: int, depth: i
 
 
 # ------------------------------------------------------------------------------------------------------------
+# DINOv2 backbone  (octic_vits/dinov2_models.py:40-260)
+# ------------------------------------------------------------------------------------------------------------
+def dino_prepare_tokens(img: Tensor, w: Dict[str, Tensor], patch: int, masks: Optional[Tensor] = None) -> Five:
+    """OcticDinoVisionTransformer.prepare_tokens_with_masks (dinov2_models.py:113-136), native resolution:
+    patch embed -> iBOT mask-token substitution on the 8-tuple -> + unfolded pos-embed -> cls token (no pos-embed,
+    'deviating from DINOv2') -> register tokens between cls and patches."""
+    xs8 = five_to_eight(patch_embed_d8(img, w, "patch_embed.", patch))
+    if masks is not None:
+        xs8 = [torch.where(masks.unsqueeze(-1), w[f"mask_token.{i}"].to(x.dtype).unsqueeze(0), x)
+               for i, x in enumerate(xs8)]
+    pos8 = five_to_eight(unfold_pos_embed([w[f"pos_embed.{i}"] for i in range(6)]))
+    xs8 = [x + p.flatten(0, 1) for x, p in zip(xs8, pos8)]
+    B = img.shape[0]
+    xs8 = [torch.cat((w[f"cls_token.{i}"].expand(B, -1, -1), x), dim=1) for i, x in enumerate(xs8)]
+    if "register_tokens.0" in w:
+        xs8 = [torch.cat((x[:, :1], w[f"register_tokens.{i}"].expand(B, -1, -1), x[:, 1:]), dim=1)
+               for i, x in enumerate(xs8)]
+    return eight_to_five(xs8)
+
+
+def octic_dino_forward_features(img: Tensor, w: Dict[str, Tensor], *, patch: int, depth: int, num_heads: int,
+                                invariant: bool = False, masks: Optional[Tensor] = None,
+                                drop_scales: Optional[Sequence[Tuple[Optional[Tensor], Optional[Tensor]]]] = None,
+                                take: Sequence[int] = ()):
+    """forward_features (dinov2_models.py:170-198): octic BlockD8 x depth/2 (the subclass ignores
+    octic_equi_break_layer), bridge or invariantisation, dense NestedTensorBlock x depth/2
+    (dinov2/layers/block.py:43-114; same maths as dense_block with ls1/ls2.gamma), LayerNorm(eps=1e-6).
+    `drop_scales[i]` = explicit per-sample residual factors of block i (stochastic depth with injected draws).
+    `take` = dense block indices whose outputs are also returned (get_intermediate_layers, :200-227)."""
+    R = w["register_tokens.0"].shape[1] if "register_tokens.0" in w else 0
+    ds = drop_scales or [(None, None)] * depth
+    xs = dino_prepare_tokens(img, w, patch, masks)
+    for i in range(depth // 2):
+        xs = block_d8(xs, w, f"blocks.{i}.", num_heads, "dinov2", ds[i][0], ds[i][1])
+    if invariant:
+        x = F.linear(power_spectrum(xs), w["invariant_proj.weight"], w["invariant_proj.bias"])
+    else:
+        x = hybrid_bridge(xs)
+    taken = []
+    for i in range(depth // 2, depth):
+        x = dense_block(x, w, f"blocks.{i}.", num_heads, 1e-6, ds[i][0], ds[i][1])
+        if i in take:
+            taken.append(x)
+    xn = F.layer_norm(x, (x.shape[-1],), w["norm.weight"], w["norm.bias"], 1e-6)
+    out = {"x_norm_clstoken": xn[:, 0], "x_norm_regtokens": xn[:, 1:R + 1], "x_norm_patchtokens": xn[:, R + 1:],
+           "x_prenorm": x, "masks": masks}
+    return (out, taken) if take else out
+
+
+# ------------------------------------------------------------------------------------------------------------
 # group actions used by the equivariance tests  (octic_vits/d8_utils.py:76-274)
 # ------------------------------------------------------------------------------------------------------------
 GROUP = ("e", "r", "rr", "rrr", "m", "mr", "mrr", "mrrr")

@@ -107,6 +107,69 @@ def test_factories_and_param_counts():
     assert sum(p.numel() for p in m.parameters()) == 12_439_432 or abs(sum(p.numel() for p in m.parameters()) / 1e6 - 12.44) < 0.01
 
 
+@pytest.mark.parametrize("name", ["model_dinov2", "model_dinov2_inv"])
+def test_dinov2_reference_state_dict_loads_key_for_key(golden, name):
+    """OcticDinoVisionTransformer (reference dinov2_models.py:40-111): same keys, in the same order, same shapes."""
+    from octic_vits_b200.dinov2_models import OcticDinoVisionTransformer
+    fx = golden(name)
+    model = OcticDinoVisionTransformer(**fx["cfg"])
+    # the base class passes init_values=init_scale (1e-4) to every block, overriding a partial's 1e-5 (model.py:116-137)
+    assert float(model.blocks[0].ls1.alpha_A1[0].detach()) == pytest.approx(1e-4)
+    assert float(model.blocks[-1].ls1.gamma[0].detach()) == pytest.approx(1e-4)
+    assert list(model.state_dict().keys()) == list(fx["sd"].keys())
+    for k, v in model.state_dict().items():
+        assert v.shape == fx["sd"][k].shape, k
+    model.load_state_dict(fx["sd"], strict=True)
+    frozen = sorted(n for n, p in model.named_parameters() if not p.requires_grad)
+    want = [f"{g}.{i}" for g in ("cls_token", "mask_token") for i in range(1, 8)]
+    if fx["cfg"]["num_register_tokens"]:
+        want += [f"register_tokens.{i}" for i in range(1, 8)]
+    assert frozen == sorted(want)
+    assert isinstance(model.head, torch.nn.Identity)
+    assert model.no_weight_decay() >= {"pos_embed.0", "cls_token.0", "_orig_mod.pos_embed.5"}
+
+
+def test_dinov2_factories_and_contract():
+    from octic_vits_b200 import dinov2_models as DM
+    from octic_vits_b200.deit_models import create_model, list_models
+    assert {"hybrid_dinov2_vit_large_patch16", "hybrid_dinov2_vit_huge_patch16", "d8_inv_early_dinov2_vit_large_patch16",
+            "d8_inv_early_dinov2_vit_huge_patch16"} <= set(list_models())
+    m = create_model("hybrid_dinov2_vit_large_patch16", num_register_tokens=4, drop_path_rate=0.3)
+    assert m.depth == 24 and m.embed_dim == 1024 and m.register_tokens[0].shape == (1, 4, 128)
+    assert isinstance(m.blocks[0], DM.NestedTensorBlockD8) and isinstance(m.blocks[12], DM.NestedTensorBlock)
+    assert m.blocks[12].sample_drop_ratio == 0.3 and m.blocks[0].sample_drop_ratio == 0.3
+    with pytest.raises(AssertionError):
+        DM.OcticDinoVisionTransformer(img_size=32, patch_size=8, embed_dim=64, depth=3, num_heads=2)
+    with pytest.raises(AssertionError):
+        m.blocks[12]("not a tensor")
+    with pytest.raises(AssertionError):
+        m.blocks[0]("not a tuple")
+    with pytest.raises(AssertionError):
+        DM.MemEffAttention(64, 2)(torch.zeros(1, 4, 64), attn_bias=object())
+    with pytest.raises(AssertionError):          # only dense-half blocks can be taken (reference :206)
+        m.get_intermediate_layers(torch.zeros(1, 3, 224, 224), n=[3])
+    if not torch.cuda.is_available():
+        from octic_vits_b200._lib import OcticError
+        with pytest.raises(OcticError):
+            m(torch.zeros(1, 3, 224, 224))
+
+
+def test_dinov2_subset_stochastic_depth_factor():
+    """drop_add_residual_stochastic_depth (dinov2/layers/block.py:117-140) as a per-sample factor"""
+    from octic_vits_b200.dinov2_models import Block, subset_drop_scale
+    torch.manual_seed(0)
+    s = subset_drop_scale(10, 0.35, "cpu")
+    assert int((s > 0).sum()) == 6 and torch.allclose(s[s > 0], torch.tensor(10 / 6))
+    assert float(s.sum()) == pytest.approx(10.0)
+    assert int((subset_drop_scale(3, 0.99, "cpu") > 0).sum()) == 1
+    blk = Block(64, 2, init_values=1e-5, drop_path=0.05).train()
+    s1, s2 = blk._drop_scales(8, "cpu")                      # <= 0.1: Bernoulli mask / keep
+    assert all(v == 0.0 or v == pytest.approx(1 / 0.95) for v in s1.tolist())
+    s1, _ = blk._drop_scales(8, "cpu", nested=True)          # list input: always the subset rule
+    assert int((s1 > 0).sum()) == 7
+    assert blk.eval()._drop_scales(8, "cpu") == (None, None)
+
+
 def test_pos_embed_unfold_matches_oracle(golden):
     from octic_vits_b200.model import unfold_pos_embed_packed
     from oracle import octic_oracle as O

@@ -149,3 +149,35 @@ def test_oracle_equivariance_of_the_trunk(golden):
         want = O.token_action(g, base, has_cls=True)
         for a, b in zip(moved, want):
             torch.testing.assert_close(a, b, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("tag", ["model_dinov2", "model_dinov2_inv"])
+def test_dinov2_backbone(golden, tag):
+    """OcticDinoVisionTransformer (dinov2_models.py:40-260): token preparation with iBOT masks + registers, the
+    feature dict, forward(), get_intermediate_layers and parameter gradients (tools/make_golden_dinov2.py)."""
+    fx = golden(tag)
+    cfg = fx["cfg"]
+    kw = dict(patch=cfg["patch_size"], depth=cfg["depth"], num_heads=cfg["num_heads"], invariant=cfg["invariant"])
+    tok = O.dino_prepare_tokens(fx["img"], fx["sd"], cfg["patch_size"], fx["masks"])
+    for a, b in zip(tok, fx["tokens0"]):
+        close(a, b, rtol=2e-5, atol=5e-5)
+    feat = O.octic_dino_forward_features(fx["img"], fx["sd"], masks=fx["masks"], **kw)
+    for k, v in fx["feat"].items():
+        close(feat[k], v, rtol=1e-4, atol=5e-4)
+    assert feat["x_norm_regtokens"].shape[1] == cfg["num_register_tokens"]
+    feat2 = O.octic_dino_forward_features(fx["img2"], fx["sd"], **kw)
+    for k, v in fx["feat2"].items():
+        close(feat2[k], v, rtol=1e-4, atol=5e-4)
+    plain, taken = O.octic_dino_forward_features(fx["img"], fx["sd"], take=(cfg["depth"] - 1,), **kw)
+    close(plain["x_norm_clstoken"], fx["plain"], rtol=1e-4, atol=5e-4)
+    import torch.nn.functional as F
+    last = F.layer_norm(taken[0], (taken[0].shape[-1],), fx["sd"]["norm.weight"], fx["sd"]["norm.bias"], 1e-6)
+    R = cfg["num_register_tokens"]
+    close(last[:, 1 + R:], fx["inter_patch"], rtol=1e-4, atol=5e-4)
+    close(last[:, 0], fx["inter_cls"], rtol=1e-4, atol=5e-4)
+    w = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in fx["sd"].items()}
+    out = O.octic_dino_forward_features(fx["img"], w, masks=fx["masks"], **kw)
+    ((out["x_norm_clstoken"] * fx["w_cls"]).sum() + (out["x_norm_patchtokens"] * fx["w_patch"]).sum()).backward()
+    assert len(fx["gparams"]) > 40
+    for k, g in fx["gparams"].items():
+        close(w[k].grad, g, rtol=2e-4, atol=2e-3)
