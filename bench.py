@@ -173,6 +173,11 @@ def run_ours(args):
     from octic_vits_b200.parallel import FlatGrads, GraphedTrainStep
     fg = FlatGrads(model.parameters())
     flat = fg.flat
+    opt = None
+    if args.optimizer != "none":
+        # fused parameter update (optim.FusedOptimizer: LAMB = the DeiT-III recipe, experiments/train_deit.py:42)
+        from octic_vits_b200.optim import FusedOptimizer
+        opt = FusedOptimizer(model, fg, kind=args.optimizer, lr=1e-3, weight_decay=0.05)
 
     img_dev = torch.randn(B, 3, MODEL["img"], MODEL["img"], device=dev)
     tgt_dev = torch.randint(0, MODEL["classes"], (B,), device=dev)
@@ -186,10 +191,12 @@ def run_ours(args):
         loss = torch.nn.functional.cross_entropy(logits, tgt)
         loss.backward()
         fg.all_reduce()
+        if opt is not None:
+            opt.step()
         return loss
 
     # public-API step: fwd + loss + bwd captured in a CUDA graph (parallel.GraphedTrainStep), all-reduce after the replay
-    gstep = GraphedTrainStep(model, fg, img_dev.shape, warmup=args.warmup, use_graph=not args.no_graph)
+    gstep = GraphedTrainStep(model, fg, img_dev.shape, warmup=args.warmup, use_graph=not args.no_graph, optimizer=opt)
     step = gstep if gstep.graphed else eager_step
 
     def barrier():
@@ -267,7 +274,9 @@ def run_ours(args):
             "config": {"workload": "hybrid_deit_huge_patch14 (embed 1280, depth 32: 16 octic + 16 dense, heads 16, patch 14) "
                                    "DeiT-III training step: fwd + bwd" + (" + NCCL grad all-reduce" if world > 1 else ""),
                        "img": MODEL["img"], "batch_per_gpu": B, "global_batch": world * B, "tokens_per_image": 257,
-                       "drop_path": args.drop_path, "parallelism": f"dp{world}", "optimizer_step": False,
+                       "drop_path": args.drop_path, "parallelism": f"dp{world}",
+                       "optimizer_step": False if opt is None else f"fused {args.optimizer} (3 launches/step, weight "
+                                                                    "re-pack inside the graph)",
                        "cuda_graph": bool(gstep.graphed),
                        "l2": "activations per step (>50 GB) exceed the 126 MB L2; no explicit flush"},
             "model_tflops": ips * flops_img / 1e12,
@@ -306,6 +315,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the captured CUDA graph")
+    ap.add_argument("--optimizer", default="none", choices=["none", "lamb", "adamw"],
+                    help="also run the fused parameter update every step (the headline metric is fwd+bwd)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -255,6 +255,49 @@ int octic_im2col_patches(const float* img, int B, int Cin, int Himg, int Wimg, i
 /* fp32 <-> bf16 casts of [rows, cols] matrices (row strides in elements). */
 int octic_cast_f32_to_bf16(const float* x, long ldx, void* y, long ldy, long rows, int cols, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Parameter update of the training step, one or two streaming kernels over ALL parameters:
+ *   LAMB   -- the DeiT-III recipe's optimizer (experiments/train_deit.py:42 `args.opt = "fusedlamb"`, created by
+ *             timm.optim.create_optimizer at deit/main.py:365 -> apex.optimizers.FusedLAMB, apex pinned at commit
+ *             2386a912164 in DEIT_ENV.md:5-14; neither timm nor apex is vendored in the reference);
+ *   AdamW  -- the DINOv2 recipe's optimizer (dinov2/train/train.py:67-68 torch.optim.AdamW);
+ *   EMA    -- teacher / model-EMA update fused into the parameter write (dinov2/train/ssl_meta_arch.py:370-379
+ *             `_foreach_mul_` + `_foreach_add_`; deit/engine.py:81-82 ModelEma.update).
+ * Gradients and both moments live in flat fp32 buffers (the .grad views of parallel.FlatGrads); parameters (and EMA
+ * targets) stay where the framework allocated them and are reached through a chunk table: chunk i covers `len`
+ * elements (<= 8192) of one parameter tensor `p` (EMA copy `ema`, may be NULL) whose gradient/moments start at flat
+ * element `off`; `seg` indexes the per-tensor hyper-parameters.
+ *
+ *   stage 1   g' = g * min(1, max_grad_norm / sqrt(*gnorm_sq))                 (gnorm_sq == NULL: no clipping)
+ *             m = beta1*m + beta3*g';  v = beta2*v + (1-beta2)*g'^2
+ *             u = (m/bc1) / (sqrt(v/bc2) + eps) + weight_decay[seg]*p
+ *             apply != 0 (AdamW):  p -= lr*lr_scale[seg]*u  [; ema = mom*ema + (1-mom)*p]
+ *             apply == 0 (LAMB):   g <- u (in place), seg_norms[seg] += (|p|^2, |u|^2)
+ *   stage 2   (LAMB) p -= lr*lr_scale[seg]*trust*u,  trust = |p|/|u| when (use_nvlamb or weight_decay[seg] != 0) and
+ *             both norms are non-zero, else 1  [; ema update as above]
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct {
+  float* p;     /* parameter tensor + element offset of this chunk                         */
+  float* ema;   /* EMA copy of the same elements, or NULL                                  */
+  long off;     /* first element in the flat gradient / moment buffers                     */
+  int len;      /* elements in this chunk                                                  */
+  int seg;      /* parameter tensor index (hyper-parameters, norms)                        */
+} octic_optim_chunk;
+
+typedef struct {
+  float weight_decay;
+  float lr_scale;
+} octic_optim_seg;
+
+/* out[0] += sum_i x[i]^2  (out is zeroed by the caller) */
+int octic_optim_sqnorm(const float* x, long n, float* out, void* stream);
+int octic_optim_stage1(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, float* g, float* m,
+                       float* v, float* seg_norms, const float* gnorm_sq, float max_grad_norm, float beta1,
+                       float beta2, float beta3, float eps, float bc1, float bc2, float lr, int apply,
+                       float ema_momentum, void* stream);
+int octic_optim_lamb_stage2(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, const float* u,
+                            const float* seg_norms, float lr, int use_nvlamb, float ema_momentum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

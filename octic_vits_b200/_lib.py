@@ -65,6 +65,14 @@ class LsFinSeg(C.Structure):
                 ("dw_acc", C.c_void_p)]
 
 
+class OptimChunk(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("ema", C.c_void_p), ("off", C.c_long), ("len", C.c_int), ("seg", C.c_int)]
+
+
+class OptimSeg(C.Structure):
+    _fields_ = [("weight_decay", C.c_float), ("lr_scale", C.c_float)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
 
 # name -> argtypes; every function returns int.  Keep in sync with include/octic_b200.h (tests check that every
@@ -96,6 +104,9 @@ SIGNATURES = {
     "octic_bridge_permute": [_P, _L, _P, _L, _L, _I, _P],
     "octic_im2col_patches": [_P, _I, _I, _I, _I, _I, _P, _L, _P],
     "octic_cast_f32_to_bf16": [_P, _L, _P, _L, _L, _I, _P],
+    "octic_optim_sqnorm": [_P, _L, _P, _P],
+    "octic_optim_stage1": [_P, _I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _F, _I, _F, _P],
+    "octic_optim_lamb_stage2": [_P, _I, _P, _P, _P, _F, _I, _F, _P],
 }
 
 _lib = None

@@ -19,6 +19,13 @@ from ._lib import EPI_BF16, EPI_F32, EPI_GELU_BF16, EPI_GELU_BWD, EPI_RESID, Oct
 # (optimizer steps bump ._version; load_state_dict copies in place and bumps it too)
 # ----------------------------------------------------------------------------------------------------------------
 _pack_cache: dict = {}
+_param_epoch = 0     # bumped by writers that bypass autograd's version counters (optim.FusedOptimizer)
+
+
+def bump_param_epoch() -> None:
+    """Invalidate every cached pack: parameters were rewritten through raw pointers (the fused optimizer kernels)."""
+    global _param_epoch
+    _param_epoch += 1
 
 
 def _cached(tensors, build):
@@ -28,7 +35,7 @@ def _cached(tensors, build):
         with torch.no_grad():
             return build()
     ident = tuple(id(t) for t in tensors)
-    key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
+    key = (_param_epoch,) + tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in tensors)
     hit = _pack_cache.get(ident)
     if hit is not None and hit[0] == key and all(r() is t for r, t in zip(hit[2], tensors)):
         return hit[1]

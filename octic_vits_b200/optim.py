@@ -1,0 +1,136 @@
+"""Fused parameter update for the training step: LAMB (the DeiT-III recipe,
+experiments/train_deit.py:42 `fusedlamb` -> apex FusedLAMB through timm.optim.create_optimizer, deit/main.py:365),
+AdamW (the DINOv2 recipe, dinov2/train/train.py:67-68) and the EMA / teacher update (deit/engine.py:81-82,
+dinov2/train/ssl_meta_arch.py:370-379) -- two or three kernel launches per step for the WHOLE model instead of one
+multi-tensor launch group per optimizer phase.
+
+    fg  = FlatGrads(model.parameters())
+    opt = FusedOptimizer(model, fg, kind="lamb", lr=3e-3, weight_decay=0.05)        # or kind="adamw"
+    loss.backward(); fg.all_reduce(); opt.step()
+
+Gradients are read from the flat buffer of `parallel.FlatGrads` (LAMB overwrites them with the update direction; the
+buffer is zeroed at the start of the next step anyway); moments are two more flat fp32 buffers with the same offsets.
+Parameters stay where they are and are reached through a chunk table (include/octic_b200.h `octic_optim_chunk`).
+The kernels write parameters through raw pointers, so `step()` bumps functional's pack epoch: the bf16 GEMM operands
+are re-packed on next use.  No CPU path: CPU parameters raise OcticError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Optional, Tuple
+
+import torch
+
+from . import functional as OF
+from ._lib import OcticError, OptimChunk, OptimSeg, call
+from .parallel import FlatGrads
+
+CHUNK = 8192
+
+
+def timm_no_decay(model: torch.nn.Module) -> set:
+    """Names without weight decay under timm's `param_groups_weight_decay` (what create_optimizer applies at
+    deit/main.py:365): 1-D parameters, biases, and model.no_weight_decay() (model.py:229-234)."""
+    skip = set(model.no_weight_decay()) if hasattr(model, "no_weight_decay") else set()
+    return {n for n, p in model.named_parameters()
+            if p.requires_grad and (p.ndim <= 1 or n.endswith(".bias") or n in skip)}
+
+
+class FusedOptimizer:
+    """kind = "lamb": apex FusedLAMB defaults (bias_correction, grad_averaging, adam_w_mode, max_grad_norm=1.0,
+    use_nvlamb=False: the trust ratio only applies to tensors with weight decay);  kind = "adamw": torch.optim.AdamW.
+    `lr_scales` maps parameter names to a learning-rate multiplier (layer-wise decay / patch-embed multiplier of the
+    DINOv2 recipe).  `ema` = (ema_model, momentum): ema_model's parameters with the same names are updated as
+    ema = momentum*ema + (1-momentum)*param inside the kernel that writes the parameter."""
+
+    def __init__(self, model: torch.nn.Module, flat_grads: FlatGrads, kind: str = "lamb", lr: float = 1e-3,
+                 betas: Tuple[float, float] = (0.9, 0.999), eps: Optional[float] = None, weight_decay: float = 0.0,
+                 max_grad_norm: Optional[float] = None, no_decay: Optional[Iterable[str]] = None,
+                 lr_scales: Optional[Dict[str, float]] = None, grad_averaging: bool = True, use_nvlamb: bool = False,
+                 ema: Optional[Tuple[torch.nn.Module, float]] = None):
+        if kind not in ("lamb", "adamw"):
+            raise ValueError(f"unknown optimizer kind {kind!r}")
+        self.kind, self.lr, self.betas = kind, float(lr), (float(betas[0]), float(betas[1]))
+        self.eps = float(eps) if eps is not None else (1e-6 if kind == "lamb" else 1e-8)
+        self.max_grad_norm = float(max_grad_norm) if max_grad_norm is not None else (1.0 if kind == "lamb" else 0.0)
+        self.grad_averaging, self.use_nvlamb = grad_averaging, use_nvlamb
+        self.fg, self.step_count = flat_grads, 0
+        names = {id(p): n for n, p in model.named_parameters()}
+        no_decay = timm_no_decay(model) if no_decay is None else set(no_decay)
+        lr_scales = lr_scales or {}
+        dev = flat_grads.flat.device
+        if dev.type != "cuda":
+            raise OcticError("FusedOptimizer needs CUDA parameters: there is no CPU path")
+        ema_params, self.ema_momentum = {}, 0.0
+        if ema is not None:
+            ema_params, self.ema_momentum = dict(ema[0].named_parameters()), float(ema[1])
+        chunks, segs = [], []
+        for seg, (p, off) in enumerate(zip(flat_grads.params, flat_grads.offsets)):
+            name = names.get(id(p))
+            if name is None:
+                raise ValueError("flat_grads holds a parameter that is not in model.named_parameters()")
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise OcticError(f"{name}: parameters must be contiguous fp32")
+            e = ema_params.get(name)
+            if e is not None and (e.shape != p.shape or e.dtype != torch.float32 or not e.is_contiguous() or e.device != p.device):
+                raise OcticError(f"{name}: EMA copy must match the parameter (shape, fp32, contiguous, same device)")
+            segs.append((0.0 if name in no_decay else float(weight_decay), float(lr_scales.get(name, 1.0))))
+            for s in range(0, p.numel(), CHUNK):
+                n = min(CHUNK, p.numel() - s)
+                chunks.append((p.data_ptr() + 4 * s, e.data_ptr() + 4 * s if e is not None else 0, off + s, n, seg))
+        self.nchunks, self.nseg = len(chunks), len(segs)
+        self._ptrs = [p.data_ptr() for p in flat_grads.params]
+        ch = (OptimChunk * len(chunks))(*[OptimChunk(*c) for c in chunks])
+        sg = (OptimSeg * len(segs))(*[OptimSeg(*s) for s in segs])
+        self.chunks = torch.frombuffer(bytearray(bytes(ch)), dtype=torch.uint8).to(dev)
+        self.segs = torch.frombuffer(bytearray(bytes(sg)), dtype=torch.uint8).to(dev)
+        self.seg_hparams = segs
+        self.exp_avg = torch.zeros_like(flat_grads.flat)
+        self.exp_avg_sq = torch.zeros_like(flat_grads.flat)
+        self.scratch = torch.zeros(1 + 2 * self.nseg, dtype=torch.float32, device=dev)   # [gnorm^2 | (|p|^2, |u|^2) per seg]
+
+    def set_lr(self, lr: float) -> None:
+        self.lr = float(lr)
+
+    def set_ema_momentum(self, m: float) -> None:
+        self.ema_momentum = float(m)
+
+    def step(self) -> None:
+        """Consumes the (already all-reduced) flat gradients.  3 launches for LAMB (+1 memset), 1-2 for AdamW."""
+        if any(p.data_ptr() != q for p, q in zip(self.fg.params[:4], self._ptrs[:4])):
+            raise OcticError("parameters were re-allocated after the optimizer was built (call .to()/.cuda() first)")
+        self.step_count += 1
+        b1, b2 = self.betas
+        bc1, bc2 = 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count
+        beta3 = (1.0 - b1) if (self.grad_averaging or self.kind == "adamw") else 1.0
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        g, gnorm = self.fg.flat, None
+        lamb = self.kind == "lamb"
+        if lamb or self.max_grad_norm > 0.0:
+            self.scratch.zero_()
+        if self.max_grad_norm > 0.0:
+            call("octic_optim_sqnorm", g.data_ptr(), g.numel(), self.scratch.data_ptr(), st)
+            gnorm = self.scratch.data_ptr()
+        norms = self.scratch.data_ptr() + 4
+        call("octic_optim_stage1", self.chunks.data_ptr(), self.nchunks, self.segs.data_ptr(), g.data_ptr(),
+             self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), norms if lamb else None, gnorm, self.max_grad_norm,
+             b1, b2, beta3, self.eps, bc1, bc2, self.lr, 0 if lamb else 1, self.ema_momentum, st)
+        if lamb:
+            call("octic_optim_lamb_stage2", self.chunks.data_ptr(), self.nchunks, self.segs.data_ptr(), g.data_ptr(),
+                 norms, self.lr, 1 if self.use_nvlamb else 0, self.ema_momentum, st)
+        OF.bump_param_epoch()
+
+    def grad_norm(self) -> torch.Tensor:
+        """global gradient norm seen by the last step (device scalar; 0 when clipping is off)"""
+        return self.scratch[0].sqrt()
+
+    def state_dict(self) -> dict:
+        return {"kind": self.kind, "step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+
+    def load_state_dict(self, sd: dict) -> None:
+        if sd["kind"] != self.kind or sd["exp_avg"].numel() != self.exp_avg.numel():
+            raise ValueError("optimizer state does not match this optimizer")
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])

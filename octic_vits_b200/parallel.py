@@ -32,11 +32,15 @@ class FlatGrads:
         if not self.params:
             raise ValueError("no trainable parameters")
         dev = self.params[0].device
-        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32, device=dev)
+        # every view starts on a 16-byte boundary (the fused optimizer streams the buffer with 16-byte accesses)
+        self.offsets: List[int] = []
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            self.offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
         if fuse_accumulation:
             # the wgrad kernels add straight into these views (no zero fill + autograd accumulation kernel per weight)
             from . import functional as OF
@@ -71,13 +75,15 @@ class GraphedTrainStep:
     Inputs may live on the host (pinned) or on the device; gradients land in `fg.flat` (the parameters' .grad views).
     Input pipeline: `stage(images, targets)` starts the host -> device copy of a batch on a copy stream (it overlaps the
     step that is still running) and `run()` consumes the staged batch; `step(images, targets)` = stage + run.
-    The gradient all-reduce stays outside the graph: it is a single NCCL call per step.  If capture is impossible
+    The gradient all-reduce stays outside the graph: it is a single NCCL call per step, followed -- when an
+    `optimizer` (optim.FusedOptimizer) is given -- by its 2-4 launches; the weight packs are then part of the graph so
+    that every replay sees the updated parameters.  If capture is impossible
     (e.g. an op that synchronises), `graphed` is False and every call runs the eager step instead.
     """
 
     def __init__(self, model: torch.nn.Module, flat_grads: FlatGrads, image_shape, *, target_dtype=torch.long,
-                 loss_fn: Optional[Callable] = None, warmup: int = 3, use_graph: bool = True):
-        self.model, self.fg = model, flat_grads
+                 loss_fn: Optional[Callable] = None, warmup: int = 3, use_graph: bool = True, optimizer=None):
+        self.model, self.fg, self.optimizer = model, flat_grads, optimizer
         self.loss_fn = loss_fn or torch.nn.functional.cross_entropy
         dev = flat_grads.flat.device
         self.img = torch.zeros(tuple(image_shape), device=dev)
@@ -97,6 +103,11 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        if optimizer is not None:
+            # parameters change between replays: capture the fp32 -> bf16 weight packs inside the graph (cache miss
+            # on first use of every weight) so that each replay re-packs from the current values
+            from . import functional as OF
+            OF.bump_param_epoch()
         try:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -143,4 +154,6 @@ class GraphedTrainStep:
         else:
             loss = self._eager()
         self.fg.all_reduce()
+        if self.optimizer is not None:
+            self.optimizer.step()             # consumes the all-reduced flat gradients (optim.FusedOptimizer)
         return loss
