@@ -13,9 +13,10 @@ attention.py:36-89 `Attention` / `MemEffAttention`, mlp.py:16-40 `Mlp`, layer_sc
 Differences from the reference, all of them reference defects that this mirror does not
 inherit: list inputs (multi-crop) run without xformers -- the reference's block-diagonal attention over concatenated
 crops is, per crop, plain attention within each image, which is what the kernels compute crop by crop;
-`get_intermediate_layers(reshape=True)` works (the reference divides by the patch-size tuple).  Like the reference,
-the subclass ignores `octic_equi_break_layer` (first depth/2 blocks are octic) and passes `init_values=init_scale`
-(1e-4) to every block, overriding the factories' `partial(..., init_values=1e-5)` (model.py:116-137).
+`get_intermediate_layers(reshape=True)` works (the reference divides by the patch-size tuple); an explicit
+`octic_equi_break_layer=k` is honoured (the reference subclass swallows it and always uses depth/2, which stays the
+default).  Like the reference, `init_values=init_scale` (1e-4) reaches every block, overriding the factories'
+`partial(..., init_values=1e-5)` (model.py:116-137).
 """
 from __future__ import annotations
 
@@ -162,13 +163,23 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
                  num_heads: int = 12, mlp_ratio: float = 4.0, num_register_tokens: int = 0,
                  drop_path_rate: float = 0.0, octic_block_layers: Callable = NestedTensorBlockD8,
                  standard_block_layers: Callable = partial(NestedTensorBlock, attn_class=MemEffAttention),
-                 invariant: bool = False, **kwargs):
+                 invariant: bool = False, octic_equi_break_layer: Optional[int] = None,
+                 dynamic_img_size: bool = False, **kwargs):
+        """`octic_equi_break_layer` = number of leading octic blocks (README.md:36).  The reference subclass swallows
+        it in **kwargs and always breaks at depth/2; None keeps that behaviour, an int is
+        honoured here because BASELINE.json configs[4] sweeps it.  `dynamic_img_size=True` (not in the reference)
+        enables the multi-resolution path the reference intends but cannot run (Appendix B.1): square inputs whose side
+        is an even multiple of the patch size get a bicubically interpolated pos-embed (`interpolate_spatial_tuple`,
+        d8_utils.py:453-499) -- this is what DINOv2 local crops need.  Other **kwargs are ignored as in the reference."""
         super().__init__(img_size=img_size, patch_size=patch_size, embed_dim=embed_dim, depth=depth,
                          num_heads=num_heads, mlp_ratio=mlp_ratio, num_register_tokens=num_register_tokens,
                          octic_block_layers=octic_block_layers, standard_block_layers=standard_block_layers,
                          drop_path_rate=drop_path_rate, invariant=invariant, qkv_bias=True, ffn_bias=True,
-                         proj_bias=True)
+                         proj_bias=True, octic_equi_break_layer=octic_equi_break_layer)
         self.depth = depth
+        self.dynamic_img_size = dynamic_img_size
+        if dynamic_img_size:
+            self.patch_embed.strict_img_size = False
         C = embed_dim // 8
         g = img_size // patch_size // 2
         self.cls_token = nn.ParameterList([nn.Parameter(torch.zeros(1, 1, C), requires_grad=(i == 0)) for i in range(8)])
@@ -205,8 +216,16 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
         OF.require_cuda(x)
         B = x.shape[0]
         pos = unfold_pos_embed_packed(self.pos_embed)                                   # [np, D]
-        if pos.shape[0] != self.patch_embed.num_patches or x.shape[-1] != x.shape[-2]:
-            raise NotImplementedError("positional-embedding interpolation (the reference path is broken, SURVEY App. B)")
+        p = self.patch_embed.patch_size[0]
+        h0, w0 = x.shape[-2] // p, x.shape[-1] // p
+        if pos.shape[0] != h0 * w0 or h0 != w0:
+            if not self.dynamic_img_size:
+                raise NotImplementedError("positional-embedding interpolation needs dynamic_img_size=True (the "
+                                          "reference path is broken, SURVEY Appendix B.1)")
+            M = int(round(pos.shape[0] ** 0.5))
+            grid = pos.view(M, M, -1).permute(2, 0, 1).unsqueeze(0).float()
+            grid = nn.functional.interpolate(grid, size=(h0, w0), mode="bicubic", antialias=False)
+            pos = grid[0].permute(1, 2, 0).reshape(h0 * w0, -1)
         lead_rows = [self._packed(self.cls_token)[0]]
         if self.register_tokens is not None:
             lead_rows.append(self._packed(self.register_tokens)[0])
@@ -227,7 +246,7 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
     def _backbone_packed(self, t: Tensor, take: Sequence[int] = ()) -> Tuple[Tensor, List[Tensor]]:
         """octic blocks -> bridge / invariantisation -> dense blocks on one crop batch; returns the pre-norm tokens
         and the outputs of the dense blocks listed in `take`."""
-        half = self.depth // 2
+        half = self.octic_equi_break_layer
         for blk in self.blocks[:half]:
             if hasattr(blk, "forward_packed"):
                 t = blk.forward_packed(t)
@@ -262,7 +281,7 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
         """reference :138-168.  Each crop batch runs through the blocks' list interface when they have one
         (NestedTensorBlock*: stochastic depth then follows the reference's list rule), else block by block."""
         ts = [self.prepare_tokens_packed(x, m) for x, m in zip(x_list, masks_list)]
-        half = self.depth // 2
+        half = self.octic_equi_break_layer
         octic, dense = self.blocks[:half], self.blocks[half:]
         if all(isinstance(b, NestedTensorBlockD8) for b in octic) and all(isinstance(b, NestedTensorBlock) for b in dense):
             for blk in octic:
@@ -293,7 +312,7 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
         """reference :200-227 (only dense-half blocks can be taken)"""
         total = len(self.blocks)
         blocks_to_take = range(total - n, total) if isinstance(n, int) else n
-        assert all(i > self.depth // 2 for i in blocks_to_take), \
+        assert all(i > self.octic_equi_break_layer for i in blocks_to_take), \
             f"All block indices must be > half depth, got {blocks_to_take}"
         _, output = self._backbone_packed(self.prepare_tokens_packed(x), take=tuple(blocks_to_take))
         assert len(output) == len(blocks_to_take), f"only {len(output)} / {len(blocks_to_take)} blocks found"

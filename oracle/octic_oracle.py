@@ -362,6 +362,13 @@ def dino_prepare_tokens(img: Tensor, w: Dict[str, Tensor], patch: int, masks: Op
         xs8 = [torch.where(masks.unsqueeze(-1), w[f"mask_token.{i}"].to(x.dtype).unsqueeze(0), x)
                for i, x in enumerate(xs8)]
     pos8 = five_to_eight(unfold_pos_embed([w[f"pos_embed.{i}"] for i in range(6)]))
+    h0, w0 = img.shape[-2] // patch, img.shape[-1] // patch
+    if pos8[0].shape[0] * pos8[0].shape[1] != xs8[0].shape[1] or h0 != w0:
+        # interpolate_spatial_tuple (d8_utils.py:453-499) as written; the reference never reaches it (its callers pass
+        # the patch-size tuple), so this branch is UNPINNED by reference outputs
+        st = torch.stack([p.float() for p in pos8], dim=0).permute(0, 3, 1, 2)
+        st = F.interpolate(st, size=(h0, w0), mode="bicubic", antialias=False).permute(0, 2, 3, 1)
+        pos8 = [st[i].to(xs8[0].dtype) for i in range(8)]
     xs8 = [x + p.flatten(0, 1) for x, p in zip(xs8, pos8)]
     B = img.shape[0]
     xs8 = [torch.cat((w[f"cls_token.{i}"].expand(B, -1, -1), x), dim=1) for i, x in enumerate(xs8)]

@@ -146,6 +146,8 @@ def test_dinov2_factories_and_contract():
         m.blocks[0]("not a tuple")
     with pytest.raises(AssertionError):
         DM.MemEffAttention(64, 2)(torch.zeros(1, 4, 64), attn_bias=object())
+    k3 = DM.OcticDinoVisionTransformer(img_size=32, patch_size=8, embed_dim=64, depth=4, num_heads=2, octic_equi_break_layer=3)
+    assert [isinstance(b, DM.NestedTensorBlockD8) for b in k3.blocks] == [True, True, True, False]
     with pytest.raises(AssertionError):          # only dense-half blocks can be taken (reference :206)
         m.get_intermediate_layers(torch.zeros(1, 3, 224, 224), n=[3])
     if not torch.cuda.is_available():

@@ -141,3 +141,30 @@ def test_dinov2_large_backbone_runs_config5_shapes():
     for n, p in student.named_parameters():
         if p.requires_grad:
             assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_dinov2_local_crops_dynamic_img_size(golden):
+    """dynamic_img_size=True (not runnable in the reference): 96 px local crops next to 64 px
+    global crops in one list.  Parity against the oracle's restatement of interpolate_spatial_tuple (unpinned by
+    reference outputs) and D8 invariance of the invariant backbone's cls feature at the interpolated resolution."""
+    fx = golden("model_dinov2_inv")
+    cfg, sd = fx["cfg"], fx["sd"]
+    model = build(fx, dynamic_img_size=True).eval()
+    with pytest.raises(NotImplementedError):
+        build(fx).eval()(torch.zeros(1, 3, 96, 96, device=DEV))
+    with pytest.raises(AssertionError):
+        model(torch.zeros(1, 3, 88, 88, device=DEV))              # not an even multiple of the patch size
+    torch.manual_seed(5)
+    big, small = torch.randn(2, 3, 64, 64), torch.randn(3, 3, 96, 96)
+    kw = dict(patch=16, depth=cfg["depth"], num_heads=cfg["num_heads"], invariant=True)
+    with torch.no_grad():
+        outs = model([big.to(DEV), small.to(DEV)], is_training=True)
+        for o, im in zip(outs, (big, small)):
+            want = O.octic_dino_forward_features(im, sd, **kw)
+            assert o["x_norm_patchtokens"].shape[1] == (im.shape[-1] // 16) ** 2
+            for k in KEYS:
+                check(o[k], want[k], what=f"{im.shape[-1]} px {k}")
+        base = model(small.to(DEV))
+        for g in O.GROUP:
+            moved = model(O.image_action(g, small).to(DEV))
+            check(moved, base, rel=3e-2, mx=8e-2, what=f"cls invariance under {g} at 96 px")
