@@ -272,9 +272,12 @@ int octic_cast_f32_to_bf16(const float* x, long ldx, void* y, long ldy, long row
  *             m = beta1*m + beta3*g';  v = beta2*v + (1-beta2)*g'^2
  *             u = (m/bc1) / (sqrt(v/bc2) + eps) + weight_decay[seg]*p
  *             apply != 0 (AdamW):  p -= lr*lr_scale[seg]*u  [; ema = mom*ema + (1-mom)*p]
- *             apply == 0 (LAMB):   g <- u (in place), seg_norms[seg] += (|p|^2, |u|^2)
- *   stage 2   (LAMB) p -= lr*lr_scale[seg]*trust*u,  trust = |p|/|u| when (use_nvlamb or weight_decay[seg] != 0) and
+ *             apply == 0 (LAMB):   g <- u (in place), chunk_norms[chunk] = (|p|^2, |u|^2) of the chunk
+ *   stage 2   (LAMB) per-tensor norms = fixed-order sums of the chunk partials (into seg_norms[nsegs][2]), then
+ *             p -= lr*lr_scale[seg]*trust*u,  trust = |p|/|u| when (use_nvlamb or weight_decay[seg] != 0) and
  *             both norms are non-zero, else 1  [; ema update as above]
+ * All reductions are deterministic (no float atomics): replicas holding identical all-reduced gradients stay
+ * bit-identical.
  * --------------------------------------------------------------------------------------------------------- */
 typedef struct {
   float* p;     /* parameter tensor + element offset of this chunk                         */
@@ -287,16 +290,21 @@ typedef struct {
 typedef struct {
   float weight_decay;
   float lr_scale;
+  int first_chunk;   /* chunks of one tensor are contiguous in the table                   */
+  int num_chunks;
 } octic_optim_seg;
 
-/* out[0] += sum_i x[i]^2  (out is zeroed by the caller) */
-int octic_optim_sqnorm(const float* x, long n, float* out, void* stream);
+#define OCTIC_OPTIM_SQNORM_PARTIALS 1184   /* floats of workspace octic_optim_sqnorm needs (148 SMs x 8) */
+
+/* out[0] = sum_i x[i]^2 (two launches: per-CTA partials, fixed-order final sum) */
+int octic_optim_sqnorm(const float* x, long n, float* partials, float* out, void* stream);
 int octic_optim_stage1(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, float* g, float* m,
-                       float* v, float* seg_norms, const float* gnorm_sq, float max_grad_norm, float beta1,
+                       float* v, float* chunk_norms, const float* gnorm_sq, float max_grad_norm, float beta1,
                        float beta2, float beta3, float eps, float bc1, float bc2, float lr, int apply,
                        float ema_momentum, void* stream);
-int octic_optim_lamb_stage2(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, const float* u,
-                            const float* seg_norms, float lr, int use_nvlamb, float ema_momentum, void* stream);
+int octic_optim_lamb_stage2(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, int nsegs,
+                            const float* u, const float* chunk_norms, float* seg_norms, float lr, int use_nvlamb,
+                            float ema_momentum, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,7 +70,7 @@ class OptimChunk(C.Structure):
 
 
 class OptimSeg(C.Structure):
-    _fields_ = [("weight_decay", C.c_float), ("lr_scale", C.c_float)]
+    _fields_ = [("weight_decay", C.c_float), ("lr_scale", C.c_float), ("first_chunk", C.c_int), ("num_chunks", C.c_int)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_long, C.c_float
@@ -104,9 +104,9 @@ SIGNATURES = {
     "octic_bridge_permute": [_P, _L, _P, _L, _L, _I, _P],
     "octic_im2col_patches": [_P, _I, _I, _I, _I, _I, _P, _L, _P],
     "octic_cast_f32_to_bf16": [_P, _L, _P, _L, _L, _I, _P],
-    "octic_optim_sqnorm": [_P, _L, _P, _P],
+    "octic_optim_sqnorm": [_P, _L, _P, _P, _P],
     "octic_optim_stage1": [_P, _I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _F, _I, _F, _P],
-    "octic_optim_lamb_stage2": [_P, _I, _P, _P, _P, _F, _I, _F, _P],
+    "octic_optim_lamb_stage2": [_P, _I, _P, _I, _P, _P, _P, _F, _I, _F, _P],
 }
 
 _lib = None
@@ -142,7 +142,8 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_linear_d8_pack_weights_scaled": 5, "octic_attention_bwd": 2}   # bwd: delta + main (legacy: +1)
+KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_linear_d8_pack_weights_scaled": 5, "octic_attention_bwd": 2,
+                    "octic_optim_sqnorm": 2, "octic_optim_lamb_stage2": 2}   # bwd: delta + main (legacy: +1)
 
 
 class _Stats:

@@ -1,6 +1,8 @@
 // Fused parameter update (LAMB / AdamW + EMA) over all parameters of the model in one or two launches.
 // HBM-bound streaming kernels: one CTA per <= 8192-element chunk of one parameter tensor, 16-byte accesses when the
-// chunk is 16-byte aligned, per-tensor norms by block reduction + one atomicAdd pair per CTA.
+// chunk is 16-byte aligned.  Every reduction (global gradient norm, per-tensor norms) is DETERMINISTIC: CTAs write
+// partial sums, a small kernel adds them in a fixed order -- data-parallel replicas that hold bit-identical gradients
+// after the all-reduce therefore stay bit-identical (float atomics would let them drift by an ulp per step).
 // Algorithmic bytes per parameter element: AdamW 16 read + 12 write (+8 with EMA); LAMB stage 1 16 + 12, stage 2
 // 8 + 4 (+8 with EMA).  See include/octic_b200.h for the arithmetic and the reference call sites.
 #include "octic_capi_internal.h"
@@ -28,7 +30,8 @@ __device__ __forceinline__ float block_sum(float x, float* sh) {
   return t;   // valid in thread 0
 }
 
-__global__ void __launch_bounds__(OPT_THREADS) optim_sqnorm_kernel(const float* __restrict__ x, long n, float* out) {
+__global__ void __launch_bounds__(OPT_THREADS) optim_sqnorm_kernel(const float* __restrict__ x, long n,
+                                                                   float* __restrict__ partials) {
   __shared__ float sh[OPT_THREADS / 32];
   float acc = 0.f;
   const long stride = static_cast<long>(gridDim.x) * OPT_THREADS;
@@ -45,7 +48,34 @@ __global__ void __launch_bounds__(OPT_THREADS) optim_sqnorm_kernel(const float* 
     for (long i = tid; i < n; i += stride) acc += x[i] * x[i];
   }
   const float t = block_sum(acc, sh);
-  if (threadIdx.x == 0) atomicAdd(out, t);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// out[j] = sum of `count` partials in a fixed order (thread-strided, then the shuffle tree); one CTA per output.
+// mode 0: one output from partials[0..count);  mode 1: per tensor, two interleaved partials per chunk.
+__global__ void __launch_bounds__(OPT_THREADS)
+optim_reduce_kernel(const float* __restrict__ partials, int count, const octic_optim_seg* __restrict__ segs,
+                    float* __restrict__ out) {
+  __shared__ float sh[OPT_THREADS / 32];
+  if (segs == nullptr) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < count; i += OPT_THREADS) acc += partials[i];
+    const float t = block_sum(acc, sh);
+    if (threadIdx.x == 0) out[0] = t;
+    return;
+  }
+  const octic_optim_seg sg = segs[blockIdx.x];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < sg.num_chunks; i += OPT_THREADS) {
+    a += partials[2 * (sg.first_chunk + i)];
+    b += partials[2 * (sg.first_chunk + i) + 1];
+  }
+  const float ta = block_sum(a, sh);
+  const float tb = block_sum(b, sh);
+  if (threadIdx.x == 0) {
+    out[2 * blockIdx.x] = ta;
+    out[2 * blockIdx.x + 1] = tb;
+  }
 }
 
 // one element of stage 1; returns the update u and advances the moments
@@ -61,7 +91,7 @@ __device__ __forceinline__ float adam_update(float p, float g, float& m, float& 
 template <bool APPLY>
 __global__ void __launch_bounds__(OPT_THREADS)
 optim_stage1_kernel(const octic_optim_chunk* __restrict__ chunks, const octic_optim_seg* __restrict__ segs,
-                    float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* seg_norms,
+                    float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float* __restrict__ chunk_norms,
                     const float* __restrict__ gnorm_sq, OptArgs a) {
   __shared__ float sh[OPT_THREADS / 32];
   const octic_optim_chunk c = chunks[blockIdx.x];
@@ -127,8 +157,8 @@ optim_stage1_kernel(const octic_optim_chunk* __restrict__ chunks, const octic_op
     const float ps = block_sum(psq, sh);
     const float us = block_sum(usq, sh);
     if (threadIdx.x == 0) {
-      atomicAdd(seg_norms + 2 * c.seg, ps);
-      atomicAdd(seg_norms + 2 * c.seg + 1, us);
+      chunk_norms[2 * blockIdx.x] = ps;
+      chunk_norms[2 * blockIdx.x + 1] = us;
     }
   }
 }
@@ -174,41 +204,45 @@ using namespace octic;
 
 extern "C" {
 
-int octic_optim_sqnorm(const float* x, long n, float* out, void* stream) {
-  if (x == nullptr || out == nullptr || n < 0) return OCTIC_ERR_ARG;
-  if (n == 0) return OCTIC_OK;
+int octic_optim_sqnorm(const float* x, long n, float* partials, float* out, void* stream) {
+  if (x == nullptr || out == nullptr || partials == nullptr || n < 0) return OCTIC_ERR_ARG;
   long blocks = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
-  const long cap = 148L * 8;
-  if (blocks > cap) blocks = cap;
+  if (blocks > OCTIC_OPTIM_SQNORM_PARTIALS) blocks = OCTIC_OPTIM_SQNORM_PARTIALS;
   if (blocks < 1) blocks = 1;
-  optim_sqnorm_kernel<<<static_cast<unsigned>(blocks), OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(x, n, out);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  optim_sqnorm_kernel<<<static_cast<unsigned>(blocks), OPT_THREADS, 0, s>>>(x, n, partials);
+  optim_reduce_kernel<<<1, OPT_THREADS, 0, s>>>(partials, static_cast<int>(blocks), nullptr, out);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
 int octic_optim_stage1(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, float* g, float* m,
-                       float* v, float* seg_norms, const float* gnorm_sq, float max_grad_norm, float beta1,
+                       float* v, float* chunk_norms, const float* gnorm_sq, float max_grad_norm, float beta1,
                        float beta2, float beta3, float eps, float bc1, float bc2, float lr, int apply,
                        float ema_momentum, void* stream) {
   if (chunks == nullptr || segs == nullptr || g == nullptr || m == nullptr || v == nullptr || nchunks < 0)
     return OCTIC_ERR_ARG;
-  if (!apply && seg_norms == nullptr) return OCTIC_ERR_ARG;
+  if (!apply && chunk_norms == nullptr) return OCTIC_ERR_ARG;
   if (!(bc1 > 0.f) || !(bc2 > 0.f)) return OCTIC_ERR_ARG;
   if (nchunks == 0) return OCTIC_OK;
   OptArgs a{max_grad_norm, beta1, beta2, beta3, eps, 1.f / bc1, 1.f / bc2, lr, ema_momentum};
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (apply)
-    optim_stage1_kernel<true><<<nchunks, OPT_THREADS, 0, s>>>(chunks, segs, g, m, v, seg_norms, gnorm_sq, a);
+    optim_stage1_kernel<true><<<nchunks, OPT_THREADS, 0, s>>>(chunks, segs, g, m, v, chunk_norms, gnorm_sq, a);
   else
-    optim_stage1_kernel<false><<<nchunks, OPT_THREADS, 0, s>>>(chunks, segs, g, m, v, seg_norms, gnorm_sq, a);
+    optim_stage1_kernel<false><<<nchunks, OPT_THREADS, 0, s>>>(chunks, segs, g, m, v, chunk_norms, gnorm_sq, a);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
-int octic_optim_lamb_stage2(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, const float* u,
-                            const float* seg_norms, float lr, int use_nvlamb, float ema_momentum, void* stream) {
-  if (chunks == nullptr || segs == nullptr || u == nullptr || seg_norms == nullptr || nchunks < 0) return OCTIC_ERR_ARG;
-  if (nchunks == 0) return OCTIC_OK;
-  optim_lamb_stage2_kernel<<<nchunks, OPT_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(chunks, segs, u, seg_norms, lr,
-                                                                                            use_nvlamb, ema_momentum);
+int octic_optim_lamb_stage2(const octic_optim_chunk* chunks, int nchunks, const octic_optim_seg* segs, int nsegs,
+                            const float* u, const float* chunk_norms, float* seg_norms, float lr, int use_nvlamb,
+                            float ema_momentum, void* stream) {
+  if (chunks == nullptr || segs == nullptr || u == nullptr || chunk_norms == nullptr || seg_norms == nullptr ||
+      nchunks < 0 || nsegs < 0)
+    return OCTIC_ERR_ARG;
+  if (nchunks == 0 || nsegs == 0) return OCTIC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  optim_reduce_kernel<<<nsegs, OPT_THREADS, 0, s>>>(chunk_norms, 0, segs, seg_norms);
+  optim_lamb_stage2_kernel<<<nchunks, OPT_THREADS, 0, s>>>(chunks, segs, u, seg_norms, lr, use_nvlamb, ema_momentum);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 

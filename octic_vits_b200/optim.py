@@ -26,6 +26,7 @@ from ._lib import OcticError, OptimChunk, OptimSeg, call
 from .parallel import FlatGrads
 
 CHUNK = 8192
+SQNORM_PARTIALS = 1184      # OCTIC_OPTIM_SQNORM_PARTIALS
 
 
 def timm_no_decay(model: torch.nn.Module) -> set:
@@ -74,7 +75,8 @@ class FusedOptimizer:
             e = ema_params.get(name)
             if e is not None and (e.shape != p.shape or e.dtype != torch.float32 or not e.is_contiguous() or e.device != p.device):
                 raise OcticError(f"{name}: EMA copy must match the parameter (shape, fp32, contiguous, same device)")
-            segs.append((0.0 if name in no_decay else float(weight_decay), float(lr_scales.get(name, 1.0))))
+            segs.append((0.0 if name in no_decay else float(weight_decay), float(lr_scales.get(name, 1.0)), len(chunks),
+                         (p.numel() + CHUNK - 1) // CHUNK))
             for s in range(0, p.numel(), CHUNK):
                 n = min(CHUNK, p.numel() - s)
                 chunks.append((p.data_ptr() + 4 * s, e.data_ptr() + 4 * s if e is not None else 0, off + s, n, seg))
@@ -84,10 +86,13 @@ class FusedOptimizer:
         sg = (OptimSeg * len(segs))(*[OptimSeg(*s) for s in segs])
         self.chunks = torch.frombuffer(bytearray(bytes(ch)), dtype=torch.uint8).to(dev)
         self.segs = torch.frombuffer(bytearray(bytes(sg)), dtype=torch.uint8).to(dev)
-        self.seg_hparams = segs
+        self.seg_hparams = [(wd, sc) for wd, sc, _, _ in segs]
         self.exp_avg = torch.zeros_like(flat_grads.flat)
         self.exp_avg_sq = torch.zeros_like(flat_grads.flat)
-        self.scratch = torch.zeros(1 + 2 * self.nseg, dtype=torch.float32, device=dev)   # [gnorm^2 | (|p|^2, |u|^2) per seg]
+        # reduction workspace: [gnorm^2 | pad | per-CTA gnorm partials | (|p|^2, |u|^2) per tensor | ... per chunk]
+        self._o_part, self._o_seg = 4, 4 + SQNORM_PARTIALS
+        self._o_chunk = self._o_seg + 2 * self.nseg
+        self.scratch = torch.zeros(self._o_chunk + 2 * self.nchunks, dtype=torch.float32, device=dev)
 
     def set_lr(self, lr: float) -> None:
         self.lr = float(lr)
@@ -96,7 +101,8 @@ class FusedOptimizer:
         self.ema_momentum = float(m)
 
     def step(self) -> None:
-        """Consumes the (already all-reduced) flat gradients.  3 launches for LAMB (+1 memset), 1-2 for AdamW."""
+        """Consumes the (already all-reduced) flat gradients.  5 launches for LAMB (grad-norm partials + final sum,
+        stage 1, per-tensor norm sums, stage 2), 1 for AdamW (3 with clipping).  No atomics: bit-reproducible."""
         if any(p.data_ptr() != q for p, q in zip(self.fg.params[:4], self._ptrs[:4])):
             raise OcticError("parameters were re-allocated after the optimizer was built (call .to()/.cuda() first)")
         self.step_count += 1
@@ -106,18 +112,18 @@ class FusedOptimizer:
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         g, gnorm = self.fg.flat, None
         lamb = self.kind == "lamb"
-        if lamb or self.max_grad_norm > 0.0:
-            self.scratch.zero_()
+        base = self.scratch.data_ptr()
         if self.max_grad_norm > 0.0:
-            call("octic_optim_sqnorm", g.data_ptr(), g.numel(), self.scratch.data_ptr(), st)
-            gnorm = self.scratch.data_ptr()
-        norms = self.scratch.data_ptr() + 4
+            call("octic_optim_sqnorm", g.data_ptr(), g.numel(), base + 4 * self._o_part, base, st)
+            gnorm = base
+        chunk_norms = base + 4 * self._o_chunk
         call("octic_optim_stage1", self.chunks.data_ptr(), self.nchunks, self.segs.data_ptr(), g.data_ptr(),
-             self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), norms if lamb else None, gnorm, self.max_grad_norm,
-             b1, b2, beta3, self.eps, bc1, bc2, self.lr, 0 if lamb else 1, self.ema_momentum, st)
+             self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), chunk_norms if lamb else None, gnorm,
+             self.max_grad_norm, b1, b2, beta3, self.eps, bc1, bc2, self.lr, 0 if lamb else 1, self.ema_momentum, st)
         if lamb:
-            call("octic_optim_lamb_stage2", self.chunks.data_ptr(), self.nchunks, self.segs.data_ptr(), g.data_ptr(),
-                 norms, self.lr, 1 if self.use_nvlamb else 0, self.ema_momentum, st)
+            call("octic_optim_lamb_stage2", self.chunks.data_ptr(), self.nchunks, self.segs.data_ptr(), self.nseg,
+                 g.data_ptr(), chunk_norms, base + 4 * self._o_seg, self.lr, 1 if self.use_nvlamb else 0,
+                 self.ema_momentum, st)
         OF.bump_param_epoch()
 
     def grad_norm(self) -> torch.Tensor:

@@ -70,12 +70,23 @@ def run(kind, steps=4, ema=False, **kw):
             torch.testing.assert_close(dict(ema_model.named_parameters())[n].detach().cpu(), r, rtol=2e-5, atol=2e-6)
         assert torch.equal(ema_model.frozen, Bag().frozen.to(DEV))
     assert torch.equal(model.frozen.cpu(), Bag().frozen)
+    opt.final_params = [p.detach().clone() for p in fg.params]
     return opt
 
 
 def test_fused_lamb_matches_oracle():
     opt = run("lamb", lr=3e-3, weight_decay=0.05)
     assert float(opt.grad_norm()) > 0
+
+
+def test_fused_update_is_bit_reproducible():
+    """no float atomics in the norm reductions: two runs from the same state give identical bits, which is what keeps
+    data-parallel replicas (identical all-reduced gradients) identical"""
+    a = run("lamb", lr=3e-3, weight_decay=0.05, steps=6)
+    b = run("lamb", lr=3e-3, weight_decay=0.05, steps=6)
+    for x, y in zip(a.final_params, b.final_params):
+        assert torch.equal(x, y)
+    assert torch.equal(a.exp_avg_sq, b.exp_avg_sq) and float(a.grad_norm()) == float(b.grad_norm())
 
 
 def test_fused_lamb_with_ema_matches_oracle():
