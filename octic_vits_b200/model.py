@@ -68,6 +68,9 @@ class OcticVisionTransformer(nn.Module):
         self.octic_equi_break_layer = octic_equi_break_layer
         self.invariant = invariant
         self.num_register_tokens = num_register_tokens
+        # optional callable applied (as a tensor hook) to the gradient that flows from the dense half into the octic
+        # half: parallel.install_early_allreduce starts the gradient exchange of the dense half there
+        self._bridge_grad_hook = None
         if num_register_tokens > 0 and type(self) is OcticVisionTransformer:
             # the reference's base-class register path indexes range(8) over a 5-tuple and cannot run
             # (SURVEY.md Appendix A.5); only the DINOv2 subclass (dinov2_models.py) supports registers.
@@ -165,6 +168,8 @@ class OcticVisionTransformer(nn.Module):
             t = t.view(B, N, D)
         else:
             t = OF.BridgeFn.apply(_rows(t)).view(B, N, D)
+        if self._bridge_grad_hook is not None and t.requires_grad:
+            t.register_hook(self._bridge_grad_hook)
         for blk in self.blocks[self.octic_equi_break_layer:]:
             t = blk(t)
         if self.global_pool:

@@ -45,21 +45,111 @@ class FlatGrads:
             # the wgrad kernels add straight into these views (no zero fill + autograd accumulation kernel per weight)
             from . import functional as OF
             OF.ACCUMULATE_INTO_GRAD = True
+        self.split = self.flat.numel()      # flat[split:] = gradients that are final early in backward (none by default)
+        self._early_done = False
+        self._comm_stream = None
 
     def zero(self) -> None:
         self.flat.zero_()
 
-    def all_reduce(self, average: bool = True) -> None:
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            if average and dist.get_backend() == "nccl":
-                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)      # the division happens inside the NCCL kernel
-            else:
-                dist.all_reduce(self.flat)
-                if average:
-                    self.flat.div_(dist.get_world_size())
+    def begin_step(self) -> None:
+        """zero the buffer and forget any early all-reduce of the previous step"""
+        self.flat.zero_()
+        self._early_done = False
+
+    @staticmethod
+    def _reduce(t: torch.Tensor, average: bool) -> None:
+        if t.numel() == 0:
+            return
+        if average and dist.get_backend() == "nccl":
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)      # the division happens inside the NCCL kernel
+        else:
+            dist.all_reduce(t)
+            if average:
+                t.div_(dist.get_world_size())
+
+    @staticmethod
+    def _distributed() -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    # ---- overlap of the exchange with backward -------------------------------------------------------------------
+    def mark_early_from(self, first: torch.nn.Parameter) -> None:
+        """Declare that the gradients of `first` and of every parameter after it in the buffer are final once the
+        backward pass has passed a known point (for the hybrid ViT: the bridge between the dense and the octic half --
+        blocks[k:], norm and head sit at the end of model.parameters() and their backward runs first)."""
+        for p, o in zip(self.params, self.offsets):
+            if p is first:
+                self.split = o
+                return
+        raise ValueError("parameter is not in this buffer")
+
+    def all_reduce_early(self, average: bool = True) -> None:
+        """All-reduce flat[split:] on a communication stream that forks from the current stream here; the rest of
+        backward keeps running on the current stream.  Called from an autograd hook (install_early_allreduce)."""
+        if self._early_done or self.split >= self.flat.numel() or not self._distributed():
+            return
+        tail = self.flat[self.split:]
+        if tail.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=tail.device)
+            cur = torch.cuda.current_stream(tail.device)
+            self._comm_stream.wait_stream(cur)
+            with torch.cuda.stream(self._comm_stream):
+                self._reduce(tail, average)
+        else:
+            self._reduce(tail, average)
+        self._early_done = True
+
+    def join_early(self) -> None:
+        """Make the current stream wait for the early all-reduce (must run before a CUDA-graph capture ends)."""
+        if self._early_done and self._comm_stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._comm_stream)
+
+    def all_reduce(self, average: bool = True, early_done: Optional[bool] = None) -> None:
+        """Mean (or sum) over ranks of every gradient not yet reduced by all_reduce_early() in this step.
+        `early_done` overrides the per-step flag (a CUDA-graph replay re-runs the captured early all-reduce without
+        passing through Python)."""
+        done = self._early_done if early_done is None else early_done
+        self._early_done = False
+        if not self._distributed():
+            return
+        if done:
+            self.join_early()
+            self._reduce(self.flat[:self.split], average)
+        else:
+            self._reduce(self.flat, average)
 
     def nbytes(self) -> int:
         return self.flat.numel() * 4
+
+
+def install_early_allreduce(model: torch.nn.Module, fg: FlatGrads) -> bool:
+    """Overlap the gradient exchange with backward for OcticVisionTransformer-style models: the model calls
+    `model._bridge_grad_hook` on the gradient that flows from the dense half into the octic half; at that point the
+    gradients of blocks[k:], norm and head are final, and their all-reduce (88 % of the bytes for the hybrid ViT-H/14)
+    runs on a side stream while the octic half is still in backward.  Returns False (and installs nothing) when the
+    model has no such hook point or the parameter order does not allow it."""
+    k = getattr(model, "octic_equi_break_layer", None)
+    blocks = getattr(model, "blocks", None)
+    if k is None or blocks is None or k >= len(blocks) or not hasattr(model, "_bridge_grad_hook"):
+        return False
+    first = next((p for p in blocks[k].parameters() if p.requires_grad), None)
+    if first is None:
+        return False
+    early_ok = {id(p) for b in blocks[k:] for p in b.parameters()}
+    for name in ("norm", "head"):
+        early_ok |= {id(p) for p in getattr(model, name, torch.nn.Identity()).parameters()}
+    fg.mark_early_from(first)
+    tail = [p for p, o in zip(fg.params, fg.offsets) if o >= fg.split]
+    if not all(id(p) in early_ok for p in tail):          # e.g. DINOv2 mask_token: registered last, used first
+        fg.split = fg.flat.numel()
+        return False
+
+    def hook(grad):
+        fg.all_reduce_early()
+        return grad
+    model._bridge_grad_hook = hook
+    return True
 
 
 class GraphedTrainStep:
@@ -93,7 +183,7 @@ class GraphedTrainStep:
         self._staged = torch.cuda.Event()
         self._consumed = torch.cuda.Event()
         self._consumed.record()
-        self.graph, self.loss, self.graphed = None, None, False
+        self.graph, self.loss, self.graphed, self.early_in_graph = None, None, False, False
         if not use_graph:
             return
         side = torch.cuda.Stream(device=dev)
@@ -108,21 +198,33 @@ class GraphedTrainStep:
             # on first use of every weight) so that each replay re-packs from the current values
             from . import functional as OF
             OF.bump_param_epoch()
-        try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                loss = self._eager()
-            self.graph, self.loss, self.graphed = graph, loss, True
-        except Exception as e:                            # noqa: BLE001 - any capture failure -> eager path, reported
-            self.capture_error = repr(e)
-            torch.cuda.synchronize(dev)
+        for attempt in (0, 1):
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    loss = self._eager()
+                # a replay re-runs whatever early all-reduce the capture recorded (NCCL inside the graph)
+                self.early_in_graph = self.fg._early_done
+                self.fg._early_done = False
+                self.graph, self.loss, self.graphed = graph, loss, True
+                break
+            except Exception as e:                        # noqa: BLE001 - any capture failure -> eager path, reported
+                self.capture_error = repr(e)
+                torch.cuda.synchronize(dev)
+                self.fg._early_done = False
+                if attempt == 0 and getattr(model, "_bridge_grad_hook", None) is not None:
+                    model._bridge_grad_hook = None        # retry without the in-graph exchange
+                    self.fg.split = self.fg.flat.numel()
+                    continue
+                break
 
     def _eager(self) -> torch.Tensor:
         from . import ops
         ops.begin_step()                  # one zero fill for all red.add scratch of the step
-        self.fg.flat.zero_()
+        self.fg.begin_step()
         loss = self.loss_fn(self.model(self.img), self.tgt)
         loss.backward()
+        self.fg.join_early()              # the early all-reduce (if any) rejoins the step's stream here
         return loss
 
     def stage(self, images: torch.Tensor, targets: torch.Tensor) -> None:
@@ -151,9 +253,10 @@ class GraphedTrainStep:
         if self.graphed:
             self.graph.replay()
             loss = self.loss
+            self.fg.all_reduce(early_done=self.early_in_graph)
         else:
             loss = self._eager()
-        self.fg.all_reduce()
+            self.fg.all_reduce()
         if self.optimizer is not None:
             self.optimizer.step()             # consumes the all-reduced flat gradients (optim.FusedOptimizer)
         return loss

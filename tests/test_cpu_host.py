@@ -259,3 +259,90 @@ def test_flat_grad_allreduce_world2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+_GLOO_EARLY_WORKER = r"""
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from octic_vits_b200.parallel import FlatGrads, install_early_allreduce, shard_batch
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+
+
+class Toy(torch.nn.Module):
+    # the hook point and parameter order of OcticVisionTransformer: front end | blocks[:k] | blocks[k:] | norm | head
+    def __init__(self, late_param_last=False):
+        super().__init__()
+        self.embed = torch.nn.Linear(6, 8)
+        self.blocks = torch.nn.ModuleList([torch.nn.Linear(8, 8) for _ in range(4)])
+        self.norm = torch.nn.LayerNorm(8)
+        self.head = torch.nn.Linear(8, 3)
+        if late_param_last:
+            self.mask_token = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(8))])   # registered last, used first (DINOv2)
+        self.octic_equi_break_layer = 2
+        self._bridge_grad_hook = None
+        self.fired = 0
+
+    def forward(self, x):
+        t = self.embed(x) + (self.mask_token[0] if hasattr(self, "mask_token") else 0)
+        for b in self.blocks[:2]:
+            t = torch.tanh(b(t))
+        if self._bridge_grad_hook is not None and t.requires_grad:
+            t.register_hook(self._bridge_grad_hook)
+        for b in self.blocks[2:]:
+            t = torch.tanh(b(t))
+        return self.head(self.norm(t))
+
+
+torch.manual_seed(0)
+model, ref = Toy(), Toy()
+ref.load_state_dict(model.state_dict())
+fg = FlatGrads(model.parameters(), fuse_accumulation=False)
+assert install_early_allreduce(model, fg)
+names = [n for n, _ in model.named_parameters()]
+assert fg.split == fg.offsets[names.index("blocks.2.weight")] and 0 < fg.split < fg.flat.numel()
+calls = []
+orig = fg.all_reduce_early
+fg.all_reduce_early = lambda *a, **k: (calls.append(fg._early_done), orig(*a, **k))
+data = torch.randn(8, 6, generator=torch.Generator().manual_seed(1))
+a, b = shard_batch(8, rank, 2)
+for step in range(2):                                   # two steps: the per-step flag must reset
+    fg.begin_step()
+    model(data[a:b]).square().sum().backward()
+    assert fg._early_done                               # the hook fired during backward and reduced flat[split:]
+    fg.all_reduce()                                     # ... so this reduces only flat[:split]
+    assert not fg._early_done
+    ref.zero_grad()
+    ref(data).square().sum().backward()
+    for (n, p), q in zip(model.named_parameters(), ref.parameters()):
+        assert torch.allclose(p.grad, q.grad / 2, atol=1e-5), (step, n)
+assert calls == [False, False]
+# a parameter of the octic side registered after the head: the overlap must refuse
+m2 = Toy(late_param_last=True)
+fg2 = FlatGrads(m2.parameters(), fuse_accumulation=False)
+assert not install_early_allreduce(m2, fg2) and fg2.split == fg2.flat.numel() and m2._bridge_grad_hook is None
+fg2.begin_step()
+m2(data[a:b]).square().sum().backward()
+fg2.all_reduce()
+ref2 = Toy(late_param_last=True); ref2.load_state_dict(m2.state_dict())
+ref2(data).square().sum().backward()
+for (n, p), q in zip(m2.named_parameters(), ref2.parameters()):
+    assert torch.allclose(p.grad, q.grad / 2, atol=1e-5), n
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_early_allreduce_overlap_world2_gloo(tmp_path):
+    """parallel.install_early_allreduce: the dense half's gradients are exchanged from an autograd hook at the bridge,
+    the rest after backward; the result equals the single all-reduce."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "worker_early.py"
+    script.write_text(_GLOO_EARLY_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT), str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
