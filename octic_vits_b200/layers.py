@@ -614,6 +614,55 @@ class PatchEmbedD8(nn.Module):
             torch.nn.init.xavier_uniform_(w.view([w.shape[0], -1]))
 
 
+class IsotypicToPatchD8(nn.Module):
+    """reference d8_layers.py:499-588: octic features -> image patches (the equivariant counterpart of the MAE
+    decoder head; exercised by experiments/test_equivariance.py:257-274).  The LinearD8 runs on the grouped tcgen05
+    GEMM; the per-token quadrant unfolding is index shuffling on [B, L, p, p, c] and stays in torch."""
+
+    def __init__(self, dim, patch_side, out_channels=3, bias=True, reshape_to_image=False):
+        super().__init__()
+        if patch_side % 2 != 0:
+            raise NotImplementedError("Odd patch side not implemented.")
+        self.dim = dim
+        self.patch_side = patch_side
+        self.out_channels = out_channels
+        self.reshape_to_image = reshape_to_image
+        self.lin8 = LinearD8(dim, 2 * (patch_side ** 2 * out_channels), bias=bias)
+
+    @staticmethod
+    def _quadrants(w: Tensor, s_rot: float, s_flip: float) -> Tensor:
+        left = torch.cat((w, s_rot * w.rot90(1, (2, 3))), dim=2)
+        right = torch.cat((s_rot * w.rot90(3, (2, 3)), w.rot90(2, (2, 3))), dim=2)
+        full = torch.cat((left, right), dim=3)
+        return full + s_flip * full.flip(3)
+
+    def forward_packed(self, x: Tensor) -> Tensor:
+        B, L, _ = x.shape
+        y = self.lin8.forward_packed(x).float()
+        h, c = self.patch_side // 2, self.out_channels
+        C = y.shape[-1] // 8
+        # packed columns: A1 | A2 | B1 | B2 | E row 0 = (x4, x6) | E row 1 = (x5, x7); x6 / x7 are not used (:566-583)
+        a1, a2, b1, b2, x4, x5 = (0.25 * y[..., i * C:(i + 1) * C].reshape(B, L, h, h, c) for i in (0, 1, 2, 3, 4, 6))
+        out = (self._quadrants(a1, 1.0, 1.0) + self._quadrants(a2, 1.0, -1.0) + self._quadrants(b1, -1.0, 1.0)
+               + self._quadrants(b2, -1.0, -1.0))
+        for comp, turns in ((x4, 0), (x5, 1)):
+            e = SQRT2 * comp
+            col = torch.cat((e, e.flip(2)), dim=2)
+            full = torch.cat((col, -col.flip(3)), dim=3)
+            out = out + (full.rot90(turns, (2, 3)) if turns else full)
+        p = self.patch_side
+        if self.reshape_to_image:
+            H = W = int(math.sqrt(L))
+            out = out.reshape(B, H, W, p, p, c)
+            return out.permute(0, 5, 1, 3, 2, 4).reshape(B, c, H * p, W * p)
+        return out.reshape(B, L, p ** 2 * c)
+
+    def forward(self, xs):
+        x = OF.pack_five(xs)
+        OF.require_cuda(x)
+        return self.forward_packed(x)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # dense half (deit/vit.py:14-134; timm Block)
 # ----------------------------------------------------------------------------------------------------------------

@@ -299,6 +299,28 @@ def patch_embed_d8(img: Tensor, w: Dict[str, Tensor], prefix: str, patch: int) -
     return eight_to_five(flat)
 
 
+def isotypic_to_patch(xs: Five, w: Dict[str, Tensor], prefix: str, patch_side: int, out_channels: int = 3,
+                      reshape_to_image: bool = False) -> Tensor:
+    """IsotypicToPatchD8.forward (d8_layers.py:520-588): LinearD8(dim, 2 p^2 c) -> per irrep a quadrant
+    [B, L, p/2, p/2, c] (scaled 1/4) unfolded to the full patch with the irrep's symmetry; the E irrep contributes its
+    first two components (sqrt(2) x4 as is, sqrt(2) x5 rotated by 90 degrees), x6/x7 are not used."""
+    ys = five_to_eight(linear_d8(xs, w, f"{prefix}lin8."))
+    B, L, _ = ys[0].shape
+    h = patch_side // 2
+    q = [0.25 * y.reshape(B, L, h, h, out_channels) for y in ys]
+    out = sum(_unfold_quadrant(q[i], *_SIGNS[name], (2, 3)) for i, name in enumerate(IRREPS))
+    for i, turns in ((4, 0), (5, 1)):
+        x = math.sqrt(2.0) * q[i]
+        col = torch.cat((x, x.flip(2)), dim=2)
+        full = torch.cat((col, -col.flip(3)), dim=3)
+        out = out + (full.rot90(turns, (2, 3)) if turns else full)
+    if reshape_to_image:
+        H = W = int(math.isqrt(L))
+        out = out.reshape(B, H, W, patch_side, patch_side, out_channels)
+        return out.permute(0, 5, 1, 3, 2, 4).reshape(B, out_channels, H * patch_side, W * patch_side)
+    return out.reshape(B, L, patch_side ** 2 * out_channels)
+
+
 def unfold_pos_embed(ps: Sequence[Tensor]) -> Five:
     """isotypic_dim_interpolation(dim=0) + convert_8tuple_to_5tuple (d8_utils.py:388-451, model.py:174):
     six [h/2, w/2, C] parameters -> 5-tuple of [h, w, C] x4 and [h, w, 2, 2C]."""

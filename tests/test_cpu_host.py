@@ -47,7 +47,8 @@ def test_no_cpu_fallback(lib):
     assert lib.octic_device_ok() == 0
     xs = tuple(torch.randn(1, 3, 8) for _ in range(4)) + (torch.randn(1, 3, 2, 16),)
     for mod in (L.LinearD8(64, 64), L.LayerNormD8(64), L.TritonGeluD8(), L.AttentionD8(64, 2), L.MlpD8(64),
-                L.Layer_scale_init_BlockD8(64, 2), L.BlockD8(64, 2), L.PowerSpectrumInvariant(64)):
+                L.Layer_scale_init_BlockD8(64, 2), L.BlockD8(64, 2), L.PowerSpectrumInvariant(64),
+                L.IsotypicToPatchD8(64, 4, out_channels=4)):
         with pytest.raises(OcticError):
             mod(xs)
 

@@ -85,6 +85,22 @@ def test_power_spectrum_golden(golden):
         check(x.grad, g, rel=5e-3, mx=1e-2, what="power spectrum grad")
 
 
+@pytest.mark.parametrize("tag", ["image", "tokens"])
+def test_isotypic_to_patch_golden(golden, tag):
+    """IsotypicToPatchD8 (d8_layers.py:499-588) vs the reference's own output and autograd gradients."""
+    fx = golden("isotypic_to_patch")[tag]
+    mod = L.IsotypicToPatchD8(dim=64, **fx["kw"]).to(DEV)
+    mod.load_state_dict(fx["sd"], strict=True)
+    xs = tuple(x.clone().to(DEV).requires_grad_(True) for x in fx["in"])
+    y = mod(xs)
+    check(y.detach(), fx["out"], what="patches")
+    (y * fx["gout"].to(DEV)).sum().backward()
+    for i, (a, b) in enumerate(zip(xs, fx["gin"])):
+        check(a.grad, b, rel=3e-2, mx=8e-2, what=f"gin[{i}]")
+    for k, g in fx["gparams"].items():
+        check(dict(mod.named_parameters())[k].grad, g, rel=3e-2, mx=8e-2, what=f"grad {k}")
+
+
 def test_dense_block_golden(golden):
     fx = golden("dense_block_deit")
     blk = L.Layer_scale_init_Block(64, 2, qkv_bias=True).to(DEV)

@@ -181,3 +181,32 @@ def test_dinov2_backbone(golden, tag):
     assert len(fx["gparams"]) > 40
     for k, g in fx["gparams"].items():
         close(w[k].grad, g, rtol=2e-4, atol=2e-3)
+
+
+@pytest.mark.parametrize("tag", ["image", "tokens"])
+def test_isotypic_to_patch(golden, tag):
+    """IsotypicToPatchD8 (d8_layers.py:499-588), forward and gradients (tools/make_golden_extra.py)."""
+    fx = golden("isotypic_to_patch")[tag]
+    w = {k: v.clone().requires_grad_(True) for k, v in fx["sd"].items()}
+    xs = tuple(x.clone().requires_grad_(True) for x in fx["in"])
+    kw = fx["kw"]
+    y = O.isotypic_to_patch(xs, w, "", kw["patch_side"], kw["out_channels"], kw["reshape_to_image"])
+    close(y, fx["out"])
+    (y * fx["gout"]).sum().backward()
+    for a, b in zip(xs, fx["gin"]):
+        close(a.grad, b, rtol=1e-4, atol=1e-4)
+    for k, g in fx["gparams"].items():
+        close(w[k].grad, g, rtol=1e-4, atol=1e-4)
+
+
+def test_isotypic_to_patch_is_equivariant(golden):
+    """experiments/test_equivariance.py:257-274 on the oracle: acting on the octic tokens and then decoding to an image
+    equals decoding and then acting on the image."""
+    fx = golden("isotypic_to_patch")["image"]
+    w = {k: v.double() for k, v in fx["sd"].items()}
+    xs = tuple(x.double() for x in fx["in"])
+    f = lambda t: O.isotypic_to_patch(t, w, "", fx["kw"]["patch_side"], fx["kw"]["out_channels"], True)
+    base = f(xs)
+    for g in O.GROUP:
+        moved = f(O.token_action(g, xs, has_cls=False))
+        torch.testing.assert_close(moved, O.image_action(g, base), rtol=1e-10, atol=1e-10)
