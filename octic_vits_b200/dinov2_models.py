@@ -37,15 +37,26 @@ _PACK_ORDER = (0, 1, 2, 3, 4, 6, 5, 7)
 
 
 def named_apply(fn: Callable, module: nn.Module, name="", depth_first=True, include_root=False) -> nn.Module:
-    """reference dinov2_models.py:18-26"""
-    if not depth_first and include_root:
-        fn(module=module, name=name)
-    for child_name, child_module in module.named_children():
-        child_name = ".".join((name, child_name)) if name else child_name
-        named_apply(fn=fn, module=child_module, name=child_name, depth_first=depth_first, include_root=True)
-    if depth_first and include_root:
-        fn(module=module, name=name)
+    """Same contract as the reference helper (dinov2_models.py:18-26): call fn(module=, name=) on every descendant
+    (and on the root when include_root), children before parents when depth_first."""
+    if depth_first:                       # post-order: a module after all of its descendants
+        visits = _post_order(module, name, include_root)
+    else:                                 # pre-order, which is what named_modules() yields
+        visits = [(n if not name else (f"{name}.{n}" if n else name), m) for n, m in module.named_modules()]
+        if not include_root:
+            visits = visits[1:]
+    for n, m in visits:
+        fn(module=m, name=n)
     return module
+
+
+def _post_order(module: nn.Module, name: str, include_self: bool):
+    out = []
+    for child_name, child in module.named_children():
+        out += _post_order(child, f"{name}.{child_name}" if name else child_name, True)
+    if include_self:
+        out.append((name, module))
+    return out
 
 
 def init_weights_vit_timm(module: nn.Module, name: str = ""):
