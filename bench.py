@@ -285,6 +285,7 @@ def run_ours(args):
                        "optimizer_step": False if opt is None else f"fused {args.optimizer} (3 launches/step, weight "
                                                                     "re-pack inside the graph)",
                        "cuda_graph": bool(gstep.graphed), "allreduce_overlap": bool(overlap),
+                       "weight_repack_in_step": True,   # fp32 -> bf16 weight packs run every step (as autocast re-casts)
                        "l2": "activations per step (>50 GB) exceed the 126 MB L2; no explicit flush"},
             "model_tflops": ips * flops_img / 1e12,
             "tc_util_vs_sustained_peak": ips * flops_img / 1e12 / (world * peaks["tf_sustained"]),

@@ -307,6 +307,30 @@ def test_graphed_train_step_matches_eager():
     assert abs(float(step.run()) - loss_g2) <= 1e-5 * max(1.0, abs(loss_g2))
 
 
+def test_graphed_step_sees_parameter_updates_of_any_optimizer():
+    """The weight packs live inside the captured graph (repack_weights, default): after a plain torch optimizer changed
+    the parameters, a replay computes with the NEW values -- loss and gradients equal the eager step at those values."""
+    from octic_vits_b200.parallel import FlatGrads, GraphedTrainStep
+    torch.manual_seed(4)
+    model = OcticVisionTransformer(img_size=64, patch_size=16, embed_dim=128, depth=4, num_heads=2, num_classes=10,
+                                   qkv_bias=True, init_scale=0.5).to(DEV).train()
+    fg = FlatGrads(model.parameters())
+    img = torch.randn(4, 3, 64, 64, device=DEV)
+    tgt = torch.randint(0, 10, (4,), device=DEV)
+    step = GraphedTrainStep(model, fg, img.shape, warmup=2)
+    eager = GraphedTrainStep(model, fg, img.shape, use_graph=False)
+    assert step.graphed, getattr(step, "capture_error", "")
+    sgd = torch.optim.SGD([p for p in model.parameters() if p.requires_grad], lr=0.5)
+    loss0 = float(step(img, tgt))
+    sgd.step()                                        # reads the flat .grad views, bumps the parameters' versions
+    loss_e = float(eager(img, tgt))
+    grads_e = fg.flat.clone()
+    loss_g = float(step(img, tgt))
+    assert abs(loss_e - loss0) > 1e-3                 # the update really moved the loss
+    assert abs(loss_g - loss_e) <= 1e-4 * max(1.0, abs(loss_e))
+    assert rel_err(fg.flat, grads_e) < 1e-3
+
+
 def test_headline_model_equivariance_report(capsys):
     """BASELINE.json metric 'D8 equiv error' on the HEADLINE model: hybrid octic ViT-H/14 (DeiT-III init, layer scale
     1e-4 as shipped, and an O(1)-weights variant), bf16 GPU path, 224 px.  Equivariance of the 16-block octic trunk under
