@@ -37,6 +37,19 @@ def timm_no_decay(model: torch.nn.Module) -> set:
             if p.requires_grad and (p.ndim <= 1 or n.endswith(".bias") or n in skip)}
 
 
+def build_chunk_table(numels, offsets, ptrs, ema_ptrs, hparams, chunk: int = CHUNK):
+    """Host-side tables of the C ABI (include/octic_b200.h): one `octic_optim_seg` per parameter tensor and its
+    `octic_optim_chunk`s (<= `chunk` elements each, contiguous per tensor).  `ptrs` / `ema_ptrs` are device addresses
+    (0 = no EMA copy), `offsets` the tensors' first elements in the flat gradient buffer, `hparams` (weight_decay,
+    lr_scale) per tensor.  Returns (chunks, segs) as lists of tuples in the structs' field order."""
+    chunks, segs = [], []
+    for seg, (n, off, ptr, eptr, (wd, scale)) in enumerate(zip(numels, offsets, ptrs, ema_ptrs, hparams)):
+        segs.append((float(wd), float(scale), len(chunks), (n + chunk - 1) // chunk))
+        for s in range(0, n, chunk):
+            chunks.append((ptr + 4 * s, eptr + 4 * s if eptr else 0, off + s, min(chunk, n - s), seg))
+    return chunks, segs
+
+
 class FusedOptimizer:
     """kind = "lamb": apex FusedLAMB defaults (bias_correction, grad_averaging, adam_w_mode, max_grad_norm=1.0,
     use_nvlamb=False: the trust ratio only applies to tensors with weight decay);  kind = "adamw": torch.optim.AdamW.
@@ -60,13 +73,11 @@ class FusedOptimizer:
         no_decay = timm_no_decay(model) if no_decay is None else set(no_decay)
         lr_scales = lr_scales or {}
         dev = flat_grads.flat.device
-        if dev.type != "cuda":
-            raise OcticError("FusedOptimizer needs CUDA parameters: there is no CPU path")
         ema_params, self.ema_momentum = {}, 0.0
         if ema is not None:
             ema_params, self.ema_momentum = dict(ema[0].named_parameters()), float(ema[1])
-        chunks, segs = [], []
-        for seg, (p, off) in enumerate(zip(flat_grads.params, flat_grads.offsets)):
+        ema_ptrs, hparams = [], []
+        for p in flat_grads.params:
             name = names.get(id(p))
             if name is None:
                 raise ValueError("flat_grads holds a parameter that is not in model.named_parameters()")
@@ -75,18 +86,19 @@ class FusedOptimizer:
             e = ema_params.get(name)
             if e is not None and (e.shape != p.shape or e.dtype != torch.float32 or not e.is_contiguous() or e.device != p.device):
                 raise OcticError(f"{name}: EMA copy must match the parameter (shape, fp32, contiguous, same device)")
-            segs.append((0.0 if name in no_decay else float(weight_decay), float(lr_scales.get(name, 1.0)), len(chunks),
-                         (p.numel() + CHUNK - 1) // CHUNK))
-            for s in range(0, p.numel(), CHUNK):
-                n = min(CHUNK, p.numel() - s)
-                chunks.append((p.data_ptr() + 4 * s, e.data_ptr() + 4 * s if e is not None else 0, off + s, n, seg))
+            ema_ptrs.append(e.data_ptr() if e is not None else 0)
+            hparams.append((0.0 if name in no_decay else float(weight_decay), float(lr_scales.get(name, 1.0))))
+        chunks, segs = build_chunk_table([p.numel() for p in flat_grads.params], flat_grads.offsets,
+                                         [p.data_ptr() for p in flat_grads.params], ema_ptrs, hparams)
         self.nchunks, self.nseg = len(chunks), len(segs)
+        self.seg_hparams = [(wd, sc) for wd, sc, _, _ in segs]
+        if dev.type != "cuda":
+            raise OcticError("FusedOptimizer needs CUDA parameters: there is no CPU path")
         self._ptrs = [p.data_ptr() for p in flat_grads.params]
         ch = (OptimChunk * len(chunks))(*[OptimChunk(*c) for c in chunks])
         sg = (OptimSeg * len(segs))(*[OptimSeg(*s) for s in segs])
         self.chunks = torch.frombuffer(bytearray(bytes(ch)), dtype=torch.uint8).to(dev)
         self.segs = torch.frombuffer(bytearray(bytes(sg)), dtype=torch.uint8).to(dev)
-        self.seg_hparams = [(wd, sc) for wd, sc, _, _ in segs]
         self.exp_avg = torch.zeros_like(flat_grads.flat)
         self.exp_avg_sq = torch.zeros_like(flat_grads.flat)
         # reduction workspace: [gnorm^2 | pad | per-CTA gnorm partials | (|p|^2, |u|^2) per tensor | ... per chunk]

@@ -347,3 +347,70 @@ def test_early_allreduce_overlap_world2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in _lib.py have the size and the field offsets the C compiler gives the structs of
+    include/octic_b200.h (a drift would corrupt every descriptor passed through the C ABI)."""
+    import ctypes as C
+    from octic_vits_b200 import _lib
+    pairs = {"octic_gemm_group": _lib.GemmGroup, "octic_gemm_desc": _lib.GemmDesc, "octic_wgrad_group": _lib.WgradGroup,
+             "octic_wgrad_desc": _lib.WgradDesc, "octic_lsfin_seg": _lib.LsFinSeg, "octic_optim_chunk": _lib.OptimChunk,
+             "octic_optim_seg": _lib.OptimSeg}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT / "include" / "octic_b200.h"}"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    got = {}
+    for line in subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout.splitlines():
+        cname, field, val = line.split()
+        got[(cname, field)] = int(val)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_optimizer_chunk_table_covers_every_parameter_once():
+    from octic_vits_b200.optim import CHUNK, build_chunk_table, timm_no_decay
+    from octic_vits_b200.deit_models import create_model
+    from octic_vits_b200.parallel import FlatGrads
+    model = create_model("hybrid_deit_small_patch16", num_classes=10)
+    fg = FlatGrads(model.parameters(), fuse_accumulation=False)
+    assert all(o % 4 == 0 for o in fg.offsets) and fg.flat.numel() >= sum(p.numel() for p in fg.params)
+    numels = [p.numel() for p in fg.params]
+    ptrs = [p.data_ptr() for p in fg.params]
+    chunks, segs = build_chunk_table(numels, fg.offsets, ptrs, [0] * len(ptrs), [(0.05, 1.0)] * len(ptrs))
+    assert len(segs) == len(fg.params)
+    covered = torch.zeros(fg.flat.numel(), dtype=torch.int32)
+    for i, (p, e, off, n, seg) in enumerate(chunks):
+        assert 0 < n <= CHUNK and e == 0
+        first, count = segs[seg][2], segs[seg][3]
+        assert first <= i < first + count
+        assert p == ptrs[seg] + 4 * (off - fg.offsets[seg])           # same element in the parameter and the flat buffer
+        covered[off:off + n] += 1
+    for o, n in zip(fg.offsets, numels):
+        assert bool((covered[o:o + n] == 1).all())
+    assert int(covered.sum()) == sum(numels)                           # padding elements are never touched
+    assert sum(s[3] for s in segs) == len(chunks)
+    nd = timm_no_decay(model)
+    assert "cls_token.0" in nd and "pos_embed.3" in nd and "blocks.0.norm1.scaling.alpha_E" in nd
+    assert "blocks.0.attn.qkv.lin_A1.bias" in nd and "blocks.0.attn.qkv.lin_E.weight" not in nd
+    assert "blocks.7.gamma_1" in nd and "head.weight" not in nd and "cls_token.1" not in nd   # frozen: not a candidate
+    # the product class refuses CPU parameters (after validating them and building the tables): no CPU path
+    from octic_vits_b200.optim import FusedOptimizer
+    from octic_vits_b200._lib import OcticError
+    ema = create_model("hybrid_deit_small_patch16", num_classes=10)
+    for kind in ("lamb", "adamw"):
+        with pytest.raises(OcticError, match="no CPU path"):
+            FusedOptimizer(model, fg, kind=kind, lr=1e-3, weight_decay=0.05, ema=(ema, 0.99), lr_scales={"head.weight": 0.5})
+    with pytest.raises(ValueError):
+        FusedOptimizer(model, fg, kind="sgd")
+    with pytest.raises(ValueError):
+        FusedOptimizer(ema, fg)                                        # fg's parameters are not this model's
