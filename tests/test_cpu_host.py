@@ -399,6 +399,13 @@ def test_optimizer_chunk_table_covers_every_parameter_once():
         assert bool((covered[o:o + n] == 1).all())
     assert int(covered.sum()) == sum(numels)                           # padding elements are never touched
     assert sum(s[3] for s in segs) == len(chunks)
+    from octic_vits_b200._lib import OptimChunk, OptimSeg
+    ch = (OptimChunk * len(chunks))(*[OptimChunk(*c) for c in chunks])
+    sg = (OptimSeg * len(segs))(*[OptimSeg(*t) for t in segs])
+    last = chunks[-1]
+    assert (ch[len(chunks) - 1].p, ch[len(chunks) - 1].off, ch[len(chunks) - 1].len, ch[len(chunks) - 1].seg) == (last[0], last[2], last[3], last[4])
+    assert ch[0].ema is None and sg[3].first_chunk == segs[3][2] and sg[3].num_chunks == segs[3][3]
+    assert abs(sg[0].weight_decay - 0.05) < 1e-7 and sg[0].lr_scale == 1.0
     nd = timm_no_decay(model)
     assert "cls_token.0" in nd and "pos_embed.3" in nd and "blocks.0.norm1.scaling.alpha_E" in nd
     assert "blocks.0.attn.qkv.lin_A1.bias" in nd and "blocks.0.attn.qkv.lin_E.weight" not in nd
