@@ -12,7 +12,14 @@ def register_model(fn):
     return fn
 
 
+def _register_all() -> None:
+    """the DINOv2 factories (dinov2_models.py) register themselves on import, as the reference's modules do with timm"""
+    from . import dinov2_models  # noqa: F401
+
+
 def create_model(model_name: str, **kwargs):
+    if model_name not in _REGISTRY:
+        _register_all()
     if model_name not in _REGISTRY:
         raise RuntimeError(f"Unknown model ({model_name})")
     kwargs = {k: v for k, v in kwargs.items() if v is not None}
@@ -20,6 +27,7 @@ def create_model(model_name: str, **kwargs):
 
 
 def list_models():
+    _register_all()
     return sorted(_REGISTRY)
 
 
