@@ -316,8 +316,7 @@ def run_ours(args):
         # a CUDA graph that captured NCCL kernels keeps the communicator alive: release it before tearing NCCL down
         # (with --overlap the process otherwise hangs in destroy_process_group, observed at 2 GPUs)
         if overlap:
-            gstep.graph = None
-            torch.cuda.synchronize()
+            gstep.close()
             dist.barrier()
         dist.destroy_process_group()
 

@@ -67,6 +67,8 @@ dist.broadcast(other, src=0)
 same = torch.equal(other, flat_p)
 print(f"[rank {rank}] LAMB x6: losses {losses[0]:.4f} -> {losses[-1]:.4f}, replicas bit-identical: {same}", flush=True)
 assert same
+step.close()          # graphs that captured NCCL kernels must go before the communicator does
+ostep.close()
 dist.barrier()
 dist.destroy_process_group()
 if rank == 0:
