@@ -2,10 +2,15 @@
 """bench.py -- headline benchmark of the octic ViT hot path (contract: see the task brief / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+                    [--optimizer none|lamb|adamw] [--overlap] [--drop-path P] [--no-graph] [--no-cpu-baseline]
 
 Metric (BASELINE.json): hybrid octic ViT-H/14 (DeiT-III: embed 1280, depth 32, heads 16, patch 14, 224 px) images/s,
 forward + backward (+ NCCL gradient all-reduce when N > 1), bf16 compute / fp32 residual, synthetic images, random-init
 weights.  One process per GPU (torchrun for N > 1); the batch is sharded over ranks (weak scaling: B images per GPU).
+
+The step is the public-API parallel.GraphedTrainStep: bf16 weight re-pack + forward + loss + backward replayed from one
+CUDA graph.  `--optimizer` adds the fused parameter update (optim.FusedOptimizer) to every step; `--overlap` (N > 1)
+moves the all-reduce of the dense half's gradients inside the graph, concurrent with the octic half's backward.
 
 `--impl reference` times the reference algorithm on the host CPU cores (the oracle port of the reference PyTorch
 path, oracle/octic_oracle.py -- the reference itself is pure PyTorch and is not present on the GPU box).
