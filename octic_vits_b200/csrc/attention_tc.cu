@@ -274,8 +274,10 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   uint8_t* Ks = smem;
   uint8_t* Vs = Ks + kv_bytes;
   uint8_t* Qs = Vs + kv_bytes;
-  float* xch = reinterpret_cast<float*>(Qs + q_bytes);           // [2][128] row max / row sum exchange between warp pairs
-  int* ocb = reinterpret_cast<int*>(xch + 256);
+  float* xch = reinterpret_cast<float*>(Qs + q_bytes);           // [2][128] row max exchange between warp pairs
+  float* xcl = xch + 256;                                        // [2][128] row sum exchange (own array: the sum of a
+                                                                 // fast warp must not overwrite a max its partner has not read)
+  int* ocb = reinterpret_cast<int*>(xcl + 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ocb + NU + (NU & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
   // tail warp: q row [HD] + reduction scratch [32][17] (16-byte aligned for vector loads)
@@ -564,9 +566,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
       }
       if (warp_valid) {
         // total row sum = both warps of the quarter (written before, read after the pair barrier)
-        xch[bsel * 128 + rloc] = l;
+        xcl[bsel * 128 + rloc] = l;
         named_bar_sync(1 + q4, 64);
-        l += xch[(bsel ^ 1) * 128 + rloc];
+        l += xcl[(bsel ^ 1) * 128 + rloc];
       }
       mbar_wait(&bars[BAR_OFULL], pho);
       pho ^= 1u;
@@ -1005,7 +1007,7 @@ static int pick_box_rows(int Rk) { return Rk > 256 ? Rk / 2 : Rk; }
 
 static size_t fwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 256 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 16 + (hd + 32 * 17) * 4 + 1024;
+  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 512 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 16 + (hd + 32 * 17) * 4 + 1024;
 }
 static size_t bwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
