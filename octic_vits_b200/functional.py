@@ -41,6 +41,11 @@ def _cached(tensors, build):
         return hit[1]
     with torch.no_grad():
         pk = build()
+    if hit is None:
+        # drop the entry (bf16 packs + transposes, ~1.5x the fp32 bytes) as soon as any of its parameters dies, instead of
+        # keeping it on the GPU until the id is reused
+        for t in tensors:
+            weakref.finalize(t, _pack_cache.pop, ident, None)
     _pack_cache[ident] = (key, pk, tuple(weakref.ref(t) for t in tensors))
     return pk
 
@@ -74,14 +79,23 @@ def _c(t: torch.Tensor) -> torch.Tensor:
 # ----------------------------------------------------------------------------------------------------------------
 FOLD_GAMMA = True
 # Weight gradients go straight into an existing fp32 `.grad` (the wgrad kernels accumulate with red.add anyway) and the
-# Function returns None for that parameter: no zero fill, no autograd accumulation kernel.  Opt-in (parallel.FlatGrads
-# switches it on): tensor hooks on those parameters do not see the gradient.
-ACCUMULATE_INTO_GRAD = False
+# Function returns None for that parameter: no zero fill, no autograd accumulation kernel.  Opt-in PER PARAMETER:
+# parallel.FlatGrads tags the parameters whose .grad it owns (`_octic_accumulate`); models it does not manage keep plain
+# autograd semantics (tensor hooks see the gradient, torch.autograd.grad has no side effect).  The module flag is a
+# process-wide kill switch for tests.
+ACCUMULATE_INTO_GRAD = True
+ACCUMULATE_ATTR = "_octic_accumulate"
 _aux_slot = None     # (data_ptr, shape, bf16 copy, column sums) of the most recent layer-norm backward output
 
 
+def reset_step_state() -> None:
+    """Forget every hand-off between autograd nodes of an unfinished step (after a failed CUDA-graph capture)."""
+    global _aux_slot
+    _aux_slot = None
+
+
 def _grad_target(p):
-    if not ACCUMULATE_INTO_GRAD or not isinstance(p, torch.nn.Parameter):
+    if not ACCUMULATE_INTO_GRAD or not isinstance(p, torch.nn.Parameter) or not getattr(p, ACCUMULATE_ATTR, False):
         return None
     g = p.grad
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:

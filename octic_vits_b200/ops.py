@@ -87,6 +87,11 @@ def begin_step() -> None:
     ZERO_POOL.begin_step()
 
 
+def reset_zero_pool() -> None:
+    """Drop the step's pool buffer (after a failed CUDA-graph capture its zero fill was recorded, not executed)."""
+    ZERO_POOL.end()
+
+
 def zeros_f32(n: int, device) -> torch.Tensor:
     return ZERO_POOL.take(int(n), device)
 

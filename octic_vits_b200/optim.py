@@ -54,7 +54,9 @@ class FusedOptimizer:
     """kind = "lamb": apex FusedLAMB defaults (bias_correction, grad_averaging, adam_w_mode, max_grad_norm=1.0,
     use_nvlamb=False: the trust ratio only applies to tensors with weight decay);  kind = "adamw": torch.optim.AdamW.
     `lr_scales` maps parameter names to a learning-rate multiplier (layer-wise decay / patch-embed multiplier of the
-    DINOv2 recipe).  `ema` = (ema_model, momentum): ema_model's parameters with the same names are updated as
+    DINOv2 recipe); `set_weight_decay` / `set_lr_scales` change them between steps (cosine weight-decay schedule,
+    last-layer freezing).  Default eps: 1e-6 for LAMB (apex FusedLAMB's default; the DeiT recipe passes --opt-eps, whose
+    default is 1e-8: give eps= explicitly to match a run), 1e-8 for AdamW.  `ema` = (ema_model, momentum): ema_model's parameters with the same names are updated as
     ema = momentum*ema + (1-momentum)*param inside the kernel that writes the parameter."""
 
     def __init__(self, model: torch.nn.Module, flat_grads: FlatGrads, kind: str = "lamb", lr: float = 1e-3,
@@ -92,6 +94,9 @@ class FusedOptimizer:
                                          [p.data_ptr() for p in flat_grads.params], ema_ptrs, hparams)
         self.nchunks, self.nseg = len(chunks), len(segs)
         self.seg_hparams = [(wd, sc) for wd, sc, _, _ in segs]
+        self._seg_layout = [(c0, nc) for _, _, c0, nc in segs]
+        self._names = [names[id(p)] for p in flat_grads.params]
+        self._decayed = [name not in no_decay for name in self._names]
         if dev.type != "cuda":
             raise OcticError("FusedOptimizer needs CUDA parameters: there is no CPU path")
         self._ptrs = [p.data_ptr() for p in flat_grads.params]
@@ -109,13 +114,34 @@ class FusedOptimizer:
     def set_lr(self, lr: float) -> None:
         self.lr = float(lr)
 
+    def _write_segs(self) -> None:
+        """Re-upload the per-tensor table (weight decay, lr multiplier) -- a few KB, stream ordered."""
+        segs = [(wd, sc, c0, nc) for (wd, sc), (c0, nc) in zip(self.seg_hparams, self._seg_layout)]
+        sg = (OptimSeg * len(segs))(*[OptimSeg(*s_) for s_ in segs])
+        self.segs.copy_(torch.frombuffer(bytearray(bytes(sg)), dtype=torch.uint8), non_blocking=False)
+
+    def set_weight_decay(self, weight_decay: float) -> None:
+        """New weight decay for every decayed tensor (the cosine weight-decay schedule of the DINOv2 recipe,
+        dinov2/train/train.py:87-93); tensors in `no_decay` stay at 0."""
+        self.seg_hparams = [(float(weight_decay) if d else 0.0, sc) for (_, sc), d in zip(self.seg_hparams, self._decayed)]
+        self._write_segs()
+
+    def set_lr_scales(self, lr_scales: Dict[str, float]) -> None:
+        """New per-parameter learning-rate multipliers by name (layer-wise decay, last-layer freezing = 0.0); names that
+        are not given keep their multiplier."""
+        unknown = set(lr_scales) - set(self._names)
+        if unknown:
+            raise ValueError(f"unknown parameter names: {sorted(unknown)[:4]}")
+        self.seg_hparams = [(wd, float(lr_scales.get(n, sc))) for (wd, sc), n in zip(self.seg_hparams, self._names)]
+        self._write_segs()
+
     def set_ema_momentum(self, m: float) -> None:
         self.ema_momentum = float(m)
 
     def step(self) -> None:
         """Consumes the (already all-reduced) flat gradients.  5 launches for LAMB (grad-norm partials + final sum,
         stage 1, per-tensor norm sums, stage 2), 1 for AdamW (3 with clipping).  No atomics: bit-reproducible."""
-        if any(p.data_ptr() != q for p, q in zip(self.fg.params[:4], self._ptrs[:4])):
+        if any(p.data_ptr() != q for p, q in zip(self.fg.params, self._ptrs)):
             raise OcticError("parameters were re-allocated after the optimizer was built (call .to()/.cuda() first)")
         self.step_count += 1
         b1, b2 = self.betas
@@ -144,11 +170,27 @@ class FusedOptimizer:
 
     def state_dict(self) -> dict:
         return {"kind": self.kind, "step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
-                "lr": self.lr, "betas": self.betas, "eps": self.eps}
+                "lr": self.lr, "betas": self.betas, "eps": self.eps, "max_grad_norm": self.max_grad_norm,
+                "ema_momentum": self.ema_momentum, "grad_averaging": self.grad_averaging, "use_nvlamb": self.use_nvlamb,
+                "seg_hparams": list(self.seg_hparams), "names": list(self._names)}
 
     def load_state_dict(self, sd: dict) -> None:
+        """Restores moments, step count AND every hyper-parameter that state_dict() saved (older dicts without the
+        hyper-parameter keys keep the current values)."""
         if sd["kind"] != self.kind or sd["exp_avg"].numel() != self.exp_avg.numel():
             raise ValueError("optimizer state does not match this optimizer")
+        if "names" in sd and list(sd["names"]) != self._names:
+            raise ValueError("optimizer state was saved for a different parameter list")
         self.step_count = int(sd["step"])
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.lr = float(sd.get("lr", self.lr))
+        self.betas = tuple(float(b) for b in sd.get("betas", self.betas))
+        self.eps = float(sd.get("eps", self.eps))
+        self.max_grad_norm = float(sd.get("max_grad_norm", self.max_grad_norm))
+        self.ema_momentum = float(sd.get("ema_momentum", self.ema_momentum))
+        self.grad_averaging = bool(sd.get("grad_averaging", self.grad_averaging))
+        self.use_nvlamb = bool(sd.get("use_nvlamb", self.use_nvlamb))
+        if "seg_hparams" in sd:
+            self.seg_hparams = [(float(wd), float(sc)) for wd, sc in sd["seg_hparams"]]
+            self._write_segs()

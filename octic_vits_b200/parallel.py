@@ -41,13 +41,24 @@ class FlatGrads:
         self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
+        self.fused = bool(fuse_accumulation)
         if fuse_accumulation:
-            # the wgrad kernels add straight into these views (no zero fill + autograd accumulation kernel per weight)
+            # the wgrad kernels add straight into these views (no zero fill + autograd accumulation kernel per weight);
+            # the opt-in is a tag on the parameters this buffer owns, not a process-wide switch
             from . import functional as OF
-            OF.ACCUMULATE_INTO_GRAD = True
+            for p in self.params:
+                setattr(p, OF.ACCUMULATE_ATTR, True)
         self.split = self.flat.numel()      # flat[split:] = gradients that are final early in backward (none by default)
         self._early_done = False
         self._comm_stream = None
+
+    def close(self) -> None:
+        """Give the parameters back to plain autograd accumulation (their .grad views stay valid)."""
+        from . import functional as OF
+        for p in self.params:
+            if hasattr(p, OF.ACCUMULATE_ATTR):
+                delattr(p, OF.ACCUMULATE_ATTR)
+        self.fused = False
 
     def zero(self) -> None:
         self.flat.zero_()
@@ -100,9 +111,11 @@ class FlatGrads:
             self._reduce(tail, average)
         self._early_done = True
 
-    def join_early(self) -> None:
-        """Make the current stream wait for the early all-reduce (must run before a CUDA-graph capture ends)."""
-        if self._early_done and self._comm_stream is not None:
+    def join_early(self, force: bool = False) -> None:
+        """Make the current stream wait for the early all-reduce (must run before a CUDA-graph capture ends).
+        `force`: the caller knows an early all-reduce ran (e.g. inside a replayed graph) although the per-step flag
+        has already been cleared."""
+        if (self._early_done or force) and self._comm_stream is not None:
             torch.cuda.current_stream(self.flat.device).wait_stream(self._comm_stream)
 
     def all_reduce(self, average: bool = True, early_done: Optional[bool] = None) -> None:
@@ -114,7 +127,7 @@ class FlatGrads:
         if not self._distributed():
             return
         if done:
-            self.join_early()
+            self.join_early(force=True)     # the flag above is already cleared: the wait must not depend on it
             self._reduce(self.flat[:self.split], average)
         else:
             self._reduce(self.flat, average)
@@ -218,6 +231,15 @@ class GraphedTrainStep:
                 self.capture_error = repr(e)
                 torch.cuda.synchronize(dev)
                 self.fg._early_done = False
+                # Kernels issued during a failed capture were only RECORDED: the bf16 weight packs allocated in this
+                # attempt hold uninitialised memory although their cache keys look valid, the zero pool was handed out
+                # without being cleared and an autograd hand-off may be parked.  Drop all of it before the retry / the
+                # eager fallback computes with garbage.
+                from . import functional as OF, ops as _ops
+                OF.clear_pack_cache()
+                OF.bump_param_epoch()
+                OF.reset_step_state()
+                _ops.reset_zero_pool()
                 if attempt == 0 and getattr(model, "_bridge_grad_hook", None) is not None:
                     model._bridge_grad_hook = None        # retry without the in-graph exchange
                     self.fg.split = self.fg.flat.numel()

@@ -331,6 +331,60 @@ def test_graphed_step_sees_parameter_updates_of_any_optimizer():
     assert rel_err(fg.flat, grads_e) < 1e-3
 
 
+def test_failed_graph_capture_falls_back_to_a_correct_eager_step():
+    """ADVICE r01 (parallel.py): kernels issued during a FAILED capture are only recorded, so the bf16 weight packs
+    allocated in that attempt hold uninitialised memory under valid-looking cache keys.  A loss_fn that synchronises
+    (.item()) makes the capture fail; the eager fallback must then equal a plain eager step, not run on garbage packs."""
+    from octic_vits_b200.parallel import FlatGrads, GraphedTrainStep
+    torch.manual_seed(7)
+    model = OcticVisionTransformer(img_size=64, patch_size=16, embed_dim=128, depth=4, num_heads=2, num_classes=10,
+                                   qkv_bias=True, init_scale=0.5).to(DEV).train()
+    fg = FlatGrads(model.parameters())
+    img = torch.randn(4, 3, 64, 64, device=DEV)
+    tgt = torch.randint(0, 10, (4,), device=DEV)
+    ref = GraphedTrainStep(model, fg, img.shape, use_graph=False)
+    loss_ref = float(ref(img, tgt))
+    grads_ref = fg.flat.clone()
+
+    def syncing_loss(logits, target):
+        loss = torch.nn.functional.cross_entropy(logits, target)
+        loss.item()                                   # illegal during stream capture
+        return loss
+    # every parameter gets a new version, so the failed capture has to re-pack (into never-executed buffers)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.0)
+    step = GraphedTrainStep(model, fg, img.shape, loss_fn=syncing_loss, warmup=1)
+    assert not step.graphed and "capture_error" in step.__dict__
+    loss_fb = float(step(img, tgt))
+    assert abs(loss_fb - loss_ref) <= 1e-5 * max(1.0, abs(loss_ref))
+    assert rel_err(fg.flat, grads_ref) < 1e-4
+
+
+def test_fused_grad_accumulation_is_scoped_to_the_flat_buffer_owner():
+    """ADVICE r01 (parallel.py:47): a FlatGrads must not change the autograd semantics of models it does not manage --
+    tensor hooks on their weights still see the gradient and .grad is produced by autograd."""
+    from octic_vits_b200.parallel import FlatGrads
+    torch.manual_seed(8)
+    mk = lambda: OcticVisionTransformer(img_size=32, patch_size=16, embed_dim=64, depth=2, num_heads=2, num_classes=4,
+                                        qkv_bias=True, init_scale=0.5).to(DEV).train()
+    managed, free = mk(), mk()
+    fg = FlatGrads(managed.parameters())
+    seen = []
+    w = free.blocks[0].attn.qkv.lin_E.weight
+    w.register_hook(lambda g: seen.append(g.detach().clone()))
+    img = torch.randn(2, 3, 32, 32, device=DEV)
+    free(img).sum().backward()
+    assert len(seen) == 1 and w.grad is not None and torch.equal(seen[0], w.grad)
+    fg.zero()
+    managed(img).sum().backward()
+    wm = managed.blocks[0].attn.qkv.lin_E.weight
+    assert wm.grad.data_ptr() == fg.flat[fg.offsets[[id(p) for p in fg.params].index(id(wm))]:].data_ptr()
+    assert float(wm.grad.abs().sum()) > 0
+    fg.close()
+    assert not any(getattr(p, "_octic_accumulate", False) for p in managed.parameters())
+
+
 def test_headline_model_equivariance_report(capsys):
     """BASELINE.json metric 'D8 equiv error' on the HEADLINE model: hybrid octic ViT-H/14 (DeiT-III init, layer scale
     1e-4 as shipped, and an O(1)-weights variant), bf16 GPU path, 224 px.  Equivariance of the 16-block octic trunk under

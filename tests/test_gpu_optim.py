@@ -146,3 +146,43 @@ def test_graphed_train_step_with_optimizer_learns_and_matches_eager():
     num = sum(float((pg[n] - pe[n]).pow(2).sum()) for n in pg)
     den = sum(float(pe[n].pow(2).sum()) for n in pe)
     assert (num / den) ** 0.5 < 2e-2
+
+
+def test_schedulable_hyperparameters_and_state_round_trip():
+    """ADVICE r01 (optim.py:90): weight decay and per-parameter lr multipliers can be changed after construction (cosine
+    weight-decay schedule, last-layer freezing of the DINOv2 recipe), every hyper-parameter survives
+    state_dict() -> load_state_dict(), and a re-allocated parameter anywhere in the list is detected."""
+    torch.manual_seed(0)
+    model = Bag().to(DEV)
+    fg = FlatGrads(model.parameters())
+    opt = FusedOptimizer(model, fg, kind="adamw", lr=1e-2, weight_decay=0.1, ema=None)
+    ref_p = [p.detach().cpu().clone() for p in fg.params]
+    m = [torch.zeros_like(p) for p in ref_p]
+    v = [torch.zeros_like(p) for p in ref_p]
+    gen = torch.Generator().manual_seed(3)
+    sched = [(0.1, 1.0), (0.3, 1.0), (0.3, 0.0)]          # (weight decay, lr multiplier of `bias`) per step
+    for step, (wd, bias_scale) in enumerate(sched, start=1):
+        opt.set_weight_decay(wd)
+        opt.set_lr_scales({"bias": bias_scale})
+        assert [w for w, _ in opt.seg_hparams] == [wd, 0.0, 0.0, 0.0]
+        grads = [0.01 * torch.randn(p.shape, generator=gen) for p in ref_p]
+        for p, g in zip(fg.params, grads):
+            p.grad.copy_(g)
+        opt.step()
+        # lr multiplier 0 freezes the tensor (its moments still advance)
+        OO.adamw_step(ref_p, grads, m, v, step, opt.lr, opt.betas, opt.eps, [wd, 0.0, 0.0, 0.0], [1.0, bias_scale, 1.0, 1.0])
+    for p, r in zip(fg.params, ref_p):
+        torch.testing.assert_close(p.detach().cpu(), r, rtol=2e-5, atol=2e-6)
+    with pytest.raises(ValueError):
+        opt.set_lr_scales({"no_such_parameter": 1.0})
+    sd = opt.state_dict()
+    opt2 = FusedOptimizer(model, fg, kind="adamw", lr=5.0, betas=(0.5, 0.5), eps=1.0, weight_decay=0.0)
+    opt2.set_ema_momentum(0.5)
+    opt2.load_state_dict(sd)
+    assert (opt2.lr, opt2.betas, opt2.eps, opt2.ema_momentum, opt2.step_count) == (opt.lr, opt.betas, opt.eps, opt.ema_momentum, 3)
+    assert opt2.seg_hparams == opt.seg_hparams and torch.equal(opt2.segs, opt.segs)
+    assert torch.equal(opt2.exp_avg, opt.exp_avg)
+    # a parameter re-allocated after construction (here the LAST one) is caught before any kernel writes through a stale pointer
+    model.tiny.data = model.tiny.data.clone()
+    with pytest.raises(Exception, match="re-allocated"):
+        opt.step()
