@@ -2,18 +2,21 @@
 """bench.py -- headline benchmark of the octic ViT hot path (contract: see the task brief / DESIGN.md section 6).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
-                    [--optimizer none|lamb|adamw] [--overlap] [--drop-path P] [--no-graph] [--no-cpu-baseline]
+                    [--optimizer none|lamb|adamw] [--no-overlap] [--drop-path P] [--no-graph] [--no-cpu-baseline]
 
 Metric (BASELINE.json): hybrid octic ViT-H/14 (DeiT-III: embed 1280, depth 32, heads 16, patch 14, 224 px) images/s,
 forward + backward (+ NCCL gradient all-reduce when N > 1), bf16 compute / fp32 residual, synthetic images, random-init
 weights.  One process per GPU (torchrun for N > 1); the batch is sharded over ranks (weak scaling: B images per GPU).
 
 The step is the public-API parallel.GraphedTrainStep: bf16 weight re-pack + forward + loss + backward replayed from one
-CUDA graph.  `--optimizer` adds the fused parameter update (optim.FusedOptimizer) to every step; `--overlap` (N > 1)
-moves the all-reduce of the dense half's gradients inside the graph, concurrent with the octic half's backward.
+CUDA graph.  `--optimizer` adds the fused parameter update (optim.FusedOptimizer) to every step.  For N > 1 the all-reduce of the
+dense half's gradients (88 % of the bytes) runs inside the graph, concurrent with the octic half's backward
+(`--no-overlap`: one all-reduce after the replay).
 
-`--impl reference` times the reference algorithm on the host CPU cores (the oracle port of the reference PyTorch
-path, oracle/octic_oracle.py -- the reference itself is pure PyTorch and is not present on the GPU box).
+`--impl reference` times the reference on the host CPU cores: the vendored, unmodified reference itself when
+baseline/_ref exists (tools/vendor_reference.sh; it travels to the GPU box with the repo snapshot), else the oracle port
+of the reference PyTorch path (oracle/octic_oracle.py).  The reference on the SAME B200 (eager and torch.compile) is
+measured by tools/bench_reference_gpu.py -> profiles/r02_reference_gpu.json.
 """
 from __future__ import annotations
 
@@ -98,6 +101,55 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port of the reference PyTorch path on the host cores
 # ----------------------------------------------------------------------------------------------------------------
+def vendored_reference_step_fn(batch: int):
+    """The UNMODIFIED reference (baseline/_ref, vendored by tools/vendor_reference.sh; git-ignored, travels with gpurun)
+    on the host cores: its own OcticVisionTransformer classes through its timm factory, bf16 autocast, fwd + bwd.  Two
+    stand-ins are unavoidable on a CPU: tools/timm_shim (timm is not installed) and the reference's own PyTorch GeluD8
+    in place of the CUDA-only Triton kernel, mapped exactly as octic_vits/d8_gelu.py:517-541 maps between them.
+    Returns None when baseline/_ref is absent."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "octic_vits" / "model.py").exists():
+        return None
+    for q in (str(ROOT / "tools" / "timm_shim"), str(ref)):
+        if q not in sys.path:
+            sys.path.insert(0, q)
+    import octic_vits.deit_models  # noqa: F401  (registers the factories)
+    from octic_vits import d8_layers, d8_utils
+    from timm.models import create_model as ref_create
+
+    class CpuGeluD8(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inner = d8_layers.GeluD8()
+
+        def forward(self, xs):
+            return d8_utils.convert_8tuple_to_5tuple(self.inner(d8_utils.convert_5tuple_to_8tuple(xs)))
+
+    def swap(mod):
+        for name, child in mod.named_children():
+            if isinstance(child, d8_layers.TritonGeluD8):
+                setattr(mod, name, CpuGeluD8())
+            else:
+                swap(child)
+
+    torch.manual_seed(0)
+    model = ref_create(MODEL["name"], num_classes=MODEL["classes"]).train()
+    swap(model)
+    img = torch.randn(batch, 3, MODEL["img"], MODEL["img"])
+    tgt = torch.randint(0, MODEL["classes"], (batch,))
+    params = [q for q in model.parameters() if q.requires_grad]
+
+    def step():
+        for q in params:
+            q.grad = None
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            logits = model(img)
+        loss = torch.nn.functional.cross_entropy(logits.float(), tgt)
+        loss.backward()
+        return loss.item()
+    return step
+
+
 def cpu_reference_step_fn(batch: int):
     from oracle import octic_oracle as O
     from octic_vits_b200.deit_models import create_model
@@ -121,15 +173,24 @@ def cpu_reference_step_fn(batch: int):
 
 
 def time_cpu_reference(batch: int, steps: int, warmup: int):
+    """(images/s, s/step, threads, kind): kind = "reference" when the vendored reference itself ran, "port" for the
+    oracle restatement (baseline/_ref absent)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_reference_step_fn(batch)
+    kind = "reference"
+    step = None
+    try:
+        step = vendored_reference_step_fn(batch)
+    except Exception as e:  # noqa: BLE001  (a broken vendored copy must not take the bench line down)
+        print(f"bench.py: vendored reference unusable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+    if step is None:
+        kind, step = "port", cpu_reference_step_fn(batch)
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(steps):
         step()
     dt = (time.perf_counter() - t0) / steps
-    return batch / dt, dt, torch.get_num_threads()
+    return batch / dt, dt, torch.get_num_threads(), kind
 
 
 def run_reference_arm(args):
@@ -138,14 +199,16 @@ def run_reference_arm(args):
         return
     batch = 4
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
-    ips, dt, cores = time_cpu_reference(batch, steps, warmup)
+    ips, dt, cores, kind = time_cpu_reference(batch, steps, warmup)
+    what = ("the unmodified reference (baseline/_ref: its own OcticVisionTransformer via its timm factory; PyTorch GeluD8 "
+            "for the CUDA-only Triton kernel)" if kind == "reference" else "CPU oracle port of the reference PyTorch path")
     line = {
         "impl": "reference", "metric": "hybrid octic ViT-H/14 images/s fwd+bwd", "value": ips, "unit": "images/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "hybrid_deit_huge_patch14 fwd+bwd, 224px, CPU oracle port of the reference PyTorch path "
-                               "(bf16 autocast), bounded sample", "batch": batch},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
+        "config": {"workload": f"hybrid_deit_huge_patch14 fwd+bwd, 224px, {what}, bf16 autocast on the host cores, "
+                               "bounded sample", "batch": batch},
+        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
                          "sample": f"batch {batch}, {warmup} warm-up + {steps} timed fwd+bwd steps"},
         "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -202,7 +265,7 @@ def run_ours(args):
 
     # public-API step: fwd + loss + bwd captured in a CUDA graph (parallel.GraphedTrainStep), all-reduce after the replay
     overlap = False
-    if world > 1 and args.overlap:
+    if world > 1 and not args.no_overlap:
         # the dense half's gradients (88 % of the bytes) are all-reduced from an autograd hook at the bridge, on a side
         # stream inside the captured graph, while the octic half is still in backward
         from octic_vits_b200.parallel import install_early_allreduce
@@ -249,14 +312,28 @@ def run_ours(args):
     torch.cuda.synchronize()
     launches = _lib.STATS.kernel_launches * args.steps
 
-    # dominant kernel: the tcgen05 grouped GEMM.  Time every launch of it with CUDA events on the launching stream
-    # during extra (untimed-for-the-headline) steps, so the headline number carries no event overhead.
+    # Roofline evidence, measured live on this binary: every launch of the two kernel families that dominate the step is
+    # timed with CUDA events on the launching stream during one extra eager step (untimed for the headline, so the headline
+    # number carries no event overhead).
+    #   dense family  (tensor bound): gemm_tn_kernel with one group + gemm_wgrad_kernel = every nn.Linear of the 16 dense
+    #                 blocks, forward, dgrad and wgrad (82 % of the model FLOPs)
+    #   octic family  (HBM bound): the four LinearD8 forward GEMMs of the 16 octic blocks
     _lib.STATS.reset()
-    _lib.STATS.profile_prefixes = ("octic_gemm_bf16", "octic_linear_d8_fwd", "octic_linear_d8_dgrad")
+    _lib.STATS.profile_prefixes = ("octic_gemm_bf16", "octic_gemm_wgrad_bf16", "octic_linear_d8_fwd", "octic_linear_d8_dgrad",
+                                   "octic_linear_d8_wgrad", "octic_attention_fwd", "octic_attention_bwd")
     eager_step(img_dev, tgt_dev)
     torch.cuda.synchronize()
-    gemm_ms, gemm_flops, gemm_calls = _lib.STATS.collect()
+    fam = _lib.STATS.collect_by_name()
     _lib.STATS.profile_prefixes = ()
+    z = (0.0, 0.0, 0)
+    gemm_ms = fam.get("octic_gemm_bf16", z)[0] + fam.get("octic_gemm_wgrad_bf16", z)[0]
+    gemm_flops = fam.get("octic_gemm_bf16", z)[1] + fam.get("octic_gemm_wgrad_bf16", z)[1]
+    gemm_calls = fam.get("octic_gemm_bf16", z)[2] + fam.get("octic_gemm_wgrad_bf16", z)[2]
+    oct_ms, oct_flops, oct_calls = fam.get("octic_linear_d8_fwd", z)
+    # algorithmic bytes of the octic forward linears per token and block (fp32 residual, bf16 activations; weights are
+    # L2 resident and excluded): qkv 2D+6D, proj+residual 2D+4D+4D, fc1 2D+8D, fc2+residual 8D+4D+4D = 44 D
+    T_tokens = B * ((MODEL["img"] // MODEL["patch"]) ** 2 + 1)
+    oct_bytes = 44.0 * MODEL["dim"] * T_tokens * (MODEL["depth"] // 2)
 
     if gstep.graphed:
         gstep.stage(img_host, tgt_host)
@@ -279,9 +356,9 @@ def run_ours(args):
         ips = world * B / (ms_dev * 1e-3)
         flops_img = model_flops_per_image(True)
         achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
-        cpu_ips, cpu_dt, cores = (None, None, None)
+        cpu_ips, cpu_dt, cores, cpu_kind = (None, None, None, "port")
         if world == 1 and not args.no_cpu_baseline:
-            cpu_ips, cpu_dt, cores = time_cpu_reference(2, 2, 1)
+            cpu_ips, cpu_dt, cores, cpu_kind = time_cpu_reference(2, 2, 1)
         line = {
             "metric": "hybrid octic ViT-H/14 images/s fwd+bwd", "value": ips, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -297,20 +374,27 @@ def run_ours(args):
                        "l2": "activations per step (>50 GB) exceed the 126 MB L2; no explicit flush"},
             "model_tflops": ips * flops_img / 1e12,
             "tc_util_vs_sustained_peak": ips * flops_img / 1e12 / (world * peaks["tf_sustained"]),
-            "roofline": {"kernel": "gemm_tn_kernel (tcgen05 grouped bf16 GEMM: LinearD8 fwd/dgrad + dense Linear fwd/dgrad)",
+            "roofline": {"kernel": "gemm_tn_kernel<groups=1> + gemm_wgrad_kernel (tcgen05 bf16 GEMM, CTA pairs): every nn.Linear "
+                                   "of the 16 dense blocks, forward + dgrad + wgrad",
                          "bound": "tensor", "achieved": achieved_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved_tf / peaks["tf_sustained"]) if achieved_tf else None, "traffic": None,
+                         "frac": (achieved_tf / peaks["tf_sustained"]) if achieved_tf else None,
+                         # DRAM bytes per launch come from ncu --set full captures of single shapes, not from this run
+                         "traffic": None, "traffic_source": "profiles/r02_ncu_*.md (per-shape dram__bytes vs algorithmic bytes)",
                          "peak_source": f"{peaks['src']} (bf16 sustained)", "launches_timed": gemm_calls,
-                         "share_of_step": gemm_ms / ms_dev,
-                         # `achieved` averages 259 launches of many shapes, so there is no single per-launch traffic figure;
-                         # ncu --set full per shape (profiles/r01_ncu_s5.md, batch 128): DRAM bytes vs algorithmic bytes
-                         "traffic_samples": {
-                             "dense qkv fwd (M=32896, N=3840, K=1280)": {"dram_bytes": 3.01e8, "algorithmic_bytes": 3.47e8},
-                             "dense fc2 + residual (N=1280, K=5120)": {"dram_bytes": 8.79e8, "algorithmic_bytes": 7.71e8},
-                             "octic fc2 + residual (LinearD8 5120 -> 1280)": {"dram_bytes": 7.35e8, "algorithmic_bytes": 7.62e8},
-                             "octic qkv head-major (LinearD8 1280 -> 3840)": {"dram_bytes": 4.51e8, "algorithmic_bytes": 3.40e8}}},
-            "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "batch 2, 1 warm-up + 2 timed fwd+bwd steps of the same model (oracle port, bf16 autocast)"},
+                         "share_of_step": gemm_ms / ms_dev},
+            "roofline_octic": {"kernel": "gemm_tn_kernel<groups=6> (LinearD8 forward: qkv, proj+residual, fc1, fc2+residual of "
+                                         "the 16 octic blocks)",
+                               "bound": "hbm", "achieved": (oct_bytes / (oct_ms * 1e-3) / 1e9) if oct_ms > 0 else None,
+                               "peak": peaks["hbm"], "unit": "GB/s",
+                               "frac": (oct_bytes / (oct_ms * 1e-3) / 1e9 / peaks["hbm"]) if oct_ms > 0 else None,
+                               "traffic": None, "algorithmic_bytes_per_token_per_block": 44 * MODEL["dim"],
+                               "peak_source": f"{peaks['src']} (copy bandwidth)", "launches_timed": oct_calls,
+                               "share_of_step": oct_ms / ms_dev,
+                               "tflops": (oct_flops / (oct_ms * 1e-3) / 1e12) if oct_ms > 0 else None},
+            "step_breakdown_ms": {k: round(v[0], 3) for k, v in sorted(fam.items())},
+            "cpu_baseline": {"value": cpu_ips, "unit": "images/s", "cores": cores, "kind": cpu_kind,
+                             "sample": "batch 2, 1 warm-up + 2 timed fwd+bwd steps of the same model on the host cores, bf16 autocast ("
+                                       + ("the vendored reference itself" if cpu_kind == "reference" else "oracle port") + ")"},
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": img_host.numel() * 4 + tgt_host.numel() * 8, "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
@@ -318,12 +402,17 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        # a CUDA graph that captured NCCL kernels keeps the communicator alive: release it before tearing NCCL down
-        # (with --overlap the process otherwise hangs in destroy_process_group, observed at 2 GPUs)
-        if overlap:
-            gstep.close()
-            dist.barrier()
+        # A CUDA graph that captured NCCL kernels keeps the communicator alive: release it before tearing NCCL down (the
+        # process otherwise hangs in destroy_process_group, observed at 2 GPUs in round 1).  The result line is already
+        # printed; a watchdog ends the process if the teardown still does not return.
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        gstep.close()
+        del gstep
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def main():
@@ -336,9 +425,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the eager step instead of the captured CUDA graph")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: all-reduce the dense half's gradients from inside the captured graph while the octic half "
-                         "is still in backward (measured +1.0 %% at 2 GPUs; opt-in, see DESIGN.md section 5)")
+    ap.add_argument("--overlap", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: one all-reduce after the graph replay instead of all-reducing the dense half's gradients "
+                         "from inside the captured graph while the octic half is still in backward (DESIGN.md section 5)")
     ap.add_argument("--optimizer", default="none", choices=["none", "lamb", "adamw"],
                     help="also run the fused parameter update every step (the headline metric is fwd+bwd)")
     args = ap.parse_args()

@@ -160,13 +160,19 @@ class _Stats:
 
     def collect(self):
         """(total ms, total algorithmic FLOPs, number of timed calls) of the profiled entry points; synchronises."""
+        per = self.collect_by_name()
+        return (sum(v[0] for v in per.values()), sum(v[1] for v in per.values()), sum(v[2] for v in per.values()))
+
+    def collect_by_name(self):
+        """{entry point: (ms, algorithmic FLOPs, calls)} of the profiled entry points; synchronises."""
         import torch
         torch.cuda.synchronize()
-        ms = sum(a.elapsed_time(b) for a, b, _ in self._events)
-        flops = sum(f for _, _, f in self._events)
-        n = len(self._events)
+        per = {}
+        for name, a, b, f in self._events:
+            ms0, f0, n0 = per.get(name, (0.0, 0.0, 0))
+            per[name] = (ms0 + a.elapsed_time(b), f0 + f, n0 + 1)
         self._events = []
-        return ms, flops, n
+        return per
 
 
 STATS = _Stats()
@@ -182,7 +188,7 @@ def call(name: str, *args, flops: float = 0.0, extra_kernels: int = 0) -> None:
         a.record()
         rc = fn(*args)
         b.record()
-        STATS._events.append((a, b, flops))
+        STATS._events.append((name, a, b, flops))
     else:
         rc = fn(*args)
     check(rc, name)

@@ -39,13 +39,14 @@ constexpr int kAccStride = 256;                       // columns between the two
 struct SmemLayout {
   uint32_t a_off, b_off, stg_off, bar_off, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int stages, int b_stage_bytes, int epi_warps) {
+// b_slots: B k-block buffers -- one per ring stage, or (weight-stationary mode) the k-blocks of one whole-K weight tile
+__host__ __device__ inline SmemLayout smem_layout(int stages, int b_stage_bytes, int epi_warps, int b_slots = -1) {
   SmemLayout L;
   L.a_off = 0;
   L.b_off = stages * kAStageBytes;
-  L.stg_off = L.b_off + stages * b_stage_bytes;
+  L.stg_off = L.b_off + (b_slots < 0 ? stages : b_slots) * b_stage_bytes;
   L.bar_off = L.stg_off + epi_warps * kStagingWords * 4;
-  L.total = L.bar_off + (2 * kMaxStages + 4) * 8 + 16;
+  L.total = L.bar_off + (2 * kMaxStages + 4) * 8 + 16 + 2 * 8;     // ring + accumulator barriers, TMEM pointer, wfull / wempty
   return L;
 }
 
@@ -118,7 +119,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int stages = p.num_stages;
   const int b_rows = p.block_n / NCTA;                    // B rows held by this CTA
   const int b_stage_bytes = b_rows * kBlockK * 2;
-  const SmemLayout L = smem_layout(stages, b_stage_bytes, kEpiWarps);
+  // Weight-stationary mode (p.ws, CTA pairs only; the small-K irrep groups of LinearD8, K <= 320): a CTA pair walks a
+  // CONTIGUOUS range of the tile list in (group, n block)-major order, so consecutive tiles share their weight tile.
+  // The whole-K weight tile is loaded once into its own buffer and only the A k-blocks stream through the ring: the
+  // L2 -> shared-memory traffic per tile drops from A + B (144 KB for a 128 x 256 x 192 tile) to A (48 KB).  In tile
+  // order the kernel was bound by exactly that traffic (1.06 GB per fc1 launch at ~10 TB/s of L2 bandwidth = 105 of its
+  // 144 us; the epilogue alone drains the same output in 65 us, profiles/r02_epilogue_probe.txt).
+  const bool ws = NCTA == 2 && p.ws != 0;
+  const SmemLayout L = smem_layout(stages, b_stage_bytes, kEpiWarps, ws ? p.ws_kb_max : -1);
   const int rank = NCTA == 2 ? static_cast<int>(cluster_ctarank()) : 0;
   const int cid = blockIdx.x / NCTA, ncl = gridDim.x / NCTA;   // this CTA (pair) and the number of them
 
@@ -127,6 +135,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull_bar = empty_bar + kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* wfull_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 4);   // weight tile landed (leader's barrier)
+  uint64_t* wempty_bar = wfull_bar + 1;                              // every MMA that reads the weight tile has completed
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -140,6 +150,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps * NCTA);   // one arrive per epilogue warp of the pair (leader's barrier)
     }
+    mbar_init(wfull_bar, 1);
+    mbar_init(wempty_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -153,11 +165,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr;
 
   const int total_tiles = p.num_m_blocks * p.tiles_per_m;     // num_m_blocks counts 128 * NCTA-row blocks
+  // tile sequence of this CTA (pair): tile_first, tile_first + tile_step, ... < tile_last
+  //   tile order      : tile = m_pair * tiles_per_m + j, CTAs take every ncl-th tile
+  //   weight stationary: tile = j * num_m_blocks + m_pair, CTAs take contiguous ranges (same j => same weight tile)
+  const int tile_first = ws ? static_cast<int>(static_cast<long>(total_tiles) * cid / ncl) : cid;
+  const int tile_last = ws ? static_cast<int>(static_cast<long>(total_tiles) * (cid + 1) / ncl) : total_tiles;
+  const int tile_step = ws ? 1 : ncl;
 
   auto decode = [&](int tile, int& m_blk, int& g, int& n_blk) {
-    const int mp = tile / p.tiles_per_m;
+    const int mp = ws ? tile % p.num_m_blocks : tile / p.tiles_per_m;
     m_blk = mp * NCTA + rank;                                  // this CTA's own 128-row block
-    int j = tile - mp * p.tiles_per_m;
+    int j = ws ? tile / p.num_m_blocks : tile - mp * p.tiles_per_m;
     g = 0;
 #pragma unroll 1
     for (int i = 1; i < p.num_groups; ++i)
@@ -170,16 +188,33 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl) {
+      int cur_j = -1;
+      uint32_t wphase = 0;
+      for (int tile = tile_first; tile < tile_last; tile += tile_step) {
         int m_blk, g, n_blk;
         decode(tile, m_blk, g, n_blk);
         const GemmGroup& G = p.g[g];
         const CUtensorMap* tmB = G.b_map ? &tmB1 : &tmB0;
+        if (NCTA == 2 && ws) {
+          const int j = tile / p.num_m_blocks;
+          if (j != cur_j) {
+            // new (group, n block): replace the stationary weight tile once every MMA that reads the old one is done
+            if (cur_j >= 0) { mbar_wait(wempty_bar, wphase); wphase ^= 1; }
+            cur_j = j;
+            if (rank == 0) mbar_arrive_expect_tx(wfull_bar, 2 * G.k_blocks * b_stage_bytes);
+            for (int kb = 0; kb < G.k_blocks; ++kb)
+              tma_load_2d_pair(smem + L.b_off + kb * b_stage_bytes, tmB, wfull_bar, kb * kBlockK,
+                               G.b_row + n_blk * p.block_n + rank * b_rows);
+          }
+        }
         for (int kb = 0; kb < G.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + L.a_off + stage * kAStageBytes;
           uint8_t* b_dst = smem + L.b_off + stage * b_stage_bytes;
-          if (NCTA == 2) {
+          if (NCTA == 2 && ws) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kAStageBytes);
+            tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], G.a_col + kb * kBlockK, m_blk * kBlockM);
+          } else if (NCTA == 2) {
             // both CTAs' loads complete on the leader's barrier, which expects the bytes of the pair
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * (kAStageBytes + b_stage_bytes));
             tma_load_2d_pair(a_dst, &tmA, &full_bar[stage], G.a_col + kb * kBlockK, m_blk * kBlockM);
@@ -200,12 +235,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
+      int cur_j = -1;
+      uint32_t wphase = 0;
+      for (int tile = tile_first; tile < tile_last; tile += tile_step, ++it) {
         int m_blk, g, n_blk;
         decode(tile, m_blk, g, n_blk);
         const int k_blocks = p.g[g].k_blocks;
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int j = ws ? tile / p.num_m_blocks : 0;
+        if (ws && j != cur_j) {
+          mbar_wait(wfull_bar, wphase);      // the stationary weight tile of this (group, n block) has landed
+          wphase ^= 1;
+          cur_j = j;
+        }
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * kAccStride;
@@ -214,7 +257,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           // K-major, SWIZZLE_128B: rows are 128 B, 8-row groups are 1024 B apart (SBO); LBO unused.
           const uint64_t da = make_smem_desc(smem_u32(smem + L.a_off + stage * kAStageBytes), 0, 1024);
-          const uint64_t db = make_smem_desc(smem_u32(smem + L.b_off + stage * b_stage_bytes), 0, 1024);
+          const uint64_t db = make_smem_desc(smem_u32(smem + L.b_off + (ws ? kb : stage) * b_stage_bytes), 0, 1024);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advancing 16 bf16 (32 B) inside the swizzle atom = +2 in the (addr >> 4) field
@@ -229,6 +272,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (kb == k_blocks - 1) umma_commit(&tfull_bar[as]);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+        if (NCTA == 2 && ws) {
+          // last tile of this weight tile: tell both producers when its MMAs have completed
+          const int nxt = tile + tile_step;
+          if (nxt < tile_last && nxt / p.num_m_blocks != j) umma_commit_pair(wempty_bar);
         }
       }
     }
@@ -275,7 +323,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     bool res_ok = false;
     auto prefetch_resid = [&](int tile_, int c0_) {
       res_ok = false;
-      if (MODE != EPI_RESID || p.resid_in == nullptr || tile_ >= total_tiles) return;
+      if (MODE != EPI_RESID || p.resid_in == nullptr || tile_ >= tile_last) return;
       int mb_, g_, nb_;
       decode(tile_, mb_, g_, nb_);
       const GemmGroup& G_ = p.g[g_];
@@ -298,8 +346,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     };
     int it = 0;
-    prefetch_resid(cid, half * 32);
-    for (int tile = cid; tile < total_tiles; tile += ncl, ++it) {
+    prefetch_resid(tile_first, half * 32);
+    for (int tile = tile_first; tile < tile_last; tile += tile_step, ++it) {
       int m_blk, g, n_blk;
       decode(tile, m_blk, g, n_blk);
       const GemmGroup& G = p.g[g];
@@ -724,9 +772,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (direct_ok(G, n0, c0)) process_direct(ra, c0);
           else process_chunk(ra, c0);
           if (c0 + kChunkStep < n_valid) prefetch_resid(tile, c0 + kChunkStep);
-          else prefetch_resid(tile + ncl, half * 32);
+          else prefetch_resid(tile + tile_step, half * 32);
         }
-        if (half * 32 >= n_valid) prefetch_resid(tile + ncl, half * 32);
+        if (half * 32 >= n_valid) prefetch_resid(tile + tile_step, half * 32);
       } else {
         uint32_t ra[32];
         for (int c0 = half * 32; c0 < n_valid; c0 += kChunkStep) {
@@ -1101,8 +1149,23 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   // scatter; the irrep groups with K = 160 / 320 (3-5 k-blocks per tile) run faster as single CTAs (same measurement).
   int kmax = 0;
   for (int i = 0; i < d->num_groups; ++i) kmax = d->groups[i].k > kmax ? d->groups[i].k : kmax;
-  const bool want_pairs = forced_ncta == 2 || (forced_ncta != 1 && (d->num_groups == 1 || kmax >= 512 || d->head_H > 0));
-  const int ncta = (want_pairs && d->block_n % 16 == 0 && d->block_n >= 32 && d->M > kBlockM && num_sms() >= 2) ? 2 : 1;
+  // Weight-stationary tile order (see gemm_tn_kernel) for the grouped small-K launches: every group's whole-K weight
+  // tile must fit next to a >= 3-stage A ring (K <= 320 -> 5 k-blocks).  OFF by default: measured SLOWER on B200 at the
+  // headline shapes (tools/gpu/r2_f.sh, profiles/r02_gemm_weight_stationary.txt: fc1 172 vs 136 us, proj + residual
+  // 166 vs 129, qkv head-major 455 vs 232) -- the L2 -> SM operand traffic it removes was not the limiter, and walking
+  // the output in (n block)-major order writes every row in 20-30 separate visits instead of one.  OCTIC_GEMM_WS=1
+  // enables it for experiments.
+  static int ws_env = -1;
+  if (ws_env < 0) {
+    const char* e = getenv("OCTIC_GEMM_WS");
+    ws_env = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  const bool pairs_possible = d->block_n % 16 == 0 && d->block_n >= 32 && d->M > kBlockM && num_sms() >= 2;
+  const bool want_ws = ws_env == 1 && forced_ncta != 1 && d->num_groups > 1 && kmax <= 320 && pairs_possible &&
+                       d->remap_group == 0;
+  const bool want_pairs = want_ws || forced_ncta == 2 ||
+                          (forced_ncta != 1 && (d->num_groups == 1 || kmax >= 512 || d->head_H > 0));
+  const int ncta = (want_pairs && pairs_possible) ? 2 : 1;
   p.num_m_blocks = (d->M + kBlockM * ncta - 1) / (kBlockM * ncta);
   int tiles = 0;
   for (int i = 0; i < d->num_groups; ++i) {
@@ -1131,7 +1194,18 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   p.head_D = d->head_D;
   p.tiles_per_m = tiles;
   const int b_stage_bytes = (d->block_n / ncta) * kBlockK * 2;
-  int stages = (kMaxDynSmem - 1024 - (kEpiWarps * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16)) / (kAStageBytes + b_stage_bytes);
+  const int fixed_bytes = 1024 + kEpiWarps * kStagingWords * 4 + (2 * kMaxStages + 4) * 8 + 16 + 2 * 8;
+  int stages = (kMaxDynSmem - fixed_bytes) / (kAStageBytes + b_stage_bytes);
+  if (want_ws) {
+    int kb_max = 0;
+    for (int i = 0; i < d->num_groups; ++i) kb_max = p.g[i].k_blocks > kb_max ? p.g[i].k_blocks : kb_max;
+    const int ring = (kMaxDynSmem - fixed_bytes - kb_max * b_stage_bytes) / kAStageBytes;
+    if (ring >= 3) {
+      p.ws = 1;
+      p.ws_kb_max = kb_max;
+      stages = ring;
+    }
+  }
   if (stages > kMaxStages) stages = kMaxStages;
   static int stage_cap = -1;      // OCTIC_GEMM_STAGES=n caps the TMA ring depth (pipeline-depth experiments)
   if (stage_cap < 0) {
@@ -1143,7 +1217,7 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   // shallow ring: a producer that runs far ahead only competes with the epilogue's own global traffic (measured,
   // tools/gpu_s5_st.sh: qkv head-major 269 -> 214 us, octic proj + residual 152 -> 127 us at 2 stages; K >= 640 and the
   // plain epilogues want the deep ring).
-  if (stage_cap == 0 && (d->head_H > 0 || (d->mode == EPI_RESID && kmax <= 320)) && stages > 2) stages = 2;
+  if (stage_cap == 0 && !p.ws && (d->head_H > 0 || (d->mode == EPI_RESID && kmax <= 320)) && stages > 2) stages = 2;
   if (stages < 2) return OCTIC_ERR_ARG;
   p.num_stages = stages;
   p.mode = d->mode;
@@ -1178,7 +1252,7 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   } else {
     tmB1 = tmB0;
   }
-  const SmemLayout L = smem_layout(stages, b_stage_bytes, kEpiWarps);
+  const SmemLayout L = smem_layout(stages, b_stage_bytes, kEpiWarps, p.ws ? p.ws_kb_max : -1);
   const int smem_bytes = L.total + 1024;
   const int total_tiles = p.num_m_blocks * p.tiles_per_m;
   int grid = num_sms() / ncta;                       // CTAs (ncta = 1) or CTA pairs (ncta = 2)

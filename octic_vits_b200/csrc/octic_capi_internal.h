@@ -34,6 +34,8 @@ struct GemmParams {
   const void* gelu_pre;
   float* colsum;
   int direct;   // 1: full aligned chunks go registers -> global without the shared-memory transpose
+  int ws;       // weight-stationary tile order (CTA pairs, small-K groups): see gemm_tn_kernel
+  int ws_kb_max;
 };
 
 struct WgradGroup {

@@ -240,6 +240,16 @@ class GraphedTrainStep:
                 OF.bump_param_epoch()
                 OF.reset_step_state()
                 _ops.reset_zero_pool()
+                # an aborted capture can leave the device's default RNG registered as "capturing" (the next torch.randn
+                # then raises "Offset increment outside graph capture"); a trivial capture that completes resets it
+                try:
+                    dummy = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(dummy):
+                        torch.zeros(1, device=dev)
+                    del dummy
+                    torch.cuda.synchronize(dev)
+                except Exception:                         # noqa: BLE001 - best effort
+                    pass
                 if attempt == 0 and getattr(model, "_bridge_grad_hook", None) is not None:
                     model._bridge_grad_hook = None        # retry without the in-graph exchange
                     self.fg.split = self.fg.flat.numel()

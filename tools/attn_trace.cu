@@ -31,18 +31,38 @@ int main(int argc, char** argv) {
   HeadMap m;
   m.octic = octic; m.hd = hd; m.D = D; m.C = D / 8; m.ch = hd / 8;
   for (int it = 0; it < 3; ++it) {
+#ifdef OCTIC_ATTN_TRACE
     int zero[2] = {0, 0};
     cudaMemcpyToSymbol(g_trace_n, zero, sizeof(zero));
+#endif
     if (bwd && it == 0) {
       launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
       cudaDeviceSynchronize();
+#ifdef OCTIC_ATTN_TRACE
       cudaMemcpyToSymbol(g_trace_n, zero, sizeof(zero));
+#endif
     }
     int rc = bwd ? launch_attn_bwd_tc(qkv, o /* stands in for dO */, lse, delta, dqkv, B, N, H, m, 0)
                  : launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e != cudaSuccess) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
   }
+  {
+    // wall time of the launch at this B (CUDA events, 5 launches after the warm-up above)
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    for (int it = 0; it < 5; ++it) {
+      if (bwd) launch_attn_bwd_tc(qkv, o, lse, delta, dqkv, B, N, H, m, 0);
+      else launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
+    }
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("B=%d %s octic=%d: %.1f us per launch\n", B, bwd ? "bwd" : "fwd", octic, ms * 200.f);
+  }
+#ifdef OCTIC_ATTN_TRACE
   std::vector<long long> tr(2 * 2048);
   int n[2];
   cudaMemcpyFromSymbol(tr.data(), g_trace, sizeof(long long) * 2 * 2048);
@@ -59,5 +79,6 @@ int main(int argc, char** argv) {
     }
     printf("\n");
   }
+#endif
   return 0;
 }
