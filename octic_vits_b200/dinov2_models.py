@@ -145,6 +145,7 @@ class NestedTensorBlock(Block):
         assert isinstance(self.attn, MemEffAttention)
         return [_DenseBlockBase.forward(self, x, nested=True) for x in x_list]
 
+    @OF.opaque_to_compile
     def forward(self, x_or_x_list):
         if isinstance(x_or_x_list, Tensor):
             return super().forward(x_or_x_list)
@@ -347,6 +348,7 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
             return tuple(zip(outputs, class_tokens))
         return tuple(outputs)
 
+    @OF.opaque_to_compile
     def forward(self, *args, is_training=False, **kwargs):
         """reference :255-260"""
         ret = self.forward_features(*args, **kwargs)

@@ -411,6 +411,38 @@ class MlpResidualFn(torch.autograd.Function):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# packed per-irrep scale vectors  (AffineD8 / LayerScaleD8 parameters, reference d8_layers.py:132-158, 189-212)
+# ----------------------------------------------------------------------------------------------------------------
+class PackAlphaFn(torch.autograd.Function):
+    """(alpha_A1, alpha_A2, alpha_B1, alpha_B2 [C], alpha_E [2C]) -> the packed [8C] vector [A1|A2|B1|B2|E|E] the kernels
+    index by packed column (alpha_E serves both E rows).  Backward: the five gradients are slices of the incoming [8C]
+    gradient, with the two E halves summed.  When the parameters' .grad tensors are consecutive views of one flat
+    buffer (parallel.FlatGrads registers them in this order) they are accumulated with two launches for the whole
+    module instead of six slice + accumulate kernels -- an octic block uses four such vectors, 16 blocks per step."""
+
+    @staticmethod
+    def forward(ctx, a1, a2, b1, b2, e):
+        ctx.params = (a1, a2, b1, b2, e)
+        return torch.cat((a1, a2, b1, b2, e, e))
+
+    @staticmethod
+    def backward(ctx, g):
+        C = ctx.params[0].numel()
+        g = _c(g)
+        tg = [_grad_target(p) for p in ctx.params]
+        if all(t is not None for t in tg):
+            base = tg[0]
+            offs = (0, C, 2 * C, 3 * C, 4 * C)
+            if all(t.data_ptr() == base.data_ptr() + 4 * o for t, o in zip(tg, offs)) and \
+                    base.untyped_storage().nbytes() >= 4 * (base.storage_offset() + 6 * C):
+                span = torch.as_strided(base, (6 * C,), (1,))
+                span.add_(g[:6 * C])
+                span[4 * C:].add_(g[6 * C:])
+                return None, None, None, None, None
+        return g[:C], g[C:2 * C], g[2 * C:3 * C], g[3 * C:4 * C], g[4 * C:6 * C] + g[6 * C:]
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # normalisation
 # ----------------------------------------------------------------------------------------------------------------
 class LayerNormFn(torch.autograd.Function):
@@ -551,6 +583,37 @@ def unpack_five(x: torch.Tensor):
     C = x.shape[-1] // 8
     return (x[..., 0:C], x[..., C:2 * C], x[..., 2 * C:3 * C], x[..., 3 * C:4 * C],
             x[..., 4 * C:].unflatten(-1, (2, 2 * C)))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# torch.compile / autocast contract of the boundary (SURVEY.md section 8b "Threading / streams")
+# ----------------------------------------------------------------------------------------------------------------
+def opaque_to_compile(fn):
+    """Decorator for the forward methods of the reference-facing modules.  The kernels are reached through a C ABI with
+    raw pointers; Dynamo cannot (and must not: no compiler-generated kernels on this path) trace into them.  Marking the
+    module forwards `torch.compiler.disable` makes `torch.compile(model)` -- what the DeiT recipe does, reference
+    deit/main.py:341-342 -- a supported call: Dynamo compiles whatever surrounds these modules and runs them as they
+    are, with their hand-written autograd, instead of failing inside ctypes."""
+    return torch.compiler.disable(fn, recursive=True)
+
+
+STRICT_AUTOCAST = False
+
+
+def set_strict_autocast(on: bool) -> None:
+    """The reference decides the GEMM dtype from the autocast context (bf16 under torch.autocast, fp32 without).  This
+    implementation has ONE arithmetic: bf16 operands with fp32 accumulation and an fp32 residual stream -- what the
+    reference computes under torch.autocast(dtype=torch.bfloat16) -- whether or not an autocast context is active.
+    With strict mode on, calling a model outside a CUDA bf16 autocast region raises instead of silently computing in
+    bf16 where the reference would have computed in fp32."""
+    global STRICT_AUTOCAST
+    STRICT_AUTOCAST = bool(on)
+
+
+def check_autocast() -> None:
+    if STRICT_AUTOCAST and not (torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+        raise OcticError("strict autocast: this implementation always computes like the reference under "
+                         "torch.autocast('cuda', dtype=torch.bfloat16); there is no fp32 (autocast-off) or fp16 GEMM path")
 
 
 def require_cuda(t: torch.Tensor) -> None:

@@ -61,6 +61,7 @@ class TritonGeluD8(nn.Module):
     """Drop-in for the reference's TritonGeluD8 (d8_gelu.py:480-482): y = R2I(gelu(I2R(x))), one fused sm_100a kernel
     (not Triton -- the name is kept because the reference passes this class around as `act_layer`)."""
 
+    @OF.opaque_to_compile
     def forward(self, xs):
         x = OF.pack_five(xs)
         OF.require_cuda(x)
@@ -94,6 +95,7 @@ class LinearD8(nn.Module):
     def weights(self):
         return (self.lin_A1.weight, self.lin_A2.weight, self.lin_B1.weight, self.lin_B2.weight, self.lin_E.weight)
 
+    @OF.opaque_to_compile
     def forward(self, x_batched):
         assert len(x_batched) == 5, "Input should be a 5-tuple"
         x = OF.pack_five(x_batched)
@@ -127,7 +129,7 @@ class AffineD8(nn.Module):
 
     def packed_alpha(self) -> Tensor:
         """[D] in packed column order; alpha_E serves both E rows (its gradient sums over them through this cat)."""
-        return torch.cat((self.alpha_A1, self.alpha_A2, self.alpha_B1, self.alpha_B2, self.alpha_E, self.alpha_E))
+        return OF.PackAlphaFn.apply(self.alpha_A1, self.alpha_A2, self.alpha_B1, self.alpha_B2, self.alpha_E)
 
     def forward(self, xs):
         y0 = self.alpha_A1 * xs[0]
@@ -170,6 +172,7 @@ class LayerNormD8(nn.Module):
             return self.scaling.packed_alpha(), self.scaling.beta
         return torch.ones(self.channels, dtype=torch.float32, device=ref.device), None
 
+    @OF.opaque_to_compile
     def forward(self, xs):
         x = OF.pack_five(xs)
         OF.require_cuda(x)
@@ -241,6 +244,7 @@ class MlpD8(nn.Module):
         return (type(self.act) is TritonGeluD8 and isinstance(self.norm, nn.Identity)
                 and self.drop1.dropout.p == 0.0 and self.drop2.dropout.p == 0.0)
 
+    @OF.opaque_to_compile
     def forward(self, xs):
         xs = self.fc1(xs)
         xs = self.act(xs)
@@ -293,6 +297,7 @@ class AttentionD8(nn.Module):
             o = OF.AttentionFn.apply(_rows(qkv), B, N, H, D // H, OF.ops.ATTN_OCTIC_PACKED)
         return o.view(B, N, D)
 
+    @OF.opaque_to_compile
     def forward(self, xs):
         x = OF.pack_five(xs)
         OF.require_cuda(x)
@@ -350,6 +355,7 @@ class _OcticBlockBase(nn.Module):
         h = self.mlp.act.forward_packed(h)
         return _branch_residual(self.mlp.fc2, h, ls2, x, s2)
 
+    @OF.opaque_to_compile
     def forward(self, xs):
         x = OF.pack_five(xs)
         OF.require_cuda(x)
@@ -437,6 +443,7 @@ class NestedTensorBlockD8(BlockD8):
     def forward_nested(self, x_list: List[Tuple[Tensor]]) -> List[Tuple[Tensor]]:
         return [super(NestedTensorBlockD8, self).forward(x) for x in x_list]
 
+    @OF.opaque_to_compile
     def forward(self, x_or_x_list):
         if isinstance(x_or_x_list, tuple):
             return super().forward(x_or_x_list)
@@ -458,6 +465,7 @@ class PowerSpectrumInvariant(nn.Module):
         super().__init__()
         self.output_dim = 6 * C // 8
 
+    @OF.opaque_to_compile
     def forward(self, xtuple):
         x = OF.pack_five(tuple(xtuple))
         OF.require_cuda(x)
@@ -596,6 +604,7 @@ class PatchEmbedD8(nn.Module):
                                         (npatch, lead, lead) if lead else (0, 0, 0))
         return out.view(tokens.shape)
 
+    @OF.opaque_to_compile
     def forward(self, x):
         OF.require_cuda(x)
         self._check(x)
@@ -690,6 +699,7 @@ class Attention(nn.Module):
         qkv = OF.LinearFn.apply(_as_bf16(_rows(x)), self.qkv.weight, self.qkv.bias, False, False)
         return OF.AttentionFn.apply(qkv, B, N, self.num_heads, D // self.num_heads, OF.ops.ATTN_DENSE).view(B, N, D)
 
+    @OF.opaque_to_compile
     def forward(self, x):
         OF.require_cuda(x)
         B, N, D = x.shape
@@ -719,6 +729,7 @@ class Mlp(nn.Module):
     def hidden_packed(self, x: Tensor) -> Tensor:
         return OF.LinearFn.apply(_as_bf16(_rows(x)), self.fc1.weight, self.fc1.bias, True, False)
 
+    @OF.opaque_to_compile
     def forward(self, x):
         OF.require_cuda(x)
         h = self.hidden_packed(x)
@@ -739,6 +750,7 @@ class _DenseBlockBase(nn.Module):
         s2 = self._dp(2).sample(batch, device) if isinstance(self._dp(2), DropPathD8) else None
         return s1, s2
 
+    @OF.opaque_to_compile
     def forward(self, x, nested: bool = False):
         """fp32 [B, N, D] -> fp32 [B, N, D]; 7 kernels: LN, qkv, attention, proj+ls+dp+res, LN, fc1+GELU, fc2+ls+dp+res.
         `nested`: the input is one element of a crop list (only the DINOv2 block's stochastic-depth rule cares)."""

@@ -159,7 +159,9 @@ class OcticVisionTransformer(nn.Module):
                 t = OF.pack_five(blk(OF.unpack_five(t)))
         return t
 
+    @OF.opaque_to_compile
     def forward_features(self, x):
+        OF.check_autocast()
         t = self.forward_trunk_packed(x)
         B, N, D = t.shape
         if self.invariant:
@@ -179,6 +181,7 @@ class OcticVisionTransformer(nn.Module):
         cls = t[:, 0]
         return OF.LayerNormFn.apply(cls, self.norm.weight, self.norm.bias, self.norm.eps, False, False)
 
+    @OF.opaque_to_compile
     def forward(self, x):
         x = self.forward_features(x)
         if self.dropout_rate:

@@ -412,8 +412,25 @@ def test_headline_model_equivariance_report(capsys):
                     worst_rel = max(worst_rel, rel_err(a, b))
                     worst_abs = max(worst_abs, float((a.float() - b).abs().max()))
         report[f"trunk_equivariance_{tag}"] = {"rel_l2_max_over_group": worst_rel, "max_abs": worst_abs, "max_abs_of_output": scale}
+        # the REFERENCE's own level at the same dtype (last row): the oracle restatement of the
+        # reference path under bf16 autocast, same weights, same images, on the host
+        sd = {k: v.detach().cpu() for k, v in hyb.state_dict().items()}
         del hyb
+        icpu = img.cpu()
+        ref_rel, ref_abs = 0.0, 0.0
+        with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+            rbase = tuple(t.float() for t in O.octic_vit_forward(icpu, sd, patch=14, depth=32, num_heads=16, return_trunk=True))
+            for g in O.GROUP:
+                moved = O.octic_vit_forward(O.image_action(g, icpu).contiguous(), sd, patch=14, depth=32, num_heads=16,
+                                            return_trunk=True)
+                want = O.token_action(g, rbase, has_cls=True)
+                for a, b in zip(moved, want):
+                    ref_rel = max(ref_rel, rel_err(a, b))
+                    ref_abs = max(ref_abs, float((a.float() - b).abs().max()))
+        report[f"trunk_equivariance_{tag}"].update({"reference_bf16_rel_l2": ref_rel, "reference_bf16_max_abs": ref_abs})
         assert worst_rel < 2e-2, report
+        # "must stay at the reference's level": within 2x of what the reference's own bf16 arithmetic gives
+        assert worst_rel <= 2.0 * ref_rel + 1e-5, report
     inv = OcticVisionTransformer(img_size=224, patch_size=14, embed_dim=1280, depth=32, num_heads=16, num_classes=1000,
                                  qkv_bias=True, invariant=True, standard_block_layers=L.Layer_scale_init_Block,
                                  octic_block_layers=L.Layer_scale_init_BlockD8).to(DEV).eval()
