@@ -71,6 +71,7 @@ class OcticVisionTransformer(nn.Module):
         # optional callable applied (as a tensor hook) to the gradient that flows from the dense half into the octic
         # half: parallel.install_early_allreduce starts the gradient exchange of the dense half there
         self._bridge_grad_hook = None
+        self._block_grad_hooks = {}      # block index -> hook on the gradient flowing into that block (more exchange buckets)
         if num_register_tokens > 0 and type(self) is OcticVisionTransformer:
             # the reference's base-class register path indexes range(8) over a 5-tuple and cannot run
             # (SURVEY.md Appendix A.5); only the DINOv2 subclass (dinov2_models.py) supports registers.
@@ -152,7 +153,9 @@ class OcticVisionTransformer(nn.Module):
         """octic half (reference model.py:172-194) -> fp32 packed [B, N, D]"""
         OF.require_cuda(x)
         t = self.embed_tokens_packed(x)
-        for blk in self.blocks[:self.octic_equi_break_layer]:
+        for i, blk in enumerate(self.blocks[:self.octic_equi_break_layer]):
+            if i in self._block_grad_hooks and t.requires_grad:
+                t.register_hook(self._block_grad_hooks[i])
             if hasattr(blk, "forward_packed"):
                 t = blk.forward_packed(t)
             else:
@@ -172,7 +175,9 @@ class OcticVisionTransformer(nn.Module):
             t = OF.BridgeFn.apply(_rows(t)).view(B, N, D)
         if self._bridge_grad_hook is not None and t.requires_grad:
             t.register_hook(self._bridge_grad_hook)
-        for blk in self.blocks[self.octic_equi_break_layer:]:
+        for i, blk in enumerate(self.blocks[self.octic_equi_break_layer:], start=self.octic_equi_break_layer):
+            if i in self._block_grad_hooks and i != self.octic_equi_break_layer and t.requires_grad:
+                t.register_hook(self._block_grad_hooks[i])
             t = blk(t)
         if self.global_pool:
             t = OF.LayerNormFn.apply(_rows(t), self.norm.weight, self.norm.bias, self.norm.eps, False, False)

@@ -48,8 +48,13 @@ class FlatGrads:
             from . import functional as OF
             for p in self.params:
                 setattr(p, OF.ACCUMULATE_ATTR, True)
-        self.split = self.flat.numel()      # flat[split:] = gradients that are final early in backward (none by default)
+        # early exchange: bounds = descending offsets o_0 > o_1 > ...; bucket i = flat[o_i : o_(i-1)] (bucket 0 runs to the end)
+        # is final -- and is all-reduced on the communication stream -- once backward has passed hook i.  split = the
+        # lowest bound: flat[:split] is what remains for all_reduce() after backward.
+        self.bounds: List[int] = []
+        self.split = self.flat.numel()
         self._early_done = False
+        self._early_n = 0
         self._comm_stream = None
 
     def close(self) -> None:
@@ -67,6 +72,7 @@ class FlatGrads:
         """zero the buffer and forget any early all-reduce of the previous step"""
         self.flat.zero_()
         self._early_done = False
+        self._early_n = 0
 
     @staticmethod
     def _reduce(t: torch.Tensor, average: bool) -> None:
@@ -84,35 +90,49 @@ class FlatGrads:
         return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
     # ---- overlap of the exchange with backward -------------------------------------------------------------------
+    def offset_of(self, p: torch.nn.Parameter) -> int:
+        for q, o in zip(self.params, self.offsets):
+            if q is p:
+                return o
+        raise ValueError("parameter is not in this buffer")
+
     def mark_early_from(self, first: torch.nn.Parameter) -> None:
         """Declare that the gradients of `first` and of every parameter after it in the buffer are final once the
         backward pass has passed a known point (for the hybrid ViT: the bridge between the dense and the octic half --
-        blocks[k:], norm and head sit at the end of model.parameters() and their backward runs first)."""
-        for p, o in zip(self.params, self.offsets):
-            if p is first:
-                self.split = o
-                return
-        raise ValueError("parameter is not in this buffer")
+        blocks[k:], norm and head sit at the end of model.parameters() and their backward runs first).  Calling it again
+        with a parameter further to the front adds another, later bucket."""
+        o = self.offset_of(first)
+        if self.bounds and o >= self.bounds[-1]:
+            raise ValueError("early buckets must be declared back to front")
+        self.bounds.append(o)
+        self.split = o
+
+    def clear_early(self) -> None:
+        self.bounds, self.split, self._early_done, self._early_n = [], self.flat.numel(), False, 0
 
     def all_reduce_early(self, average: bool = True) -> None:
-        """All-reduce flat[split:] on a communication stream that forks from the current stream here; the rest of
-        backward keeps running on the current stream.  Called from an autograd hook (install_early_allreduce)."""
-        if self._early_done or self.split >= self.flat.numel() or not self._distributed():
+        """All-reduce the next early bucket on a communication stream that forks from the current stream here; the rest
+        of backward keeps running on the current stream.  Called from autograd hooks (install_early_allreduce), once per
+        declared bound and in their order."""
+        if self._early_n >= len(self.bounds) or not self._distributed():
             return
-        tail = self.flat[self.split:]
-        if tail.is_cuda:
+        lo = self.bounds[self._early_n]
+        hi = self.bounds[self._early_n - 1] if self._early_n > 0 else self.flat.numel()
+        part = self.flat[lo:hi]
+        if part.is_cuda:
             if self._comm_stream is None:
-                self._comm_stream = torch.cuda.Stream(device=tail.device)
-            cur = torch.cuda.current_stream(tail.device)
+                self._comm_stream = torch.cuda.Stream(device=part.device)
+            cur = torch.cuda.current_stream(part.device)
             self._comm_stream.wait_stream(cur)
             with torch.cuda.stream(self._comm_stream):
-                self._reduce(tail, average)
+                self._reduce(part, average)
         else:
-            self._reduce(tail, average)
+            self._reduce(part, average)
+        self._early_n += 1
         self._early_done = True
 
     def join_early(self, force: bool = False) -> None:
-        """Make the current stream wait for the early all-reduce (must run before a CUDA-graph capture ends).
+        """Make the current stream wait for the early all-reduces (must run before a CUDA-graph capture ends).
         `force`: the caller knows an early all-reduce ran (e.g. inside a replayed graph) although the per-step flag
         has already been cleared."""
         if (self._early_done or force) and self._comm_stream is not None:
@@ -120,15 +140,15 @@ class FlatGrads:
 
     def all_reduce(self, average: bool = True, early_done: Optional[bool] = None) -> None:
         """Mean (or sum) over ranks of every gradient not yet reduced by all_reduce_early() in this step.
-        `early_done` overrides the per-step flag (a CUDA-graph replay re-runs the captured early all-reduce without
+        `early_done` overrides the per-step state (a CUDA-graph replay re-runs ALL captured early all-reduces without
         passing through Python)."""
-        done = self._early_done if early_done is None else early_done
-        self._early_done = False
+        n = self._early_n if early_done is None else (len(self.bounds) if early_done else 0)
+        self._early_done, self._early_n = False, 0
         if not self._distributed():
             return
-        if done:
+        if n > 0:
             self.join_early(force=True)     # the flag above is already cleared: the wait must not depend on it
-            self._reduce(self.flat[:self.split], average)
+            self._reduce(self.flat[:self.bounds[n - 1]], average)
         else:
             self._reduce(self.flat, average)
 
@@ -136,32 +156,56 @@ class FlatGrads:
         return self.flat.numel() * 4
 
 
-def install_early_allreduce(model: torch.nn.Module, fg: FlatGrads) -> bool:
-    """Overlap the gradient exchange with backward for OcticVisionTransformer-style models: the model calls
-    `model._bridge_grad_hook` on the gradient that flows from the dense half into the octic half; at that point the
-    gradients of blocks[k:], norm and head are final, and their all-reduce (88 % of the bytes for the hybrid ViT-H/14)
-    runs on a side stream while the octic half is still in backward.  Returns False (and installs nothing) when the
-    model has no such hook point or the parameter order does not allow it."""
+def install_early_allreduce(model: torch.nn.Module, fg: FlatGrads, boundaries: Optional[List[int]] = None) -> bool:
+    """Overlap the gradient exchange with backward for OcticVisionTransformer-style models.  The model calls
+    `model._bridge_grad_hook` on the gradient that flows from the dense half into the octic half (block k), and
+    `model._block_grad_hooks[i]` on the gradient that flows into block i; when hook i fires the gradients of blocks[i:],
+    norm and head are final, and the part of them not yet exchanged is all-reduced on a side stream while the blocks in
+    front are still in backward.  `boundaries` = block indices, default [k]: one bucket (88 % of the bytes of the hybrid
+    ViT-H/14) exchanged under the octic half's backward.  More buckets were measured and lost on 8 B200s
+    (profiles/r02_scaling_8gpu.txt: one all-reduce after the replay 137.8 ms per step, bridge bucket 136.1 ms, buckets
+    at blocks 24/16/8/2 137.5 ms): an exchange that starts under the dense half takes SMs from GEMMs that run at the
+    power cap.  Returns False (and installs nothing) when the model has no such hook points or the parameter order
+    does not allow it."""
     k = getattr(model, "octic_equi_break_layer", None)
     blocks = getattr(model, "blocks", None)
     if k is None or blocks is None or k >= len(blocks) or not hasattr(model, "_bridge_grad_hook"):
         return False
-    first = next((p for p in blocks[k].parameters() if p.requires_grad), None)
-    if first is None:
+    depth = len(blocks)
+    multi = hasattr(model, "_block_grad_hooks")
+    if boundaries is None:
+        boundaries = [k]
+    boundaries = sorted({b for b in boundaries if 0 < b < depth and (multi or b == k)}, reverse=True)
+    if k not in boundaries and not multi:
         return False
-    early_ok = {id(p) for b in blocks[k:] for p in b.parameters()}
+    tail_ok = set()
     for name in ("norm", "head"):
-        early_ok |= {id(p) for p in getattr(model, name, torch.nn.Identity()).parameters()}
-    fg.mark_early_from(first)
-    tail = [p for p, o in zip(fg.params, fg.offsets) if o >= fg.split]
-    if not all(id(p) in early_ok for p in tail):          # e.g. DINOv2 mask_token: registered last, used first
-        fg.split = fg.flat.numel()
+        tail_ok |= {id(p) for p in getattr(model, name, torch.nn.Identity()).parameters()}
+    fg.clear_early()
+    installed = []
+    for bi in boundaries:
+        first = next((p for p in blocks[bi].parameters() if p.requires_grad), None)
+        if first is None:
+            continue
+        ok = tail_ok | {id(p) for b in blocks[bi:] for p in b.parameters()}
+        off = fg.offset_of(first)
+        if not all(id(p) in ok for p, o in zip(fg.params, fg.offsets) if o >= off):   # e.g. DINOv2 mask_token: registered
+            continue                                                                  # last, used first
+        fg.mark_early_from(first)
+        installed.append(bi)
+    if not installed:
+        fg.clear_early()
         return False
 
     def hook(grad):
         fg.all_reduce_early()
         return grad
-    model._bridge_grad_hook = hook
+    if multi:
+        model._block_grad_hooks = {bi: hook for bi in installed if bi != k}
+    model._bridge_grad_hook = hook if k in installed else None
+    if k not in installed and not multi:
+        fg.clear_early()
+        return False
     return True
 
 
@@ -224,13 +268,13 @@ class GraphedTrainStep:
                     loss = self._eager()
                 # a replay re-runs whatever early all-reduce the capture recorded (NCCL inside the graph)
                 self.early_in_graph = self.fg._early_done
-                self.fg._early_done = False
+                self.fg._early_done, self.fg._early_n = False, 0
                 self.graph, self.loss, self.graphed = graph, loss, True
                 break
             except Exception as e:                        # noqa: BLE001 - any capture failure -> eager path, reported
                 self.capture_error = repr(e)
                 torch.cuda.synchronize(dev)
-                self.fg._early_done = False
+                self.fg._early_done, self.fg._early_n = False, 0
                 # Kernels issued during a failed capture were only RECORDED: the bf16 weight packs allocated in this
                 # attempt hold uninitialised memory although their cache keys look valid, the zero pool was handed out
                 # without being cleared and an autograd hand-off may be parked.  Drop all of it before the retry / the
@@ -250,9 +294,12 @@ class GraphedTrainStep:
                     torch.cuda.synchronize(dev)
                 except Exception:                         # noqa: BLE001 - best effort
                     pass
-                if attempt == 0 and getattr(model, "_bridge_grad_hook", None) is not None:
+                if attempt == 0 and (getattr(model, "_bridge_grad_hook", None) is not None
+                                     or getattr(model, "_block_grad_hooks", None)):
                     model._bridge_grad_hook = None        # retry without the in-graph exchange
-                    self.fg.split = self.fg.flat.numel()
+                    if hasattr(model, "_block_grad_hooks"):
+                        model._block_grad_hooks = {}
+                    self.fg.clear_early()
                     continue
                 break
 

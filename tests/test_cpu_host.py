@@ -329,6 +329,55 @@ ref2 = Toy(late_param_last=True); ref2.load_state_dict(m2.state_dict())
 ref2(data).square().sum().backward()
 for (n, p), q in zip(m2.named_parameters(), ref2.parameters()):
     assert torch.allclose(p.grad, q.grad / 2, atol=1e-5), n
+
+
+class ToyMulti(Toy):
+    # OcticVisionTransformer also calls per-block hooks: several exchange buckets, issued back to front during backward
+    def __init__(self):
+        super().__init__()
+        self._block_grad_hooks = {}
+
+    def forward(self, x):
+        t = self.embed(x)
+        for i, b in enumerate(self.blocks):
+            if i == 2 and self._bridge_grad_hook is not None and t.requires_grad:
+                t.register_hook(self._bridge_grad_hook)
+            elif i in self._block_grad_hooks and t.requires_grad:
+                t.register_hook(self._block_grad_hooks[i])
+            t = torch.tanh(b(t))
+        return self.head(self.norm(t))
+
+
+m3, ref3 = ToyMulti(), ToyMulti()
+ref3.load_state_dict(m3.state_dict())
+fg3 = FlatGrads(m3.parameters(), fuse_accumulation=False)
+assert install_early_allreduce(m3, fg3, boundaries=[3, 2, 1])
+n3 = [n for n, _ in m3.named_parameters()]
+assert fg3.bounds == [fg3.offsets[n3.index(f"blocks.{i}.weight")] for i in (3, 2, 1)] and fg3.split == fg3.bounds[-1]
+assert sorted(m3._block_grad_hooks) == [1, 3] and m3._bridge_grad_hook is not None
+spans = []
+orig3 = fg3._reduce
+fg3._reduce = lambda t, avg: (spans.append((t.storage_offset(), t.numel())), orig3(t, avg))
+for step in range(2):
+    fg3.begin_step()
+    m3(data[a:b]).square().sum().backward()
+    assert fg3._early_n == 3
+    fg3.all_reduce()
+    assert fg3._early_n == 0
+    ref3.zero_grad()
+    ref3(data).square().sum().backward()
+    for (n, p), q in zip(m3.named_parameters(), ref3.parameters()):
+        assert torch.allclose(p.grad, q.grad / 2, atol=1e-5), (step, n)
+# four disjoint spans per step that tile the buffer back to front: [b3, end), [b2, b3), [b1, b2), [0, b1)
+b3, b2, b1 = fg3.bounds
+want = [(b3, fg3.flat.numel() - b3), (b2, b3 - b2), (b1, b2 - b1), (0, b1)]
+assert spans == want + want, spans
+# a step in which backward stops early (only some hooks fire) still reduces every element exactly once
+fg3.begin_step(); spans.clear()
+fg3._early_n = 0
+fg3.all_reduce_early()                  # bucket 0 only
+fg3.all_reduce()
+assert spans == [(b3, fg3.flat.numel() - b3), (0, b3)], spans
 dist.barrier(); dist.destroy_process_group()
 print("ok", rank)
 """
