@@ -1,12 +1,23 @@
 // extern "C" entry points of liboctic_b200.so that are thin glue: error strings, device probe, the generic
 // grouped GEMM, and the LinearD8 / nn.Linear wrappers that turn reference-level arguments into GEMM groups.
 #include "octic_capi_internal.h"
+#include <stdlib.h>
 
 namespace octic {
 
 int pick_block_n(const int* ns, int count) {
   int maxn = 0;
   for (int i = 0; i < count; ++i) maxn = ns[i] > maxn ? ns[i] : maxn;
+  {
+    // OCTIC_BLOCK_N=n forces the N tile of the grouped (LinearD8) launches: tile-shape experiments (ragged last tiles
+    // are handled by the kernels)
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("OCTIC_BLOCK_N");
+      forced = e != nullptr ? atoi(e) : 0;
+    }
+    if (forced >= 32 && forced <= 256 && forced % 16 == 0) return forced;
+  }
   for (int bn = 256; bn >= 16; bn -= 16) {
     bool ok = true;
     for (int i = 0; i < count; ++i) ok = ok && (ns[i] % bn == 0);
@@ -155,6 +166,20 @@ static void fill_d8_groups(octic_gemm_desc* d, int Ci, int Co, bool has_bias) {
   }
 }
 
+// N-tile width of a LinearD8 launch (Co output channels per 1-D irrep, Ci input channels).  Measured on B200 at the
+// ViT-H/14 shapes (tools/gpu/r2_u.sh, profiles/r02_gemm_block_n.txt): wide outputs with a short contraction (qkv, fc1 and
+// the fc2 dgrad: K = 160 / 320) are bound by operand traffic per tile and want the largest tile, 256 columns, even with a
+// ragged last tile (fc1 126 -> 116 us, fc2 dgrad 127 -> 116, qkv 100 -> 90); the head-major scatter epilogue is bound by
+// its own latency per warp and wants 128 columns = one 32-column chunk per epilogue warp (qkv head-major 232 -> 175 us);
+// everything else keeps the largest exact divisor (proj / fc2 + residual and the long-K dgrads lose with ragged tiles).
+static int pick_block_n_d8(int Co, int Ci, bool head_major) {
+  const int ns[2] = {Co, 2 * Co};
+  const int exact = pick_block_n(ns, 2);
+  if (getenv("OCTIC_BLOCK_N") != nullptr) return exact;       // forced (pick_block_n honours it)
+  if (Co >= 480 && Ci <= 160) return head_major ? 128 : 256;
+  return exact;
+}
+
 int octic_linear_d8_fwd(const void* x, int T, int Din, int Dout, const void* w1d, const void* wE_packed,
                         const float* bias, const octic_gemm_desc* epi, void* stream) {
   if (!x || !w1d || !wE_packed || !epi || Din % 8 || Dout % 8) return OCTIC_ERR_ARG;
@@ -165,8 +190,7 @@ int octic_linear_d8_fwd(const void* x, int T, int Din, int Dout, const void* w1d
   d.b1 = wE_packed; d.b1_rows = 2L * Co; d.b1_cols = roundup64(2 * Ci); d.b1_ld = roundup64(2 * Ci);
   d.bias = bias;
   fill_d8_groups(&d, Ci, Co, bias != nullptr);
-  const int ns[2] = {Co, 2 * Co};
-  d.block_n = pick_block_n(ns, 2);
+  d.block_n = pick_block_n_d8(Co, Ci, d.head_H > 0);
   return launch_gemm_tn(&d, static_cast<cudaStream_t>(stream));
 }
 
@@ -184,8 +208,7 @@ int octic_linear_d8_dgrad(const void* dy, int T, int Din, int Dout, const void* 
   d.head_H = head_H;
   d.head_S = 1;
   fill_d8_groups(&d, Co, Ci, false);
-  const int ns[2] = {Ci, 2 * Ci};
-  d.block_n = pick_block_n(ns, 2);
+  d.block_n = pick_block_n_d8(Ci, Co, head_H > 0);
   d.mode = OCTIC_EPI_BF16;
   d.out = dx; d.ldo = Din;
   return launch_gemm_tn(&d, static_cast<cudaStream_t>(stream));

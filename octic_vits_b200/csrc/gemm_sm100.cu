@@ -116,6 +116,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // Warp roles: producer 0 / MMA 1 / epilogue 2-17 (p.roles_low, the default) or producer 16 / MMA 17 / epilogue 0-15
+  // (experiment switch, see roles_low_env).
+  const int prod_warp = p.roles_low ? 0 : kEpiWarps, mma_warp = p.roles_low ? 1 : kEpiWarps + 1;
   const int stages = p.num_stages;
   const int b_rows = p.block_n / NCTA;                    // B rows held by this CTA
   const int b_stage_bytes = b_rows * kBlockK * 2;
@@ -138,7 +141,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* wfull_bar = reinterpret_cast<uint64_t*>(tmem_ptr + 4);   // weight tile landed (leader's barrier)
   uint64_t* wempty_bar = wfull_bar + 1;                              // every MMA that reads the weight tile has completed
 
-  if (warp == 0 && lane == 0) {
+  if (warp == prod_warp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB0);
     tma_prefetch_desc(&tmB1);
@@ -154,7 +157,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(wempty_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == mma_warp) {
     if (NCTA == 2) tmem_alloc_pair(tmem_ptr, kTmemCols);
     else tmem_alloc(tmem_ptr, kTmemCols);
   }
@@ -183,7 +186,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     n_blk = j - p.g[g].tile_begin;
   };
 
-  if (warp == 0) {
+  if (warp == prod_warp) {
     // ------------------------------------------ TMA producer ------------------------------------------
     if (lane == 0) {
       int stage = 0;
@@ -228,7 +231,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == mma_warp) {
     // -------------------------------------------- MMA issuer --------------------------------------------
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc_bf16(kBlockM * NCTA, p.block_n, 0, 0);
@@ -286,7 +289,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // 32-column chunk (the epilogue is latency bound per warp: more warps, not more work per warp, keep it ahead of
     // the tensor pipe).
     // A chunk goes TMEM -> registers (thread = row) -> per-warp smem transpose -> coalesced global I/O (lane = column).
-    const int ew = warp - 2;
+    const int ew = p.roles_low ? warp - 2 : warp;
     const int q = warp & 3;
     const int half = ew >> 2;                  // 0..3: first chunk of this warp
     constexpr int kChunkStep = 32 * (kEpiWarps / 4);
@@ -320,14 +323,47 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // round trip per 8 rows (ncu: 22 % of the stall samples on the FFMAs that consume the loads).  Staged path:
     // lane = column, res[rr] = row rr (res_ok is warp-uniform); direct path: thread = row, res[] = its 32 columns.
     float res[32];
-    bool res_ok = false;
+    bool res_ok = false, res_packed = false;
+    // Packed epilogue (every full, aligned 32 x 32 chunk of the bf16-valued modes; see process_packed): the chunk is
+    // converted to bf16 BEFORE the shared-memory transpose.  ptrs_packed = the launch-wide part of the condition.
+    const bool ptrs_packed =
+        p.packed != 0 && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 &&
+        (MODE == EPI_BF16 ? p.head_H == 0 && (p.ldo & 7) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0
+         : MODE == EPI_GELU_BF16
+             ? (p.ldo & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.out) | reinterpret_cast<uintptr_t>(p.branch_out)) & 15) == 0
+             : MODE == EPI_RESID
+                   ? p.remap_group == 0 && (p.ldr & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(p.resid_out) | reinterpret_cast<uintptr_t>(p.resid_in) |
+                           reinterpret_cast<uintptr_t>(p.gamma) | reinterpret_cast<uintptr_t>(p.branch_out)) & 15) == 0 &&
+                         (p.branch_out == nullptr || (p.ldb & 7) == 0)
+                   : false);
+    auto packed_ok = [&](const GemmGroup& G_, int n0_, int c0_, int row0_) {
+      return ptrs_packed && row0_ + 32 <= p.M && c0_ + 32 <= min(p.block_n, G_.n - n0_) && ((G_.c_col + n0_ + c0_) & 7) == 0 &&
+             (G_.bias_off < 0 || ((G_.bias_off + n0_ + c0_) & 3) == 0);
+    };
     auto prefetch_resid = [&](int tile_, int c0_) {
       res_ok = false;
+      res_packed = false;
       if (MODE != EPI_RESID || p.resid_in == nullptr || tile_ >= tile_last) return;
       int mb_, g_, nb_;
       decode(tile_, mb_, g_, nb_);
       const GemmGroup& G_ = p.g[g_];
       const int n0_ = nb_ * p.block_n, row_ = mb_ * kBlockM + q * 32 + lane;
+      if (packed_ok(G_, n0_, c0_, mb_ * kBlockM + q * 32)) {
+        // packed layout: lane = (row lane >> 2 of each 8-row pass, 8 columns (lane & 3) * 8 ..): 32 bytes per pass
+        const float* rin_ = p.resid_in + static_cast<long>(mb_ * kBlockM + q * 32 + (lane >> 2)) * p.ldr + G_.c_col + n0_ + c0_ +
+                            (lane & 3) * 8;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float4 t0 = *reinterpret_cast<const float4*>(rin_ + static_cast<long>(h) * 8 * p.ldr);
+          const float4 t1 = *reinterpret_cast<const float4*>(rin_ + static_cast<long>(h) * 8 * p.ldr + 4);
+          res[8 * h] = t0.x; res[8 * h + 1] = t0.y; res[8 * h + 2] = t0.z; res[8 * h + 3] = t0.w;
+          res[8 * h + 4] = t1.x; res[8 * h + 5] = t1.y; res[8 * h + 6] = t1.z; res[8 * h + 7] = t1.w;
+        }
+        res_ok = true;
+        res_packed = true;
+        return;
+      }
       if (!direct_ok(G_, n0_, c0_)) {
         const int row0_ = mb_ * kBlockM + q * 32;
         if (p.remap_group != 0 || c0_ + 32 > min(p.block_n, G_.n - n0_) || row0_ + 32 > p.M) return;
@@ -362,6 +398,113 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
       const bool has_bias = p.bias != nullptr && G.bias_off >= 0;
 
+      // Packed path.  ncu (profiles/r02_ncu_summary.md): the small-K launches are bound by SHARED-MEMORY bandwidth, and
+      // half of the traffic is this epilogue's fp32 transpose (8 STS.128 + 8 LDS.128 per lane and chunk, 24 % of the
+      // wavefronts bank-conflict replays).  Everything that is per element and needs no neighbour -- bias, the bf16
+      // rounding of the Linear output, the GELU -- is therefore done while the thread still holds its ROW, and only
+      // the bf16 result (64 B per row) goes through shared memory: 4 STS.128 + 4 LDS.128, conflict free with the
+      // 16-byte pieces of row r stored at piece ^ (r >> 1).  After the transpose a lane owns 8 columns of 4 rows and
+      // does the global I/O (bf16 stores; fp32 residual read-modify-write with gamma and the DropPath factor).
+      auto process_packed = [&](const uint32_t (&r)[32], int c0) {
+        const int ocol0 = G.c_col + n0 + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (has_bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + G.bias_off + n0 + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(bp + j);
+            v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+          }
+        }
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        const uint32_t wr = stg + lane * 64, sw = static_cast<uint32_t>(lane >> 1);
+        const int rsub = lane >> 2, cq = lane & 3;
+        const uint32_t rd = stg + rsub * 64 + (((cq ^ (rsub >> 1)) & 3) << 4);      // + pass * 512: (row >> 1) & 3 = (rsub >> 1) & 3
+        const long orow = row0 + rsub;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) sts_v4(wr + (((j ^ sw) & 3) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        __syncwarp();
+        if (MODE == EPI_GELU_BF16) {
+          // the staged tile is the bf16 pre-activation (what the reference's Linear emits under autocast): write it out
+          // for backward, then stage gelu(pre) the same way
+          if (p.branch_out != nullptr) {
+            __nv_bfloat16* pre = reinterpret_cast<__nv_bfloat16*>(p.branch_out) + orow * p.ldo + ocol0 + cq * 8;
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const float4 t = lds_v4(rd + h * 512);
+              *reinterpret_cast<float4*>(pre + static_cast<long>(h) * 8 * p.ldo) = t;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+            float g0, g1;
+            gelu_pair(hf.x, hf.y, g0, g1);
+            w[j] = pack_bf16x2(g0, g1);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sts_v4(wr + (((j ^ sw) & 3) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          __syncwarp();
+        }
+        if (MODE == EPI_BF16 || MODE == EPI_GELU_BF16) {
+          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + ocol0 + cq * 8;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const float4 t = lds_v4(rd + h * 512);
+            *reinterpret_cast<float4*>(outp + static_cast<long>(h) * 8 * p.ldo) = t;
+          }
+        } else {
+          // EPI_RESID: out = resid + DropPath factor * gamma * bf16(acc + bias)
+          const int ocol = ocol0 + cq * 8;
+          float gm[8];
+          if (p.gamma != nullptr) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.gamma + ocol));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.gamma + ocol + 4));
+            gm[0] = g0.x; gm[1] = g0.y; gm[2] = g0.z; gm[3] = g0.w; gm[4] = g1.x; gm[5] = g1.y; gm[6] = g1.z; gm[7] = g1.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) gm[i] = 1.f;
+          }
+          const bool have_res = res_ok && res_packed;
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const long grow = orow + h * 8;
+            const float4 t = lds_v4(rd + h * 512);
+            if (p.branch_out != nullptr)
+              *reinterpret_cast<float4*>(reinterpret_cast<__nv_bfloat16*>(p.branch_out) + grow * p.ldb + ocol) = t;
+            const float sc = p.row_scale != nullptr ? __ldg(p.row_scale + grow / p.rows_per_sample) : 1.f;
+            float base[8];
+            if (have_res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) base[i] = res[8 * h + i];
+            } else if (p.resid_in != nullptr) {
+              const float4 b0 = *reinterpret_cast<const float4*>(p.resid_in + grow * p.ldr + ocol);
+              const float4 b1 = *reinterpret_cast<const float4*>(p.resid_in + grow * p.ldr + ocol + 4);
+              base[0] = b0.x; base[1] = b0.y; base[2] = b0.z; base[3] = b0.w; base[4] = b1.x; base[5] = b1.y; base[6] = b1.z; base[7] = b1.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) base[i] = 0.f;
+            }
+            const uint32_t tw[4] = {__float_as_uint(t.x), __float_as_uint(t.y), __float_as_uint(t.z), __float_as_uint(t.w)};
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&tw[i]));
+              o[2 * i] = fmaf(sc * gm[2 * i], f.x, base[2 * i]);
+              o[2 * i + 1] = fmaf(sc * gm[2 * i + 1], f.y, base[2 * i + 1]);
+            }
+            float* ro = p.resid_out + grow * p.ldr + ocol;
+            *reinterpret_cast<float4*>(ro) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(ro + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        __syncwarp();
+      };
       // Direct path: one 32-column chunk, thread = row, global I/O from registers (see above).
       auto process_direct = [&](const uint32_t (&r)[32], int c0) {
         const int row = row0 + lane;
@@ -709,7 +852,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int r8 = 0; r8 < 32; r8 += 8) {
                 float base[8];
                 // all loads of a batch before its stores (resid_in may alias resid_out)
-                if (res_ok) {
+                if (res_ok && !res_packed) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) base[i] = res[r8 + i];
                 } else {
@@ -769,7 +912,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_32x32(t_addr + c0, ra);
           tmem_ld_wait();
           // (res[] is consumed inside) then fetch the residual rows of the next chunk
-          if (direct_ok(G, n0, c0)) process_direct(ra, c0);
+          if (packed_ok(G, n0, c0, row0)) process_packed(ra, c0);
+          else if (direct_ok(G, n0, c0)) process_direct(ra, c0);
           else process_chunk(ra, c0);
           if (c0 + kChunkStep < n_valid) prefetch_resid(tile, c0 + kChunkStep);
           else prefetch_resid(tile + tile_step, half * 32);
@@ -780,7 +924,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int c0 = half * 32; c0 < n_valid; c0 += kChunkStep) {
           tmem_ld_32x32(t_addr + c0, ra);
           tmem_ld_wait();
-          if (direct_ok(G, n0, c0)) process_direct(ra, c0);
+          if ((MODE == EPI_BF16 || MODE == EPI_GELU_BF16) && packed_ok(G, n0, c0, row0)) process_packed(ra, c0);
+          else if (direct_ok(G, n0, c0)) process_direct(ra, c0);
           else process_chunk(ra, c0);
         }
       }
@@ -796,7 +941,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all();
   else __syncthreads();
-  if (warp == 1) {
+  if (warp == mma_warp) {
     tc_fence_after();
     if (NCTA == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
@@ -814,6 +959,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // warp roles as in gemm_tn_kernel: epilogue warps 0-3, TMA producer 4, MMA issuer 5 (roles_low: producer 0, MMA 1, epilogue 2-5)
+  const int prod_warp = p.roles_low ? 0 : 4, mma_warp = p.roles_low ? 1 : 5;
   const int stages = p.num_stages;
   const int b_cols = p.block_n / NCTA;                    // X columns (N extent) held by this CTA: whole 64-wide atoms
   const int b_stage_bytes = b_cols * kBlockK * 2;
@@ -827,7 +974,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == prod_warp && lane == 0) {
     tma_prefetch_desc(&tmDY);
     tma_prefetch_desc(&tmX);
     for (int s = 0; s < stages; ++s) {
@@ -840,7 +987,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == mma_warp) {
     if (NCTA == 2) tmem_alloc_pair(tmem_ptr, kTmemCols);
     else tmem_alloc(tmem_ptr, kTmemCols);
   }
@@ -901,7 +1048,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   };
   const int n_atoms = b_cols / 64;
 
-  if (warp == 0) {
+  if (warp == prod_warp) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -929,7 +1076,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == mma_warp) {
     if (lane == 0 && rank == 0) {
       const uint32_t idesc = make_idesc_bf16(kBlockM * NCTA, p.block_n, 1, 1);
       int stage = 0;
@@ -969,7 +1116,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
   } else {
     const int q = warp & 3;
-    float* stg = reinterpret_cast<float*>(smem + L.stg_off) + (warp - 2) * kStagingWords;
+    float* stg = reinterpret_cast<float*>(smem + L.stg_off) + (p.roles_low ? warp - 2 : warp) * kStagingWords;
     int it = 0;
     int round = 0, g, m_t, n_t, kb0, kb1;
     long u = r_begin;
@@ -1029,7 +1176,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all();
   else __syncthreads();
-  if (warp == 1) {
+  if (warp == mma_warp) {
     tc_fence_after();
     if (NCTA == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
     else tmem_dealloc(tmem_base, kTmemCols);
@@ -1081,6 +1228,17 @@ static int num_sms() {
 }
 
 constexpr int kMaxDynSmem = 232448;   // 227 KiB
+// Warp-role order.  Default: TMA producer / MMA issuer on warps 0 / 1.  OCTIC_GEMM_ROLES_HIGH=1 moves them to the two
+// highest warp ids (the issue arbiter is said to prefer high warp ids); measured on B200 it is neutral to worse
+// (profiles/r02_gemm_warp_roles.txt: fc2-dgrad + GELU' 420 vs 394 us, dense fc1 dgrad 333 vs 313), so it stays a switch.
+static int roles_low_env() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("OCTIC_GEMM_ROLES_HIGH");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v;
+}
 // Measured on B200 (tools/gpu_s5_e.sh, profiles/r01_gemm_epilogue_policy_s5.txt): the register-direct epilogue issues
 // one 16-byte access per lane to 32 different lines and is bound by L1 line transactions; the staged (coalesced) path
 // wins for every mode, so direct is off by default and kept only as an experiment switch.
@@ -1145,6 +1303,15 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
     direct_mask = e != nullptr ? atoi(e) : kDefaultDirectMask;
   }
   p.direct = (direct_mask >> d->mode) & 1;
+  p.roles_low = roles_low_env();
+  {
+    static int packed_env = -1;     // OCTIC_GEMM_PACKED=0: fp32-staged epilogue everywhere (A/B measurements)
+    if (packed_env < 0) {
+      const char* e = getenv("OCTIC_GEMM_PACKED");
+      packed_env = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    p.packed = packed_env;
+  }
   // Pairs pay off when the tile's MMA time dominates (dense layers, K >= 512) or the epilogue is the slow head-major
   // scatter; the irrep groups with K = 160 / 320 (3-5 k-blocks per tile) run faster as single CTAs (same measurement).
   int kmax = 0;
@@ -1163,8 +1330,13 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   const bool pairs_possible = d->block_n % 16 == 0 && d->block_n >= 32 && d->M > kBlockM && num_sms() >= 2;
   const bool want_ws = ws_env == 1 && forced_ncta != 1 && d->num_groups > 1 && kmax <= 320 && pairs_possible &&
                        d->remap_group == 0;
+  // round-2 re-measurement with the 256 / 128-column tile rule of pick_block_n_d8 (tools/gpu/r2_v.sh): wide bf16 outputs
+  // with K <= 320 and 256-column tiles gain 5-6 % as pairs (fc1 115 -> 109 us, fc2 dgrad 116 -> 109, qkv 89 -> 84); the
+  // head-major scatter epilogue stays on pairs and takes a 3-stage ring (176 -> 160 us; single CTAs 164, single CTAs with
+  // 3 stages 180).
+  const bool wide_small_k = d->num_groups > 1 && kmax <= 320 && d->block_n == 256 && d->head_H == 0 && d->mode == EPI_BF16;
   const bool want_pairs = want_ws || forced_ncta == 2 ||
-                          (forced_ncta != 1 && (d->num_groups == 1 || kmax >= 512 || d->head_H > 0));
+                          (forced_ncta != 1 && (d->num_groups == 1 || kmax >= 512 || d->head_H > 0 || wide_small_k));
   const int ncta = (want_pairs && pairs_possible) ? 2 : 1;
   p.num_m_blocks = (d->M + kBlockM * ncta - 1) / (kBlockM * ncta);
   int tiles = 0;
@@ -1217,7 +1389,11 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   // shallow ring: a producer that runs far ahead only competes with the epilogue's own global traffic (measured,
   // tools/gpu_s5_st.sh: qkv head-major 269 -> 214 us, octic proj + residual 152 -> 127 us at 2 stages; K >= 640 and the
   // plain epilogues want the deep ring).
-  if (stage_cap == 0 && !p.ws && (d->head_H > 0 || (d->mode == EPI_RESID && kmax <= 320)) && stages > 2) stages = 2;
+  if (stage_cap == 0 && !p.ws) {
+    if (d->mode == EPI_RESID && kmax <= 320 && stages > 2) stages = 2;
+    else if (d->head_H > 0 && stages > 3) stages = 3;
+    else if (d->mode == EPI_RESID && d->num_groups > 1 && stages > 4) stages = 4;     // fc2 + residual: 168 -> 158 us
+  }
   if (stages < 2) return OCTIC_ERR_ARG;
   p.num_stages = stages;
   p.mode = d->mode;
@@ -1330,6 +1506,7 @@ int launch_gemm_wgrad(const octic_wgrad_desc* d, cudaStream_t stream) {
   if (grid_l > (total_units + 3) / 4) grid_l = (total_units + 3) / 4;
   if (grid_l < 1) grid_l = 1;
   p.splits = d->splits;
+  p.roles_low = roles_low_env();
   {
     const int ncl = static_cast<int>(grid_l), rem = tiles % ncl;
     const int s_al = rem > 0 ? ncl / rem : 0;

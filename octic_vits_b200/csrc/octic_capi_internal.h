@@ -36,6 +36,8 @@ struct GemmParams {
   int direct;   // 1: full aligned chunks go registers -> global without the shared-memory transpose
   int ws;       // weight-stationary tile order (CTA pairs, small-K groups): see gemm_tn_kernel
   int ws_kb_max;
+  int packed;      // 1: bf16-packed epilogue staging where it applies (gemm_tn_kernel process_packed)
+  int roles_low;   // 1: TMA producer / MMA issuer on warps 0 / 1 (round-1 order) instead of the two highest warp ids
 };
 
 struct WgradGroup {
@@ -44,7 +46,7 @@ struct WgradGroup {
   long ldw;
 };
 struct WgradParams {
-  int T, num_groups, block_n, total_tiles, splits, num_stages, rem_splits;
+  int T, num_groups, block_n, total_tiles, splits, num_stages, rem_splits, roles_low;
   WgradGroup g[OCTIC_MAX_GROUPS];
 };
 

@@ -3,6 +3,7 @@
 // 16-byte accesses; per-token reductions are warp-shuffle, column (parameter-gradient) reductions are
 // register accumulators + one red.add per column per CTA.
 #include "octic_capi_internal.h"
+#include <stdlib.h>
 #include "gelu_math.cuh"
 
 namespace octic {
@@ -479,6 +480,97 @@ __global__ void __launch_bounds__(256) layernorm_d8_fwd_lc_kernel(const float* _
     } else {
 #pragma unroll
       for (int j = 0; j < CPL; ++j) Vec<TY, 4>::store(yr + 4 * j, o[j]);
+    }
+  }
+}
+
+// LayerNormD8 forward, lane-INTERLEAVED variant for C % 128 == 0 ... i.e. CPL = D / 128 in {8, 10} (ViT-L / ViT-H): lane l
+// owns the float4 chunks l, l + 32, ..., so every load / store instruction of the warp covers 512 (256) contiguous bytes.
+// The lane-contiguous kernel above needs few instructions but each of its 16-byte accesses touches 32 different 128-byte
+// lines: ncu shows it bound by L1 wavefronts (480 per token), 3.4 TB/s at 22 % issue utilisation
+// (profiles/r02_ncu_summary.md).  Here a 1-D irrep segment spans 4 * CPL >= 32 chunks, so the 32 chunks of one j
+// (chunk = lane + 32 j) lie in at most TWO segments, split at a compile-time lane threshold: the six sums are six
+// registers with static indices, followed by six full-warp reductions.
+template <int CPL>
+struct LnIl {
+  static constexpr int S1 = 4 * CPL;                                   // chunks per 1-D irrep segment (E rows: 2 * S1)
+  static __host__ __device__ constexpr int seg(int c) { return c < 4 * S1 ? c / S1 : 4 + (c - 4 * S1) / (2 * S1); }
+  static __host__ __device__ constexpr int seg_begin(int s) { return s < 4 ? s * S1 : 4 * S1 + (s - 4) * 2 * S1; }
+};
+template <typename TY, int CPL>
+__global__ void __launch_bounds__(256, 3) layernorm_d8_fwd_il_kernel(const float* __restrict__ x, long ldx,
+                                                                  const float* __restrict__ alpha,
+                                                                  const float* __restrict__ beta, float eps,
+                                                                  TY* __restrict__ y, long ldy, float* __restrict__ stats,
+                                                                  long T_rows, int C) {
+  using G = LnIl<CPL>;
+  static_assert(G::S1 >= 32, "at most two segments per 32 consecutive chunks");
+  const int lane = threadIdx.x & 31;
+  const long warp_global = (blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x) >> 5;
+  const long nwarps = (static_cast<long>(gridDim.x) * blockDim.x) >> 5;
+  const float inv_n1 = 1.0f / static_cast<float>(C), inv_n2 = 1.0f / static_cast<float>(2 * C);
+  for (long t = warp_global; t < T_rows; t += nwarps) {
+    float v[CPL][4];
+    const float* xr = x + t * ldx + lane * 4;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) Vec<float, 4>::load(xr + 128 * j, v[j]);
+    float sum[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      constexpr int dummy = 0; (void)dummy;
+      const int slo = G::seg(32 * j), shi = G::seg(32 * j + 31);
+      const float s4 = (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+      if (slo == shi) {
+        sum[slo] += s4;
+      } else {
+        const bool lo = lane < G::seg_begin(shi) - 32 * j;
+        sum[slo] += lo ? s4 : 0.f;
+        sum[shi] += lo ? 0.f : s4;
+      }
+    }
+    float mean[6];
+#pragma unroll
+    for (int s_ = 0; s_ < 6; ++s_) mean[s_] = warp_sum(sum[s_]) * (s_ < 4 ? inv_n1 : inv_n2);
+    float var[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      const int slo = G::seg(32 * j), shi = G::seg(32 * j + 31);
+      const bool lo = slo == shi || lane < G::seg_begin(shi) - 32 * j;
+      const float mu = lo ? mean[slo] : mean[shi];
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { v[j][i] -= mu; q = fmaf(v[j][i], v[j][i], q); }
+      if (slo == shi) {
+        var[slo] += q;
+      } else {
+        var[slo] += lo ? q : 0.f;
+        var[shi] += lo ? 0.f : q;
+      }
+    }
+    float S = 0.f;
+#pragma unroll
+    for (int s_ = 0; s_ < 6; ++s_) S += (s_ < 4 ? inv_n1 : 0.5f * inv_n2) * warp_sum(var[s_]);
+    const float rstd = sqrtf(8.0f / (S + eps));       // std = (sqrt2/4) * sqrt(S + eps)
+    if (stats != nullptr && lane == 0) {
+#pragma unroll
+      for (int s_ = 0; s_ < 6; ++s_) stats[t * 8 + s_] = mean[s_];
+      stats[t * 8 + 6] = rstd;
+    }
+    TY* yr = y + t * ldy + lane * 4;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      float a[4], o[4];
+      Vec<float, 4>::load(alpha + lane * 4 + 128 * j, a);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = v[j][i] * rstd * a[i];
+      // beta lives on the A1 columns [0, C) = chunks [0, S1)
+      if (beta != nullptr && 32 * j < G::S1 && lane + 32 * j < G::S1) {
+        float bb[4];
+        Vec<float, 4>::load(beta + lane * 4 + 128 * j, bb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] += bb[i];
+      }
+      Vec<TY, 4>::store(yr + 128 * j, o);
     }
   }
 }
@@ -1075,10 +1167,22 @@ static int ln_fwd_common(bool d8, const float* x, long ldx, const float* alpha, 
   const int grid = grid_for(T * 32, 256, 148 * 8);
   const int smem = 0;
   // lane-contiguous fast path: C % 16 == 0 with C/16 chunks per lane in {3, 8, 10} (ViT-S / L / H)
-  const int lc_cpl = (d8 && (D % 128) == 0 && (ldy % 8) == 0) ? D / 128 : 0;
+  static int ln_generic = -1;      // OCTIC_LN_GENERIC=1: lane-interleaved generic kernel instead of the lane-contiguous one (A/B)
+  if (ln_generic < 0) {
+    const char* e = getenv("OCTIC_LN_GENERIC");
+    ln_generic = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  const int lc_cpl = (!ln_generic && d8 && (D % 128) == 0 && (ldy % 8) == 0) ? D / 128 : 0;
   if (y_dtype == OCTIC_BF16) {
     __nv_bfloat16* yy = static_cast<__nv_bfloat16*>(y);
-    if (d8 && lc_cpl == 10) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 10><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    static int ln_lc = -1;           // OCTIC_LN_LC=1: the lane-contiguous kernel also for ViT-L / ViT-H widths (A/B)
+    if (ln_lc < 0) {
+      const char* e = getenv("OCTIC_LN_LC");
+      ln_lc = (e != nullptr && e[0] == '1') ? 1 : 0;
+    }
+    if (d8 && lc_cpl == 10 && !ln_lc) layernorm_d8_fwd_il_kernel<__nv_bfloat16, 10><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8 && lc_cpl == 8 && !ln_lc) layernorm_d8_fwd_il_kernel<__nv_bfloat16, 8><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
+    else if (d8 && lc_cpl == 10) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 10><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
     else if (d8 && lc_cpl == 8) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 8><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
     else if (d8 && lc_cpl == 3) layernorm_d8_fwd_lc_kernel<__nv_bfloat16, 3><<<grid, 256, 0, s>>>(x, ldx, alpha, beta, eps, yy, ldy, stats, T, D / 8);
     else if (d8) OCTIC_LN_DISPATCH(layernorm_fwd_kernel, __nv_bfloat16, true, x, ldx, alpha, beta, eps, yy, ldy, stats, T, D);
