@@ -252,6 +252,20 @@ int octic_bridge_permute(const float* x, long ldx, float* y, long ldy, long T, i
 int octic_im2col_patches(const float* img, int B, int Cin, int Himg, int Wimg, int p, void* out, long ldo,
                          void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Symmetric parameter expansion: the D8-symmetric lifting filters (LiftIrrepD8Conv2d.get_weight,
+ * octic_vits/d8_layers.py:329-373, 475-484) and the unfolded positional embedding (isotypic_dim_interpolation,
+ * octic_vits/d8_utils.py:388-451) are sparse linear maps of the stored half-size parameters; idx / coef are
+ * [n_out, K] device tables built by the caller from the reference formula (K <= 16, unused slots: coef 0).
+ *   rowmap: out[r, o] (+)= sum_k coef[o, k] * in[r, idx[o, k]]      rows r, fp32, row strides in elements
+ *   posmap: out[o, c] (+)= sum_k coef[o, k] * in[idx[o, k], c]      cols c contiguous
+ * The transposed tables give the backward of either (accumulate = 1 adds into out).
+ * --------------------------------------------------------------------------------------------------------- */
+int octic_sparse_rowmap(const float* in, long ld_in, float* out, long ld_out, long rows, int n_out, int K, const int* idx,
+                        const float* coef, int accumulate, void* stream);
+int octic_sparse_posmap(const float* in, long ld_in, float* out, long ld_out, int n_out, int cols, int K, const int* idx,
+                        const float* coef, int accumulate, void* stream);
+
 /* fp32 <-> bf16 casts of [rows, cols] matrices (row strides in elements). */
 int octic_cast_f32_to_bf16(const float* x, long ldx, void* y, long ldy, long rows, int cols, void* stream);
 

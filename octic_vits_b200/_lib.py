@@ -104,6 +104,8 @@ SIGNATURES = {
     "octic_bridge_permute": [_P, _L, _P, _L, _L, _I, _P],
     "octic_im2col_patches": [_P, _I, _I, _I, _I, _I, _P, _L, _P],
     "octic_cast_f32_to_bf16": [_P, _L, _P, _L, _L, _I, _P],
+    "octic_sparse_rowmap": [_P, _L, _P, _L, _L, _I, _I, _P, _P, _I, _P],
+    "octic_sparse_posmap": [_P, _L, _P, _L, _I, _I, _I, _P, _P, _I, _P],
     "octic_optim_sqnorm": [_P, _L, _P, _P, _P],
     "octic_optim_stage1": [_P, _I, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _F, _F, _F, _F, _I, _F, _P],
     "octic_optim_lamb_stage2": [_P, _I, _P, _I, _P, _P, _P, _F, _I, _F, _P],

@@ -257,6 +257,45 @@ __global__ void __launch_bounds__(256) gelu_bwd_kernel(const __nv_bfloat16* __re
   }
 }
 
+// ------------------------------------------------ symmetric parameter expansion ------------------------------------------------
+// The D8-symmetric lifting filters (d8_layers.py:329-373) and the unfolded positional embedding (d8_utils.py:388-451) are
+// LINEAR maps of the stored half-size parameters in which every output element is a signed combination of at most K
+// stored elements (K = 2 forward, 8 for the transposed map of backward).  The index / coefficient tables are built once
+// on the host from the reference formula itself (pushing a one-hot basis through it); these two kernels apply them:
+//   row map:  out[r, o]  (+)= sum_k coef[o, k] * in[r, idx[o, k]]     (filters: r = (c_out, c_in), o = filter tap)
+//   pos map:  out[o, c]  (+)= sum_k coef[o, k] * in[idx[o, k], c]     (positional embedding: o = position, c = channel)
+// One launch each replaces ~20 eager flip / rot90 / cat / mul / add launches per parameter (and as many in backward).
+__global__ void __launch_bounds__(256) sparse_rowmap_kernel(const float* __restrict__ in, long ld_in, float* __restrict__ out,
+                                                            long ld_out, long rows, int n_out, int K,
+                                                            const int* __restrict__ idx, const float* __restrict__ coef,
+                                                            int accumulate) {
+  const long total = rows * n_out;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const long r = i / n_out;
+    const int o = static_cast<int>(i - r * n_out);
+    const float* src = in + r * ld_in;
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(__ldg(coef + o * K + k), src[__ldg(idx + o * K + k)], acc);
+    float* dst = out + r * ld_out + o;
+    *dst = accumulate ? *dst + acc : acc;
+  }
+}
+__global__ void __launch_bounds__(256) sparse_posmap_kernel(const float* __restrict__ in, long ld_in, float* __restrict__ out,
+                                                            long ld_out, int n_out, int cols, int K,
+                                                            const int* __restrict__ idx, const float* __restrict__ coef,
+                                                            int accumulate) {
+  const long total = static_cast<long>(n_out) * cols;
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(i / cols), c = static_cast<int>(i - static_cast<long>(o) * cols);
+    float acc = 0.f;
+    for (int k = 0; k < K; ++k) acc = fmaf(__ldg(coef + o * K + k), in[static_cast<long>(__ldg(idx + o * K + k)) * ld_in + c], acc);
+    float* dst = out + static_cast<long>(o) * ld_out + c;
+    *dst = accumulate ? *dst + acc : acc;
+  }
+}
+
 // ------------------------------------------------ column sums ------------------------------------------------
 // out[c] += sum_t x[t, c];  block = 32 x 8 threads, each thread owns 2 columns and strides rows.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long ldx, long T_rows,
@@ -1359,6 +1398,23 @@ int octic_cast_f32_to_bf16(const float* x, long ldx, void* y, long ldy, long row
   if (rows == 0) return OCTIC_OK;
   cast_f32_bf16_kernel<<<grid_for(rows * (cols / 4)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, ldx, static_cast<__nv_bfloat16*>(y), ldy, rows, cols);
+  return last_err();
+}
+
+int octic_sparse_rowmap(const float* in, long ld_in, float* out, long ld_out, long rows, int n_out, int K, const int* idx,
+                        const float* coef, int accumulate, void* stream) {
+  if (!in || !out || !idx || !coef || rows < 0 || n_out <= 0 || K <= 0 || K > 16) return OCTIC_ERR_ARG;
+  if (rows == 0) return OCTIC_OK;
+  sparse_rowmap_kernel<<<grid_for(rows * n_out), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, ld_in, out, ld_out, rows, n_out,
+                                                                                           K, idx, coef, accumulate);
+  return last_err();
+}
+
+int octic_sparse_posmap(const float* in, long ld_in, float* out, long ld_out, int n_out, int cols, int K, const int* idx,
+                        const float* coef, int accumulate, void* stream) {
+  if (!in || !out || !idx || !coef || n_out <= 0 || cols <= 0 || K <= 0 || K > 16) return OCTIC_ERR_ARG;
+  sparse_posmap_kernel<<<grid_for(static_cast<long>(n_out) * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, ld_in, out, ld_out, n_out, cols, K, idx, coef, accumulate);
   return last_err();
 }
 

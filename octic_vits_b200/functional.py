@@ -546,6 +546,100 @@ class BridgeFn(torch.autograd.Function):
         return ops.bridge_permute(_c(dy))
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# symmetric parameter expansion  (reference d8_layers.py:329-373, 475-484; d8_utils.py:388-451)
+# ----------------------------------------------------------------------------------------------------------------
+def _grad_or_new(p, shape, device):
+    """(tensor to write the gradient into, whether it is the parameter's own .grad)"""
+    tg = _grad_target(p)
+    if tg is not None:
+        return tg, True
+    return torch.empty(shape, dtype=torch.float32, device=device), False
+
+
+class LiftWeightFn(torch.autograd.Function):
+    """Six half-size filter parameters [Co, Ci, p/2, p/2] -> the GEMM operand [8 Co, Ci p p] of the lifting
+    convolution, row blocks A1 | A2 | B1 | B2 | E row 0 = (E_left, E_right) | E row 1 = (rot90 E_left, rot90 E_right).
+    maps = {"A1", "A2", "B1", "B2", "E", "Er": ops.SparseMap} over the filter taps."""
+
+    KINDS = ("A1", "A2", "B1", "B2", "E", "E", "Er", "Er")
+    SRC = (0, 1, 2, 3, 4, 5, 4, 5)
+
+    @staticmethod
+    def forward(ctx, wA1, wA2, wB1, wB2, wEl, wEr, maps):
+        ws = (wA1, wA2, wB1, wB2, wEl, wEr)
+        Co, Ci, hh, _ = wA1.shape
+        taps = 4 * hh * hh
+        out = torch.empty(8 * Co, Ci * taps, dtype=torch.float32, device=wA1.device)
+        for g, (kind, si) in enumerate(zip(LiftWeightFn.KINDS, LiftWeightFn.SRC)):
+            ops.sparse_rowmap(_c(ws[si].detach()).view(Co * Ci, hh * hh), out[g * Co:(g + 1) * Co].view(Co * Ci, taps), maps[kind])
+        ctx.maps, ctx.params, ctx.dims = maps, ws, (Co, Ci, hh)
+        return out
+
+    @staticmethod
+    def backward(ctx, dw):
+        Co, Ci, hh = ctx.dims
+        taps = 4 * hh * hh
+        dw = _c(dw)
+        grads, written = [], [False] * 6
+        outs = []
+        for i, p in enumerate(ctx.params):
+            if not ctx.needs_input_grad[i]:
+                outs.append(None); grads.append(None)
+                continue
+            t, own = _grad_or_new(p, p.shape, dw.device)
+            outs.append((t, own)); grads.append(None if own else t)
+        for g, (kind, si) in enumerate(zip(LiftWeightFn.KINDS, LiftWeightFn.SRC)):
+            if outs[si] is None:
+                continue
+            t, own = outs[si]
+            ops.sparse_rowmap(dw[g * Co:(g + 1) * Co].view(Co * Ci, taps), t.view(Co * Ci, hh * hh), ctx.maps[kind], transpose=True,
+                              accumulate=own or written[si])
+            written[si] = True
+        return (*grads, None)
+
+
+class PosEmbedFn(torch.autograd.Function):
+    """Six stored positional-embedding quadrants [h/2, w/2, C] -> packed rows [h w, 8 C]
+    (A1 | A2 | B1 | B2 | E row 0 = (x4, x6) | E row 1 = (x5, x7)).  maps over the positions, as in LiftWeightFn."""
+
+    KINDS = ("A1", "A2", "B1", "B2", "E", "E", "Er", "Er")
+    SRC = (0, 1, 2, 3, 4, 5, 4, 5)
+
+    @staticmethod
+    def forward(ctx, p0, p1, p2, p3, p4, p5, maps):
+        ps = (p0, p1, p2, p3, p4, p5)
+        h2, w2, C = p0.shape
+        n_out = maps["A1"].n_out
+        rows = torch.empty(n_out, 8 * C, dtype=torch.float32, device=p0.device)
+        for g, (kind, si) in enumerate(zip(PosEmbedFn.KINDS, PosEmbedFn.SRC)):
+            ops.sparse_posmap(_c(ps[si].detach()).view(h2 * w2, C), rows[:, g * C:(g + 1) * C], maps[kind])
+        ctx.maps, ctx.params = maps, ps
+        return rows
+
+    @staticmethod
+    def backward(ctx, drows):
+        ps = ctx.params
+        h2, w2, C = ps[0].shape
+        if drows.stride(1) != 1:
+            drows = drows.contiguous()
+        grads, written, outs = [], [False] * 6, []
+        for i, p in enumerate(ps):
+            if not ctx.needs_input_grad[i]:
+                outs.append(None); grads.append(None)
+                continue
+            t, own = _grad_or_new(p, p.shape, drows.device)
+            outs.append((t, own)); grads.append(None if own else t)
+        for g, (kind, si) in enumerate(zip(PosEmbedFn.KINDS, PosEmbedFn.SRC)):
+            if outs[si] is None:
+                continue
+            t, own = outs[si]
+            ops.sparse_posmap(drows[:, g * C:(g + 1) * C], t.view(h2 * w2, C), ctx.maps[kind], transpose=True,
+                              accumulate=own or written[si])
+            written[si] = True
+        return (*grads, None)
+
+
 class Im2ColFn(torch.autograd.Function):
     """Patches of an image as GEMM rows (no gradient w.r.t. the image: it is the network input)."""
 

@@ -478,6 +478,37 @@ class PowerSpectrumInvariant(nn.Module):
 # ----------------------------------------------------------------------------------------------------------------
 # front end
 # ----------------------------------------------------------------------------------------------------------------
+def expand_filter(weight: Tensor, irrep: str) -> Tensor:
+    """The reference's filter symmetrisation (d8_layers.py:329-373) as a function of the stored half-size filter
+    [..., p/2, p/2] -> [..., p, p].  "Er" = the E filter turned by 90 degrees (second row of the 2-D irrep, :377-381)."""
+    if irrep in ("E", "Er"):
+        w = 0.5 * weight
+        w2 = torch.cat([w, w.flip(-2)], dim=-2)
+        full = torch.cat([w2, -w2.flip(-1)], dim=-1)
+        return full.rot90(1, (-2, -1)) if irrep == "Er" else full
+    s_rot = 1.0 if irrep in ("A1", "A2") else -1.0
+    s_flip = 1.0 if irrep in ("A1", "B1") else -1.0
+    w = SQRT2_OVER_4 * weight
+    left = torch.cat([w, s_rot * w.rot90(1, (-2, -1))], dim=-2)
+    right = torch.cat([s_rot * w.rot90(3, (-2, -1)), w.rot90(2, (-2, -1))], dim=-2)
+    full = torch.cat([left, right], dim=-1)
+    return full + s_flip * full.flip(-1)
+
+
+_LIFT_MAPS: dict = {}
+
+
+def lift_maps(hh: int, device):
+    """ops.SparseMap per irrep kind for half-size hh x hh filters, built once per (size, device) by pushing the one-hot
+    basis of the stored filter through expand_filter -- the kernel applies exactly the reference formula."""
+    key = (hh, str(device))
+    if key not in _LIFT_MAPS:
+        basis = torch.eye(hh * hh).view(hh * hh, 1, hh, hh)
+        _LIFT_MAPS[key] = {k: OF.ops.build_sparse_map(expand_filter(basis, k).reshape(hh * hh, 4 * hh * hh).t().contiguous(), device)
+                           for k in ("A1", "A2", "B1", "B2", "E", "Er")}
+    return _LIFT_MAPS[key]
+
+
 class LiftIrrepD8Conv2d(nn.Module):
     """Parameter holder + filter symmetrisation of the reference's lifting convolution (d8_layers.py:284-382).
     The convolution itself is run by PatchEmbedD8 as one im2col GEMM over all irreps."""
@@ -514,17 +545,7 @@ class LiftIrrepD8Conv2d(nn.Module):
 
     def expand_weight(self) -> Tensor:
         """half-size filter -> full D8-symmetric filter [Co, Ci, p, p] (tiny tensors; plain torch, differentiable)."""
-        if self.irrep == "E":
-            w = 0.5 * self.weight
-            w2 = torch.cat([w, w.flip(-2)], dim=-2)
-            return torch.cat([w2, -w2.flip(-1)], dim=-1)
-        s_rot = 1.0 if self.irrep in ("A1", "A2") else -1.0
-        s_flip = 1.0 if self.irrep in ("A1", "B1") else -1.0
-        w = SQRT2_OVER_4 * self.weight
-        left = torch.cat([w, s_rot * w.rot90(1, (-2, -1))], dim=-2)
-        right = torch.cat([s_rot * w.rot90(3, (-2, -1)), w.rot90(2, (-2, -1))], dim=-2)
-        full = torch.cat([left, right], dim=-1)
-        return full + s_flip * full.flip(-1)
+        return expand_filter(self.weight, self.irrep)
 
 
 class LiftD8(nn.Module):
@@ -545,10 +566,15 @@ class LiftD8(nn.Module):
     def packed_weight_and_bias(self):
         """GEMM operand [D, Cin*p*p] whose row blocks follow the packed row: A1, A2, B1, B2,
         E row 0 = (E_left, E_right), E row 1 = (rot90 E_left, rot90 E_right) (d8_layers.py:377-381, 475-484)."""
-        el, er = self.conv_E_left.expand_weight(), self.conv_E_right.expand_weight()
-        ws = [self.conv_A1.expand_weight(), self.conv_A2.expand_weight(), self.conv_B1.expand_weight(),
-              self.conv_B2.expand_weight(), el, er, el.rot90(1, (-2, -1)), er.rot90(1, (-2, -1))]
-        w = torch.cat([t.flatten(1) for t in ws], dim=0)
+        convs = (self.conv_A1, self.conv_A2, self.conv_B1, self.conv_B2, self.conv_E_left, self.conv_E_right)
+        if self.conv_A1.weight.is_cuda and all(type(c) is LiftIrrepD8Conv2d for c in convs):
+            # one launch per row block instead of ~150 eager flip / rot90 / cat / mul / add launches (and their backward)
+            w = OF.LiftWeightFn.apply(*[c.weight for c in convs], lift_maps(self.conv_A1.weight.shape[-1], self.conv_A1.weight.device))
+        else:
+            el, er = self.conv_E_left.expand_weight(), self.conv_E_right.expand_weight()
+            ws = [self.conv_A1.expand_weight(), self.conv_A2.expand_weight(), self.conv_B1.expand_weight(),
+                  self.conv_B2.expand_weight(), el, er, el.rot90(1, (-2, -1)), er.rot90(1, (-2, -1))]
+            w = torch.cat([t.flatten(1) for t in ws], dim=0)
         bias = None
         if self.conv_A1.bias is not None:
             bias = torch.cat((self.conv_A1.bias, self.conv_A1.bias.new_zeros(w.shape[0] - self.conv_A1.bias.shape[0])))

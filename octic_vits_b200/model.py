@@ -20,24 +20,43 @@ def trunc_normal_(tensor, mean=0.0, std=1.0, a=-2.0, b=2.0):
     return nn.init.trunc_normal_(tensor, mean=mean, std=std, a=a, b=b)
 
 
-def unfold_pos_embed_packed(ps) -> torch.Tensor:
-    """isotypic_dim_interpolation(dim=0) + convert_8tuple_to_5tuple (reference octic_vits/d8_utils.py:388-451,
-    model.py:174) producing packed rows [h*w, D] directly.  Six tiny parameters; plain differentiable torch ops."""
-    def quad(w, s_rot, s_flip):
-        left = torch.cat((w, s_rot * w.rot90(1, (0, 1))), dim=0)
-        right = torch.cat((s_rot * w.rot90(3, (0, 1)), w.rot90(2, (0, 1))), dim=0)
-        full = torch.cat((left, right), dim=1)
-        return full + s_flip * full.flip(1)
-
-    a1, a2 = quad(ps[0], 1.0, 1.0), quad(ps[1], 1.0, -1.0)
-    b1, b2 = quad(ps[2], -1.0, 1.0), quad(ps[3], -1.0, -1.0)
-    es = []
-    for p in (ps[4], ps[5]):
+def unfold_pos(p: torch.Tensor, kind: str) -> torch.Tensor:
+    """One stored positional-embedding quadrant [h/2, w/2, C] -> the full grid [h, w, C] of irrep component `kind`
+    (isotypic_dim_interpolation(dim=0), reference octic_vits/d8_utils.py:388-451); "Er" = the second row of the E pair."""
+    if kind in ("E", "Er"):
         col = torch.cat((p, p.flip(0)), dim=0)
         full = torch.cat((col, -col.flip(1)), dim=1)
-        es.append((full, full.rot90(1, (0, 1))))
-    # packed row: A1 | A2 | B1 | B2 | E row0 = (x4, x6) | E row1 = (x5, x7)
-    packed = torch.cat((a1, a2, b1, b2, es[0][0], es[1][0], es[0][1], es[1][1]), dim=-1)
+        return full.rot90(1, (0, 1)) if kind == "Er" else full
+    s_rot = 1.0 if kind in ("A1", "A2") else -1.0
+    s_flip = 1.0 if kind in ("A1", "B1") else -1.0
+    left = torch.cat((p, s_rot * p.rot90(1, (0, 1))), dim=0)
+    right = torch.cat((s_rot * p.rot90(3, (0, 1)), p.rot90(2, (0, 1))), dim=0)
+    full = torch.cat((left, right), dim=1)
+    return full + s_flip * full.flip(1)
+
+
+_POS_MAPS: dict = {}
+
+
+def pos_maps(h2: int, w2: int, device):
+    """ops.SparseMap per component kind over the positions of an h2 x w2 quadrant (one-hot basis pushed through unfold_pos)."""
+    key = (h2, w2, str(device))
+    if key not in _POS_MAPS:
+        n = h2 * w2
+        basis = torch.eye(n).view(h2, w2, n)
+        _POS_MAPS[key] = {k: OF.ops.build_sparse_map(unfold_pos(basis, k).reshape(4 * n, n), device)
+                          for k in ("A1", "A2", "B1", "B2", "E", "Er")}
+    return _POS_MAPS[key]
+
+
+def unfold_pos_embed_packed(ps) -> torch.Tensor:
+    """isotypic_dim_interpolation(dim=0) + convert_8tuple_to_5tuple (reference octic_vits/d8_utils.py:388-451,
+    model.py:174) producing packed rows [h*w, D] directly: A1 | A2 | B1 | B2 | E row0 = (x4, x6) | E row1 = (x5, x7).
+    On the GPU one sparse-map launch per column block (functional.PosEmbedFn); plain differentiable torch ops otherwise."""
+    if ps[0].is_cuda:
+        return OF.PosEmbedFn.apply(*ps, pos_maps(ps[0].shape[0], ps[0].shape[1], ps[0].device))
+    packed = torch.cat((unfold_pos(ps[0], "A1"), unfold_pos(ps[1], "A2"), unfold_pos(ps[2], "B1"), unfold_pos(ps[3], "B2"),
+                        unfold_pos(ps[4], "E"), unfold_pos(ps[5], "E"), unfold_pos(ps[4], "Er"), unfold_pos(ps[5], "Er")), dim=-1)
     return packed.flatten(0, 1)
 
 

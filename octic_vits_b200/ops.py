@@ -455,6 +455,68 @@ def im2col_patches(img: torch.Tensor, p: int) -> torch.Tensor:
     return out
 
 
+# ----------------------------------------------------------------------------------------------------------------
+# symmetric parameter expansion (lifting filters, positional embedding): sparse linear maps applied by one kernel
+# ----------------------------------------------------------------------------------------------------------------
+@dataclass
+class SparseMap:
+    """out = S in for a sparse S [n_out, n_in] with at most K entries per row, and its transpose (backward)."""
+    n_in: int
+    n_out: int
+    k_fwd: int
+    idx_fwd: torch.Tensor      # int32 [n_out, k_fwd]
+    coef_fwd: torch.Tensor     # fp32  [n_out, k_fwd]
+    k_bwd: int
+    idx_bwd: torch.Tensor      # int32 [n_in, k_bwd]
+    coef_bwd: torch.Tensor
+
+
+def _tables(dense: torch.Tensor):
+    nz = dense != 0
+    k = max(1, int(nz.sum(1).max()))
+    if k > 16:
+        raise _lib.OcticError("sparse map with more than 16 entries per row")
+    idx = torch.zeros(dense.shape[0], k, dtype=torch.int32)
+    coef = torch.zeros(dense.shape[0], k, dtype=torch.float32)
+    for o in range(dense.shape[0]):
+        cols = torch.nonzero(nz[o]).flatten()
+        idx[o, :cols.numel()] = cols.to(torch.int32)
+        coef[o, :cols.numel()] = dense[o, cols]
+    return k, idx, coef
+
+
+def build_sparse_map(dense: torch.Tensor, device) -> SparseMap:
+    """dense: fp32 [n_out, n_in] on the CPU (obtained by pushing a one-hot basis through the reference formula)."""
+    dense = dense.detach().to("cpu", torch.float32)
+    kf, idf, cf = _tables(dense)
+    kb, idb, cb = _tables(dense.t().contiguous())
+    return SparseMap(dense.shape[1], dense.shape[0], kf, idf.to(device), cf.to(device), kb, idb.to(device), cb.to(device))
+
+
+def sparse_rowmap(inp: torch.Tensor, out: torch.Tensor, m: SparseMap, transpose: bool = False, accumulate: bool = False) -> None:
+    """out[r, :] (+)= S in[r, :] (or S^T with transpose=True); inp / out: fp32 2-D with unit inner stride."""
+    _req(inp, torch.float32, "inp")
+    _req(out, torch.float32, "out")
+    n_in, n_out = (m.n_out, m.n_in) if transpose else (m.n_in, m.n_out)
+    if inp.shape[1] != n_in or out.shape != (inp.shape[0], n_out) or inp.stride(1) != 1 or out.stride(1) != 1:
+        raise _lib.OcticError(f"sparse_rowmap: shapes {tuple(inp.shape)} -> {tuple(out.shape)} do not match the map")
+    k, idx, coef = (m.k_bwd, m.idx_bwd, m.coef_bwd) if transpose else (m.k_fwd, m.idx_fwd, m.coef_fwd)
+    call("octic_sparse_rowmap", inp.data_ptr(), inp.stride(0), out.data_ptr(), out.stride(0), inp.shape[0], n_out, k,
+         idx.data_ptr(), coef.data_ptr(), int(accumulate), _stream())
+
+
+def sparse_posmap(inp: torch.Tensor, out: torch.Tensor, m: SparseMap, transpose: bool = False, accumulate: bool = False) -> None:
+    """out[o, :] (+)= sum_i S[o, i] in[i, :] (or S^T); inp [n_in, cols], out [n_out, cols], unit inner stride."""
+    _req(inp, torch.float32, "inp")
+    _req(out, torch.float32, "out")
+    n_in, n_out = (m.n_out, m.n_in) if transpose else (m.n_in, m.n_out)
+    if inp.shape[0] != n_in or out.shape != (n_out, inp.shape[1]) or inp.stride(1) != 1 or out.stride(1) != 1:
+        raise _lib.OcticError(f"sparse_posmap: shapes {tuple(inp.shape)} -> {tuple(out.shape)} do not match the map")
+    k, idx, coef = (m.k_bwd, m.idx_bwd, m.coef_bwd) if transpose else (m.k_fwd, m.idx_fwd, m.coef_fwd)
+    call("octic_sparse_posmap", inp.data_ptr(), inp.stride(0), out.data_ptr(), out.stride(0), n_out, inp.shape[1], k,
+         idx.data_ptr(), coef.data_ptr(), int(accumulate), _stream())
+
+
 def cast_bf16(x: torch.Tensor) -> torch.Tensor:
     _req(x, torch.float32, "x")
     y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)

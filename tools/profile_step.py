@@ -68,7 +68,7 @@ if args.events:
     step()
     torch.cuda.synchronize()
     evs = _lib.STATS._events
-    for name, (a, b, f) in zip(tap, evs):
+    for name, (_n, a, b, f) in zip(tap, evs):
         ms = a.elapsed_time(b)
         d = per.setdefault(name, [0.0, 0, 0.0])
         d[0] += ms; d[1] += 1; d[2] += f
