@@ -22,6 +22,7 @@
 
 #include <stdint.h>
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -233,6 +234,17 @@ int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int 
 /* delta_ws: caller-provided fp32 workspace [B, H, N] (receives rowsum(dO * O)). */
 int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_ws,
                         void* dqkv, int B, int N, int H, int hd, int layout, void* stream);
+/* Same backward with a caller-provided scratch for the staged dQ path of the tcgen05 kernel (the autograd of
+ * F.scaled_dot_product_attention at octic_vits/d8_layers.py:645-648 / deit/vit.py:44-48): the key-major pass writes
+ * dS^T (bf16) into an L2-resident slot per resident CTA and dQ = dS K is one MMA chain per 128-query tile instead of a
+ * second pass that recomputes S, dP and the exponentials.  ws: octic_attention_bwd_workspace_bytes(N, hd) bytes,
+ * 256-byte aligned, its first 4096 bytes zeroed once by the caller (slot flags; every launch leaves them zero); it
+ * may be shared by all launches on ONE stream.  ws = NULL (or a shape the staged path does not cover: the size
+ * query returns 0) runs the two-pass kernel; both produce the same gradients up to bf16 rounding of dS. */
+size_t octic_attention_bwd_workspace_bytes(int N, int hd);
+int octic_attention_bwd_ws(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_ws,
+                           void* dqkv, int B, int N, int H, int hd, int layout, void* ws, size_t ws_bytes,
+                           void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * PowerSpectrumInvariant (octic_vits/d8_invariantization.py:49-64): [T, 8C] fp32 -> [T, 6C] bf16

@@ -99,6 +99,7 @@ SIGNATURES = {
     "octic_colsum_bf16": [_P, _L, _L, _I, _P, _P],
     "octic_attention_fwd": [_P, _P, _P, _I, _I, _I, _I, _I, _P],
     "octic_attention_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "octic_attention_bwd_ws": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _P],
     "octic_power_spectrum_fwd": [_P, _L, _P, _L, _L, _I, _P],
     "octic_power_spectrum_bwd": [_P, _L, _I, _P, _L, _P, _L, _L, _I, _P],
     "octic_bridge_permute": [_P, _L, _P, _L, _L, _I, _P],
@@ -129,6 +130,8 @@ def load() -> C.CDLL:
     lib.octic_device_ok.restype = C.c_int
     lib.octic_attention_headmajor_supported.restype = C.c_int
     lib.octic_attention_headmajor_supported.argtypes = [C.c_int, C.c_int, C.c_int]
+    lib.octic_attention_bwd_workspace_bytes.restype = C.c_size_t
+    lib.octic_attention_bwd_workspace_bytes.argtypes = [C.c_int, C.c_int]
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = C.c_int
@@ -144,7 +147,7 @@ def check(rc: int, what: str) -> None:
 
 
 # kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
-KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_linear_d8_pack_weights_scaled": 5, "octic_attention_bwd": 2,
+KERNELS_PER_CALL = {"octic_linear_d8_pack_weights": 5, "octic_linear_d8_pack_weights_scaled": 5, "octic_attention_bwd": 2, "octic_attention_bwd_ws": 2,
                     "octic_optim_sqnorm": 2, "octic_optim_lamb_stage2": 2}   # bwd: delta + main (legacy: +1)
 
 
@@ -180,9 +183,12 @@ class _Stats:
 STATS = _Stats()
 
 
-def call(name: str, *args, flops: float = 0.0, extra_kernels: int = 0) -> None:
+def call(name: str, *args, flops: float = 0.0, extra_kernels: int = 0, stat: str = "") -> None:
+    """`stat`: the name the call is counted / timed under when it differs from the entry point (e.g. the `_ws` flavour
+    of an op keeps the op's name in event tables)."""
     fn = getattr(load(), name)
     STATS.kernel_launches += KERNELS_PER_CALL.get(name, 1) + extra_kernels
+    name = stat or name
     STATS.calls[name] = STATS.calls.get(name, 0) + 1
     if STATS.profile_prefixes and name in STATS.profile_prefixes:
         import torch

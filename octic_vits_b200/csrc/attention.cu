@@ -715,8 +715,16 @@ int octic_attention_fwd(const void* qkv, void* o, float* lse, int B, int N, int 
   }
 }
 
+size_t octic_attention_bwd_workspace_bytes(int N, int hd) { return attn_bwd_tc_workspace_bytes(N, hd); }
+
 int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_ws,
-                           void* dqkv, int B, int N, int H, int hd, int octic_layout, void* stream) {
+                        void* dqkv, int B, int N, int H, int hd, int octic_layout, void* stream) {
+  return octic_attention_bwd_ws(qkv, o, d_o, lse, delta_ws, dqkv, B, N, H, hd, octic_layout, nullptr, 0, stream);
+}
+
+int octic_attention_bwd_ws(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta_ws,
+                           void* dqkv, int B, int N, int H, int hd, int octic_layout, void* ws, size_t ws_bytes,
+                           void* stream) {
   if (!qkv || !o || !d_o || !lse || !delta_ws || !dqkv || B <= 0 || N <= 0) return OCTIC_ERR_ARG;
   HeadMap m;
   int rc = make_head_map(&m, H, hd, octic_layout);
@@ -726,7 +734,7 @@ int octic_attention_bwd(const void* qkv, const void* o, const void* d_o, const f
     launch_attn_delta(static_cast<const __nv_bfloat16*>(o), static_cast<const __nv_bfloat16*>(d_o), delta_ws, B, N, H, m,
                       octic_layout == OCTIC_ATTN_OCTIC_HEADMAJOR, s);
     if (cudaGetLastError() != cudaSuccess) return OCTIC_ERR_CUDA;
-    return launch_attn_bwd_tc(qkv, d_o, lse, delta_ws, dqkv, B, N, H, m, s);
+    return launch_attn_bwd_tc(qkv, d_o, lse, delta_ws, dqkv, B, N, H, m, ws, ws_bytes, s);
   }
   if (octic_layout == OCTIC_ATTN_OCTIC_HEADMAJOR) return OCTIC_ERR_ARG;
   switch (hd) {

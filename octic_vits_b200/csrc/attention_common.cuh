@@ -44,7 +44,10 @@ constexpr float kLn2 = 0.6931471805599453f;
 // launchers of the tcgen05 path (attention_tc.cu); return OCTIC_ERR_ARG when the shape is outside its envelope
 bool attn_tc_supported(int N, int hd, bool backward);
 int launch_attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, const HeadMap& m, cudaStream_t s);
+// ws: optional staged-dQ workspace (attn_bwd_tc_workspace_bytes(N, hd) bytes, 256-byte aligned, slot flags zeroed
+// once); nullptr = the two-phase kernel that recomputes S and dP for dQ.
 int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* delta, void* dqkv, int B, int N,
-                       int H, const HeadMap& m, cudaStream_t s);
+                       int H, const HeadMap& m, void* ws, size_t ws_bytes, cudaStream_t s);
+size_t attn_bwd_tc_workspace_bytes(int N, int hd);
 
 }  // namespace octic

@@ -33,6 +33,7 @@
 //   delta = rowsum(dO * O) comes from attn_delta_kernel (attention.cu).
 #include "attention_common.cuh"
 #include "sm100_ptx.cuh"
+#include <stdlib.h>
 
 namespace octic {
 
@@ -602,7 +603,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
 //  backward
 // =====================================================================================================================
 constexpr int kBwdMathThreads = 256;
-constexpr int kBwdThreads = kBwdMathThreads + 96;   // + control warp + two tail-row warps (as key / as query)
+constexpr int kBwdTailWarps = 3;                    // staged dQ: all three take the tail tokens as keys; else as key / as query / idle
+constexpr int kBwdThreads = kBwdMathThreads + 32 + 32 * kBwdTailWarps;   // + control warp + tail-row warps
 
 template <int HD, int GRAN>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV,
@@ -612,14 +614,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
                                                                      __nv_bfloat16* __restrict__ dqkv, int N, int H, HeadMap m,
                                                                      float scale, float scale_log2,
                                                                      const __grid_constant__ ChunkPlan cp,
-                                                                     int box_rows, int n_tail) {
+                                                                     int box_rows, int n_tail,
+                                                                     const __grid_constant__ CUtensorMap tmDS,
+                                                                     __nv_bfloat16* __restrict__ ds_ws, int* ds_slots,
+                                                                     int n_slots, int ds_box_rows) {
   constexpr int KS = HD / 16, CW = tc_chunk_width(HD), ACC = 4 * CW, NU = HD / (GRAN / 2);
   constexpr int NPW = (CW / 16 + 1) / 2;        // max 16-column pieces per warp in the math step
   constexpr int KS0 = (KS + 1) / 2;             // epilogue: pieces of the accumulator handled by column-half 0
   constexpr uint32_t kTmemCols = 512;
   constexpr uint32_t stg_bytes = 128 * HD * 2;
   static_assert(ACC + 2 * HD <= 512, "TMEM budget");
-  enum { BAR_KQ = 0, BAR_VDO = 1, BAR_LFULL = 2, BAR_MDONE = 4, BAR_ACC = 6, NBARS = 7 };
+  enum { BAR_KQ = 0, BAR_VDO = 1, BAR_LFULL = 2, BAR_MDONE = 4, BAR_ACC = 6, BAR_DS = 7, BAR_TAIL = 8, BAR_DSLOAD = 9,
+         BAR_DQ = 10, BAR_DQFREE = 12, NBARS = 14 };
+  // Staged dQ (ds_ws != nullptr): the query-major phase 1 (S, dP and the exponentials a second time) is replaced by
+  //   phase 0  also writes dS^T (bf16, [key][query], rows/columns up to Rk) into this CTA's slot of an L2-resident scratch,
+  //   phase 1' TMA-loads it back as the MN-major A operand of dQ_tile = dS[tile queries, all keys] K (Rk/16 K-steps).
+  // One slot per resident CTA (claimed with an atomic CAS, released after the last TMA load): 2 x SM-count slots of
+  // Rk x Rk bf16 stay in L2 (44 MB at N = 257), the data makes no HBM round trip.
+  const bool staged = ds_ws != nullptr;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int Rk = cp.off[cp.n - 1] + cp.w[cp.n - 1];
@@ -636,6 +648,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + NU + ((2 * NU) & 1));
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NBARS);
   float* tail_red = reinterpret_cast<float*>(tmem_ptr + 4);      // two tail warps x [32][33] reduction scratch
+  float* tail_xch = tail_red + 2 * 32 * 33;                      // staged: [tail warps][8 atom columns][32] partial sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / H, h = blockIdx.x - b * H;
@@ -655,7 +668,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     mbar_init(&bars[BAR_LFULL], 1); mbar_init(&bars[BAR_LFULL + 1], 1);
     mbar_init(&bars[BAR_MDONE], kBwdMathThreads); mbar_init(&bars[BAR_MDONE + 1], kBwdMathThreads);
     mbar_init(&bars[BAR_ACC], 1);
+    mbar_init(&bars[BAR_DS], kBwdMathThreads + (n_tail > 0 ? 32 * kBwdTailWarps : 0));
+    mbar_init(&bars[BAR_TAIL], 32 * kBwdTailWarps);
+    mbar_init(&bars[BAR_DSLOAD], 1);
+    mbar_init(&bars[BAR_DQ], 1); mbar_init(&bars[BAR_DQ + 1], 1);
+    mbar_init(&bars[BAR_DQFREE], kBwdMathThreads); mbar_init(&bars[BAR_DQFREE + 1], kBwdMathThreads);
     fence_mbar_init();
+    if (staged) {
+      int sl = static_cast<int>(blockIdx.x % static_cast<unsigned>(n_slots));
+      uint32_t spins = 0;
+      while (atomicCAS(&ds_slots[sl], 0, 1) != 0) {
+        sl = sl + 1 == n_slots ? 0 : sl + 1;
+        if (++spins > OCTIC_WAIT_SPINS) __trap();
+      }
+      tmem_ptr[1] = static_cast<uint32_t>(sl);
+    }
   }
   if (warp == 8) tmem_alloc(tmem_ptr, kTmemCols);
   if (tid < kBwdMathThreads) {
@@ -673,7 +700,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), do_addr = smem_u32(dOs);
   const int nt = (Nm + 127) >> 7, nc = cp.n;
-  const int jobs_per_phase = nt * nc, G = 2 * jobs_per_phase;
+  const int jobs_per_phase = nt * nc, G = staged ? jobs_per_phase : 2 * jobs_per_phase;
+  const int slot = staged ? static_cast<int>(tmem_ptr[1]) : 0;
+  // dS^T [Rk keys][ldS queries].  Measured (tools/gpu/r2_ab.sh / r2_ad.sh): a 128-byte-multiple pitch (640 B at N = 257)
+  // makes the TMA read faster (1.5 k vs 2.6 k cycles per tile) but the 32-byte-per-lane writes of the math warps slower
+  // (jobs 1.4-1.6 k -> 1.8-2.4 k cycles): 421 vs 389 us per launch, so the pitch stays Rk.
+  const int ldS = Rk;
+  __nv_bfloat16* ds_mine = staged ? ds_ws + static_cast<long>(slot) * Rk * ldS : nullptr;
 
   if (warp >= 9) {
     // -------------------------------------------------- tail warps --------------------------------------------------
@@ -681,7 +714,120 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     // stay in the column (chunk) dimension of the tensor path; their own rows are done here on the CUDA cores from the
     // same shared-memory tiles: warp 9 takes them as keys (dK_j, dV_j over all queries), warp 10 as queries (dQ_i over
     // all keys).  lane = the other token (stride 32).  P and dS are rounded to bf16 like the tensor path's operands.
-    if (n_tail > 0) {
+    if (n_tail > 0 && staged) {
+      // Staged dQ: the tail tokens' dQ rows come from the tensor path (one more query tile in phase 1'), and ALL tail
+      // warps take the tail tokens as keys, splitting the queries (warp 9 + p: lane groups p, p + 3, p + 6, ..) -- they
+      // are on the critical path now: phase 1' needs their dS^T rows and the V | dO tiles they read.
+      constexpr int TW = kBwdTailWarps, UPW = (kTailKpl + TW - 1) / TW;
+      const int half = warp - 9;
+      float* red = tail_red + half * (32 * 17);      // [32 lanes][16 columns + 1]: acc1 and acc2 go through it in turn
+      const int kpl = (Rk + 31) >> 5;
+      mbar_wait(&bars[BAR_KQ], 0);
+      mbar_wait(&bars[BAR_VDO], 0);
+      for (int r = Nm; r < N; ++r) {
+        float sx[UPW], sy[UPW];
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) { sx[u] = 0.f; sy[u] = 0.f; }
+#pragma unroll 1
+        for (int a = 0; a < KS; ++a) {
+          float f1[16], f2[16];
+          lds_row16(k_addr, Rk, a, r, f1);
+          lds_row16(v_addr, Rk, a, r, f2);
+#pragma unroll
+          for (int u = 0; u < UPW; ++u) {
+            const int i = lane + 32 * (TW * u + half);
+            if (TW * u + half < kpl && i < Rk) {
+              float g1[16], g2[16];
+              lds_row16(q_addr, Rk, a, i, g1);
+              lds_row16(do_addr, Rk, a, i, g2);
+              float ax = sx[u], ay = sy[u];
+#pragma unroll
+              for (int c = 0; c < 16; ++c) { ax = fmaf(f1[c], g1[c], ax); ay = fmaf(f2[c], g2[c], ay); }
+              sx[u] = ax; sy[u] = ay;
+            }
+          }
+        }
+        // sx = k_r . q_i, sy = v_r . dO_i  ->  sx = P[i, r], sy = dS[i, r] (rounded to bf16 like the tensor path's operands)
+#pragma unroll
+        for (int u = 0; u < UPW; ++u) {
+          const int i = lane + 32 * (TW * u + half);
+          float pv = 0.f, dv = 0.f;
+          if (TW * u + half < kpl && i < N) {
+            pv = exp2f(fmaf(sx[u], scale_log2, -lse_s[i]));
+            dv = pv * (sy[u] - del_s[i]);
+          }
+          sx[u] = __bfloat162float(__float2bfloat16(pv));
+          sy[u] = __bfloat162float(__float2bfloat16(dv));
+          if (TW * u + half < kpl && i < Rk) ds_mine[static_cast<long>(r) * ldS + i] = __float2bfloat16(dv);
+        }
+#pragma unroll 1
+        for (int a = 0; a < KS; ++a) {
+          float acc1[16], acc2[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { acc1[c] = 0.f; acc2[c] = 0.f; }
+#pragma unroll
+          for (int u = 0; u < UPW; ++u) {
+            const int i = lane + 32 * (TW * u + half);
+            if (TW * u + half < kpl && i < Rk) {
+              float g1[16], g2[16];
+              lds_row16(q_addr, Rk, a, i, g1);
+              lds_row16(do_addr, Rk, a, i, g2);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) { acc2[c] = fmaf(sy[u], g1[c], acc2[c]); acc1[c] = fmaf(sx[u], g2[c], acc1[c]); }
+            }
+          }
+          // column sums over the 32 lanes: lane l adds rows (l >> 4), (l >> 4) + 2, .. of column l & 15, one shuffle joins
+          // the two row halves
+          float tot1, tot2;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) red[lane * 17 + c] = acc1[c];
+          __syncwarp();
+          {
+            float t0 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) t0 += red[(2 * u + (lane >> 4)) * 17 + (lane & 15)];
+            tot1 = t0 + __shfl_xor_sync(0xffffffffu, t0, 16);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 16; ++c) red[lane * 17 + c] = acc2[c];
+          __syncwarp();
+          {
+            float t0 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) t0 += red[(2 * u + (lane >> 4)) * 17 + (lane & 15)];
+            tot2 = t0 + __shfl_xor_sync(0xffffffffu, t0, 16);
+          }
+          tail_xch[(half * 8 + a) * 32 + lane] = lane < 16 ? tot1 : tot2;     // lanes 0..15: dV column, lanes 16..31: dK column
+          __syncwarp();
+        }
+        named_bar_sync(6, 32 * TW);
+        if (half == 0) {
+          __nv_bfloat16* drow = drows + static_cast<long>(r) * ld3;
+          for (int a = 0; a < KS; ++a) {
+            float tot = 0.f;
+#pragma unroll
+            for (int w = 0; w < TW; ++w) tot += tail_xch[(w * 8 + a) * 32 + lane];
+            const int jc = a * 16 + (lane & 15);
+            int base, smul;
+            qkv_col(m, h, jc & ~1, base, smul);
+            base += jc & 1;
+            if (lane >= 16) drow[base + smul] = __float2bfloat16(tot * scale);
+            else drow[base + 2 * smul] = __float2bfloat16(tot);
+          }
+        }
+        named_bar_sync(6, 32 * TW);
+      }
+      if (half == 0) {
+        // key rows [N, Rk) of the scratch: nobody computes them, the dQ contraction reads them (times zero rows of K)
+        for (int r = N; r < Rk; ++r)
+          for (int i = lane; i < Rk; i += 32) ds_mine[static_cast<long>(r) * ldS + i] = __float2bfloat16(0.f);
+      }
+      __threadfence();
+      fence_proxy_async_all();
+      mbar_arrive(&bars[BAR_DS]);
+      mbar_arrive(&bars[BAR_TAIL]);      // this warp no longer reads the Q / K / V / dO tiles
+    } else if (n_tail > 0 && warp <= 10) {
       const bool as_key = warp == 9;
       float* red = tail_red + (warp - 9) * (32 * 33);
       const int kpl = (Rk + 31) >> 5;
@@ -863,6 +1009,47 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
       if (g + 2 < G) issue_l1(g + 2);
       if (leader) OCTIC_TRACE(0, 2);
     }
+    if (staged) {
+      // ---- phase 1': dQ_tile = dS[tile queries, keys] K with dS^T streamed back from the L2 scratch ----
+      // The V | dO tiles (contiguous, >= Rk * 256 bytes for hd >= 64) receive the operand: every MMA that read them has
+      // completed (last BAR_ACC) and the tail warps are done with them (BAR_TAIL).
+      mbar_wait(&bars[BAR_ACC], static_cast<uint32_t>((nt - 1) & 1));
+      mbar_wait(&bars[BAR_DS], 0);
+      if (n_tail > 0) mbar_wait(&bars[BAR_TAIL], 0);
+      tc_fence_after();
+      // operand tile: [Rk keys][128 queries] bf16 as two SWIZZLE_128B atom columns of 64 queries (Rk x 128 B each), used
+      // MN-major (M = queries): LBO = atom-column stride, SBO = 8 key rows, one K-step = 16 key rows = 2048 B
+      const uint64_t a_ds = make_smem_desc(v_addr, static_cast<uint32_t>(Rk) * 128u, 1024);
+      const uint32_t idesc_q = make_idesc_bf16(128, HD, 1, 1);
+      const int nks = Rk >> 4, ntq = (N + 127) >> 7;
+      for (int t = 0; t < ntq; ++t) {
+        const int ab = t & 1;
+        if (t >= 1) mbar_wait(&bars[BAR_DQ + ((t - 1) & 1)], static_cast<uint32_t>(((t - 1) >> 1) & 1));   // operand tile free
+        if (t >= 2) mbar_wait(&bars[BAR_DQFREE + ab], static_cast<uint32_t>(((t >> 1) - 1) & 1));          // accumulator drained
+        const int natom = (N - t * 128) > 64 ? 2 : 1;        // a last tile of <= 64 queries needs one atom column only
+        if (leader) {
+          OCTIC_TRACE(0, 8);
+          mbar_arrive_expect_tx(&bars[BAR_DSLOAD], static_cast<uint32_t>(natom * Rk) * 128u);
+          for (int a = 0; a < natom; ++a)
+            for (int r = 0; r < Rk; r += ds_box_rows)
+              tma_load_3d(v_addr + a * (Rk * 128) + r * 128, &tmDS, &bars[BAR_DSLOAD], t * 128 + 64 * a, r, slot);
+        }
+        mbar_wait(&bars[BAR_DSLOAD], static_cast<uint32_t>(t & 1));
+        tc_fence_after();
+        if (leader) OCTIC_TRACE(0, 9);
+        if (elect_one()) {
+          for (int ks = 0; ks < nks; ++ks)
+            umma_bf16(tb + ab * HD, a_ds + 128u * ks, desc_sw32_mn(k_addr, Rk, 16 * ks), idesc_q, ks != 0);
+          umma_commit(&bars[BAR_DQ + ab]);
+        }
+        __syncwarp();
+      }
+      if (leader) {
+        // every TMA read of the slot has landed: hand it to the next CTA
+        __threadfence();
+        atomicExch(&ds_slots[slot], 0);
+      }
+    }
   } else {
     // -------------------------------------------------- math warps --------------------------------------------------
     // Warp (q4, bsel) works on TMEM lane quarter q4 of EVERY job: set bsel = 0 takes the first half of the job's
@@ -879,10 +1066,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     OCTIC_TRACE_DECL;
     uint32_t pha = 0u;
     int g = 0;
-    for (int phase = 0; phase < 2; ++phase) {
+    const int nphase = staged ? 1 : 2;
+    for (int phase = 0; phase < nphase; ++phase) {
       for (int t = 0; t < nt; ++t) {
         const int row0 = t * 128;
         const int my_row = row0 + q4 * 32 + lane;
+        __nv_bfloat16* ds_row = staged ? ds_mine + static_cast<long>(my_row) * ldS : nullptr;
+        const bool ds_store = staged && my_row < Rk;
+        const bool ds_zero = my_row >= N;
         const bool warp_valid = row0 + q4 * 32 < Nm;
         float lse_r = 0.f, del_r = 0.f;
         if (phase == 1) {
@@ -927,6 +1118,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
                   // padded query columns carry lse = +inf (p = 0) and delta = 0: no explicit mask
                   bwd_piece<true>(rx[q % 3], ry[q % 3], pkp, pkd, scale_log2, lse_sa + col0 * 4, del_sa + col0 * 4, 0.f, 0.f, 16);
                   tmem_st_32x8(ix + q * 8, pkp);
+                  if (ds_store) {
+                    uint4 v0 = make_uint4(pkd[0], pkd[1], pkd[2], pkd[3]), v1 = make_uint4(pkd[4], pkd[5], pkd[6], pkd[7]);
+                    if (ds_zero) { v0 = make_uint4(0u, 0u, 0u, 0u); v1 = v0; }
+                    uint4* dst = reinterpret_cast<uint4*>(ds_row + col0);
+                    dst[0] = v0; dst[1] = v1;
+                  }
                 } else {
                   bwd_piece<false>(rx[q % 3], ry[q % 3], pkp, pkd, scale_log2, 0u, 0u, lse_r, del_r, N - col0);
                 }
@@ -939,24 +1136,57 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
           if (tid == 0) OCTIC_TRACE(1, 5);
           mbar_arrive(&bars[BAR_MDONE + buf]);
         }
+        if (staged && t == nt - 1) {
+          // this thread's part of dS^T is written: make it visible to the TMA (async proxy) reads of phase 1'
+          __threadfence();
+          fence_proxy_async_all();
+          mbar_arrive(&bars[BAR_DS]);
+        }
         // ---- flush the accumulators of this tile: TMEM -> bf16 staging -> packed global rows ----
         mbar_wait(&bars[BAR_ACC], pha);
         pha ^= 1u;
         tc_fence_after();
         if (tid == 0) OCTIC_TRACE(1, 6);
         named_bar_sync(5, kBwdMathThreads);          // the previous flush's global stores have read the staging tiles
+        if (tid == 0) OCTIC_TRACE(1, 10);
         if (warp_valid) {
           acc_half_to_stg<KS>(t_lane + ACC, hh, scale, my_stg);                               // dK or dQ
           if (phase == 0) acc_half_to_stg<KS>(t_lane + ACC + HD, hh, 1.0f, my_stg + stg_bytes);   // dV
         }
         tc_fence_before();
+        if (tid == 0) OCTIC_TRACE(1, 11);
         named_bar_sync(5, kBwdMathThreads);
+        if (tid == 0) OCTIC_TRACE(1, 12);
         const int nvalid = min(128, Nm - row0);
         store_tile<HD, GRAN>(stg, drows + static_cast<long>(row0) * ld3, ld3, nvalid, cb, sm, phase == 0 ? 1 : 0, tid,
                              kBwdMathThreads);
         if (phase == 0)
           store_tile<HD, GRAN>(stg + stg_bytes, drows + static_cast<long>(row0) * ld3, ld3, nvalid, cb, sm, 2, tid,
                                kBwdMathThreads);
+        if (tid == 0) OCTIC_TRACE(1, 7);
+      }
+    }
+    if (staged) {
+      // ---- phase 1': drain dQ of every query tile (accumulators ping-pong in the columns the S / dP buffers used) ----
+      // The tiles cover ALL N queries here (a tail token is one more, nearly empty, tile: its cost is one operand load
+      // and Rk/16 MMAs, not a pass of jobs), rows past N hold garbage and are not stored.
+      const int ntq = (N + 127) >> 7;
+      for (int t = 0; t < ntq; ++t) {
+        const int row0 = t * 128, ab = t & 1;
+        const bool warp_valid = row0 + q4 * 32 < N;
+        mbar_wait(&bars[BAR_DQ + ab], static_cast<uint32_t>((t >> 1) & 1));
+        tc_fence_after();
+        if (tid == 0) OCTIC_TRACE(1, 6);
+        named_bar_sync(5, kBwdMathThreads);          // the previous flush's global stores have read the staging tile
+        if (tid == 0) OCTIC_TRACE(1, 10);
+        if (warp_valid) acc_half_to_stg<KS>(t_lane + ab * HD, hh, scale, my_stg);
+        tc_fence_before();
+        if (tid == 0) OCTIC_TRACE(1, 11);
+        named_bar_sync(5, kBwdMathThreads);
+        if (tid == 0) OCTIC_TRACE(1, 12);
+        if (ntq > 2) mbar_arrive(&bars[BAR_DQFREE + ab]);
+        store_tile<HD, GRAN>(stg, drows + static_cast<long>(row0) * ld3, ld3, min(128, N - row0), cb, sm, 0, tid,
+                             kBwdMathThreads);
         if (tid == 0) OCTIC_TRACE(1, 7);
       }
     }
@@ -1004,6 +1234,22 @@ static int make_map_rows(CUtensorMap* map, const void* base, int B, int N, long 
   return r == CUDA_SUCCESS ? OCTIC_OK : OCTIC_ERR_TMAP;
 }
 static int pick_box_rows(int Rk) { return Rk > 256 ? Rk / 2 : Rk; }
+// staged-dQ scratch, bf16 [slots][Rk][Rk]: box = 64 columns (128 B) x box_rows rows, SWIZZLE_128B
+static int ds_pitch(int Rk) { return Rk; }   // = ldS of the kernel
+static int make_map_ds(CUtensorMap* map, const void* base, int slots, int Rk, int box_rows) {
+  EncodeTiledFn enc = attn_encode_fn();
+  if (enc == nullptr) return OCTIC_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || box_rows < 1 || box_rows > 256) return OCTIC_ERR_ARG;
+  const cuuint64_t ld = static_cast<cuuint64_t>(ds_pitch(Rk));
+  cuuint64_t dims[3] = {ld, static_cast<cuuint64_t>(Rk), static_cast<cuuint64_t>(slots)};
+  cuuint64_t strides[2] = {ld * 2, ld * 2 * static_cast<cuuint64_t>(Rk)};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? OCTIC_OK : OCTIC_ERR_TMAP;
+}
 
 static size_t fwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
@@ -1011,7 +1257,29 @@ static size_t fwd_smem(int Rk, int hd, int gran) {
 }
 static size_t bwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(4 * Rk + 256) * hd * 2 + 2 * Rk * 4 + (2 * nu + 1) * 4 + 7 * 8 + 16 + 2 * 32 * 33 * 4 + 1024;
+  return static_cast<size_t>(4 * Rk + 256) * hd * 2 + 2 * Rk * 4 + (2 * nu + 1) * 4 + 14 * 8 + 16 + 2 * 32 * 33 * 4 +
+         3 * 8 * 32 * 4 + 1024;
+}
+
+// ---- staged-dQ workspace: [kDsHeader bytes of slot flags (int, 0 = free)] [n_slots x Rk x ds_pitch(Rk) bf16] ----
+constexpr size_t kDsHeader = 4096;
+constexpr int kDsMaxSlots = static_cast<int>(kDsHeader / sizeof(int));
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 0;
+  }
+  return n;
+}
+bool attn_tc_supported(int N, int hd, bool backward);
+// the operand tile [Rk keys][128 queries] must fit into the V | dO tiles of the backward kernel
+static bool ds_staging_applies(int N, int hd) { return hd >= 64 && attn_tc_supported(N, hd, true); }
+size_t attn_bwd_tc_workspace_bytes(int N, int hd) {
+  if (!ds_staging_applies(N, hd) || sm_count() <= 0) return 0;
+  const size_t Rk = static_cast<size_t>((N + 15) / 16 * 16);
+  const int slots = 2 * sm_count() < kDsMaxSlots ? 2 * sm_count() : kDsMaxSlots;
+  return kDsHeader + static_cast<size_t>(slots) * Rk * ds_pitch(static_cast<int>(Rk)) * 2;
 }
 
 bool attn_tc_supported(int N, int hd, bool backward) {
@@ -1050,7 +1318,7 @@ static int launch_fwd_t(const void* qkv, void* o, float* lse, int B, int N, int 
 }
 template <int HD, int GRAN>
 static int launch_bwd_t(const void* qkv, const void* d_o, const float* lse, const float* delta, void* dqkv, int B, int N,
-                        int H, const HeadMap& m, const ChunkPlan& cp, cudaStream_t s) {
+                        int H, const HeadMap& m, const ChunkPlan& cp, void* ws, size_t ws_bytes, cudaStream_t s) {
   const int Rk = (N + 15) / 16 * 16;
   const size_t smem = bwd_smem(Rk, HD, GRAN);
   static bool done = false;
@@ -1065,9 +1333,30 @@ static int launch_bwd_t(const void* qkv, const void* d_o, const float* lse, cons
   if (rc) return rc;
   rc = make_map_rows(&tmDO, d_o, B, N, m.D, br);
   if (rc) return rc;
+  // staged dQ when the caller's workspace holds a slot for every CTA that can be resident (one per SM)
+  CUtensorMap tmDS = tmDO;
+  __nv_bfloat16* ds_ws = nullptr;
+  int* ds_slots = nullptr;
+  int n_slots = 0, ds_br = br;
+  if (ws != nullptr && ws_bytes > kDsHeader && ds_staging_applies(N, HD) && (reinterpret_cast<uintptr_t>(ws) & 255) == 0) {
+    const size_t per = static_cast<size_t>(Rk) * ds_pitch(Rk) * 2;
+    size_t fit = (ws_bytes - kDsHeader) / per;
+    if (fit > static_cast<size_t>(kDsMaxSlots)) fit = kDsMaxSlots;
+    if (sm_count() > 0 && fit >= static_cast<size_t>(sm_count())) {
+      n_slots = static_cast<int>(fit);
+      ds_slots = static_cast<int*>(ws);
+      ds_ws = reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + kDsHeader);
+      static int env_rows = -1;
+      if (env_rows < 0) { const char* e = getenv("OCTIC_DS_BOX_ROWS"); env_rows = e ? atoi(e) : 0; }
+      if (env_rows > 0 && env_rows <= 256 && Rk % env_rows == 0) ds_br = env_rows;
+      rc = make_map_ds(&tmDS, ds_ws, n_slots, Rk, ds_br);
+      if (rc) return rc;
+    }
+  }
   const float scale = 1.0f / sqrtf(static_cast<float>(HD));
   attn_bwd_tc_kernel<HD, GRAN><<<B * H, kBwdThreads, smem, s>>>(tmQKV, tmDO, lse, delta, static_cast<__nv_bfloat16*>(dqkv),
-                                                                N, H, m, scale, kLog2e * scale, cp, br, attn_tail_rows(N));
+                                                                N, H, m, scale, kLog2e * scale, cp, br, attn_tail_rows(N),
+                                                                tmDS, ds_ws, ds_slots, n_slots, ds_br);
   return cudaGetLastError() == cudaSuccess ? OCTIC_OK : OCTIC_ERR_CUDA;
 }
 
@@ -1090,11 +1379,11 @@ int launch_attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H
 }
 
 int launch_attn_bwd_tc(const void* qkv, const void* d_o, const float* lse, const float* delta, void* dqkv, int B, int N,
-                       int H, const HeadMap& m, cudaStream_t s) {
+                       int H, const HeadMap& m, void* ws, size_t ws_bytes, cudaStream_t s) {
   ChunkPlan cp;
   if (!attn_tc_supported(N, m.hd, true) || !make_plan(&cp, N, m.hd)) return OCTIC_ERR_ARG;
   const int gran = pick_gran(m);
-  OCTIC_TC_DISPATCH(launch_bwd_t, qkv, d_o, lse, delta, dqkv, B, N, H, m, cp, s)
+  OCTIC_TC_DISPATCH(launch_bwd_t, qkv, d_o, lse, delta, dqkv, B, N, H, m, cp, ws, ws_bytes, s)
 }
 
 }  // namespace octic

@@ -6,6 +6,7 @@ Conventions: activations are packed octic rows (see include/octic_b200.h) stored
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence
 
@@ -412,9 +413,31 @@ def attention_bwd(qkv, o, d_o, lse, B: int, N: int, H: int, hd: int, layout: int
             raise _lib.OcticError(f"{nm} must be contiguous")
     dqkv = torch.empty_like(qkv)
     delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
-    call("octic_attention_bwd", qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), delta.data_ptr(),
-         dqkv.data_ptr(), B, N, H, hd, int(layout), _stream(), flops=10.0 * B * H * N * N * hd)
+    ws = _attention_bwd_workspace(N, hd, qkv.device) if layout != 1 else None
+    call("octic_attention_bwd_ws", qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+         dqkv.data_ptr(), B, N, H, hd, int(layout), _ptr(ws), 0 if ws is None else ws.numel(), _stream(),
+         flops=10.0 * B * H * N * N * hd, stat="octic_attention_bwd")
     return dqkv
+
+
+# staged-dQ scratch of the tcgen05 attention backward: one buffer per (device, stream), grown on demand, slot flags
+# (first 4096 bytes) zeroed at allocation and left zero by every launch.  Launches on one stream are ordered, so they
+# share it; OCTIC_ATTN_STAGED_DQ=0 selects the two-pass kernel (A/B timing, tests).
+_attn_ws: dict = {}
+
+
+def _attention_bwd_workspace(N: int, hd: int, device) -> Optional[torch.Tensor]:
+    if os.environ.get("OCTIC_ATTN_STAGED_DQ", "1") == "0":
+        return None
+    need = int(_lib.load().octic_attention_bwd_workspace_bytes(int(N), int(hd)))
+    if need == 0:
+        return None
+    key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _attn_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(need, dtype=torch.uint8, device=device)
+        _attn_ws[key] = ws
+    return ws
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@ the kernels actually consume, so the comparison isolates the kernel arithmetic. 
 bf16 outputs carry one rounding (2^-9 relative), fp32 outputs of bf16 GEMMs are compared to ~1e-3 of the row scale.
 """
 import math
+import os
 
 import pytest
 import torch
@@ -447,6 +448,41 @@ def test_attention(B, N, H, hd, layout):
     assert_close(lse, want_lse, rtol=1e-3, atol=1e-3)
     dqkv = ops.attention_bwd(qkv_in, o, d_o_in, lse, B, N, H, hd, layout)
     assert_close(dqkv, qin.grad, rtol=3e-2, atol=3e-2)
+    if layout != ATTN_OCTIC_PACKED:
+        # the two-pass tcgen05 backward (no scratch: dQ from a recomputed S / dP) must agree with the staged-dQ default
+        os.environ["OCTIC_ATTN_STAGED_DQ"] = "0"
+        try:
+            dqkv2 = ops.attention_bwd(qkv_in, o, d_o_in, lse, B, N, H, hd, layout)
+        finally:
+            del os.environ["OCTIC_ATTN_STAGED_DQ"]
+        assert_close(dqkv2, qin.grad, rtol=3e-2, atol=3e-2)
+        assert_close(dqkv2, dqkv, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("layout", [ATTN_DENSE, ATTN_OCTIC_HEADMAJOR])
+def test_attention_bwd_staged_slots_recycle(layout):
+    """Staged dQ: 704 CTAs share 2 x SM-count scratch slots (claimed by CAS, released after the last TMA read), launched
+    three times back to back on one stream; every launch must reproduce the two-pass kernel's gradients and leave the
+    slot flags zero."""
+    B, N, H, hd = 44, 257, 16, 80
+    D = H * hd
+    g = torch.Generator().manual_seed(7)
+    qkv = bf(torch.randn(B * N, 3 * D, generator=g)).to(DEV)
+    d_o = bf(torch.randn(B * N, D, generator=g)).to(DEV)
+    o, lse = ops.attention_fwd(qkv, B, N, H, hd, layout)
+    os.environ["OCTIC_ATTN_STAGED_DQ"] = "0"
+    try:
+        want = ops.attention_bwd(qkv, o, d_o, lse, B, N, H, hd, layout)
+    finally:
+        del os.environ["OCTIC_ATTN_STAGED_DQ"]
+    outs = [ops.attention_bwd(qkv, o, d_o, lse, B, N, H, hd, layout) for _ in range(3)]
+    torch.cuda.synchronize()
+    for got in outs:
+        assert torch.isfinite(got.float()).all()
+        assert_close(got, want, rtol=1e-2, atol=1e-2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
+    for ws in ops._attn_ws.values():
+        assert int(ws[:4096].view(torch.int32).abs().sum()) == 0
 
 
 def test_attention_headmajor_rejects_unsupported():

@@ -12,6 +12,7 @@ int main(int argc, char** argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 20, N = 257, H = 16, hd = 80, D = H * hd;
   const bool bwd = argc > 2 && argv[2][0] == 'b';
   const int octic = argc > 3 ? atoi(argv[3]) : 0;
+  const int staged = argc > 4 ? atoi(argv[4]) : 1;      // backward: staged dQ (L2 scratch) or the two-pass kernel
   const size_t nq = static_cast<size_t>(B) * N * 3 * D;
   std::vector<__nv_bfloat16> h(nq);
   unsigned s = 12345u;
@@ -28,6 +29,9 @@ int main(int argc, char** argv) {
   cudaMalloc(&o, static_cast<size_t>(B) * N * D * 2);
   cudaMalloc(&lse, static_cast<size_t>(B) * H * N * 4);
   cudaMemcpy(qkv, h.data(), nq * 2, cudaMemcpyHostToDevice);
+  void* ws = nullptr;
+  const size_t ws_bytes = staged ? attn_bwd_tc_workspace_bytes(N, hd) : 0;
+  if (ws_bytes) { cudaMalloc(&ws, ws_bytes); cudaMemset(ws, 0, ws_bytes); }
   HeadMap m;
   m.octic = octic; m.hd = hd; m.D = D; m.C = D / 8; m.ch = hd / 8;
   for (int it = 0; it < 3; ++it) {
@@ -42,7 +46,7 @@ int main(int argc, char** argv) {
       cudaMemcpyToSymbol(g_trace_n, zero, sizeof(zero));
 #endif
     }
-    int rc = bwd ? launch_attn_bwd_tc(qkv, o /* stands in for dO */, lse, delta, dqkv, B, N, H, m, 0)
+    int rc = bwd ? launch_attn_bwd_tc(qkv, o /* stands in for dO */, lse, delta, dqkv, B, N, H, m, ws, ws_bytes, 0)
                  : launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
     cudaError_t e = cudaDeviceSynchronize();
     if (rc || e != cudaSuccess) { printf("launch rc=%d cuda=%s\n", rc, cudaGetErrorString(e)); return 1; }
@@ -53,14 +57,14 @@ int main(int argc, char** argv) {
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
     for (int it = 0; it < 5; ++it) {
-      if (bwd) launch_attn_bwd_tc(qkv, o, lse, delta, dqkv, B, N, H, m, 0);
+      if (bwd) launch_attn_bwd_tc(qkv, o, lse, delta, dqkv, B, N, H, m, ws, ws_bytes, 0);
       else launch_attn_fwd_tc(qkv, o, lse, B, N, H, m, 0);
     }
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
-    printf("B=%d %s octic=%d: %.1f us per launch\n", B, bwd ? "bwd" : "fwd", octic, ms * 200.f);
+    printf("B=%d %s octic=%d staged=%d: %.1f us per launch\n", B, bwd ? "bwd" : "fwd", octic, staged && ws_bytes, ms * 200.f);
   }
 #ifdef OCTIC_ATTN_TRACE
   std::vector<long long> tr(2 * 2048);
