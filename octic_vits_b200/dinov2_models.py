@@ -289,24 +289,45 @@ class OcticDinoVisionTransformer(OcticVisionTransformer):
         return {"x_norm_clstoken": x_norm[:, 0], "x_norm_regtokens": x_norm[:, 1:R + 1],
                 "x_norm_patchtokens": x_norm[:, R + 1:], "x_prenorm": x, "masks": masks}
 
+    concat_crops = True     # crop lists: run every per-token kernel once over the concatenated rows of all crops
+
+    def _bridge_rows(self, rows: Tensor) -> Tensor:
+        """octic half -> dense half on [T, D] rows: invariantisation + projection, or the 5 -> 8 tuple permutation"""
+        if self.invariant:
+            inv = self.invariantization.forward_packed(rows)
+            return OF.LinearFn.apply(_rows(inv), self.invariant_proj.weight, self.invariant_proj.bias, False, True)
+        return OF.BridgeFn.apply(rows)
+
     def forward_features_list(self, x_list, masks_list):
-        """reference :138-168.  Each crop batch runs through the blocks' list interface when they have one
-        (NestedTensorBlock*: stochastic depth then follows the reference's list rule), else block by block."""
+        """reference :138-168.  The reference hands the crop list to its NestedTensorBlock*s, which (with xformers)
+        concatenate the crops along the token axis under a block-diagonal attention mask (dinov2/layers/block.py:
+        212-248).  Here: the token rows of all crops are concatenated ONCE, every per-token kernel (LayerNorm, GEMMs,
+        D8-GELU, residual epilogues, bridge) runs once over all rows and attention runs once per crop resolution on its
+        row slice (`segs`); stochastic depth follows the reference's list rule with one draw per crop batch.  Models
+        whose blocks cannot take segments (non-fused children, crop lengths outside the tcgen05 attention envelope)
+        run crop by crop."""
         ts = [self.prepare_tokens_packed(x, m) for x, m in zip(x_list, masks_list)]
         half = self.octic_equi_break_layer
         octic, dense = self.blocks[:half], self.blocks[half:]
-        if all(isinstance(b, NestedTensorBlockD8) for b in octic) and all(isinstance(b, NestedTensorBlock) for b in dense):
+        nested = (all(isinstance(b, NestedTensorBlockD8) for b in octic)
+                  and all(isinstance(b, NestedTensorBlock) for b in dense))
+        segs = tuple((t.shape[0], t.shape[1]) for t in ts)
+        if nested and self.concat_crops and len(ts) > 1 and all(b.supports_segments(segs) for b in octic):
+            D = ts[0].shape[-1]
+            t = torch.cat([x.reshape(-1, D) for x in ts]).unsqueeze(0)
+            for blk in octic:
+                t = blk.forward_packed(t, segs)
+            t = self._bridge_rows(t[0]).view(1, -1, D)
+            for blk in dense:
+                t = _DenseBlockBase.forward(blk, t, True, segs)
+            out, r0 = [], 0
+            for b, n in segs:
+                out.append(t[0, r0:r0 + b * n].view(b, n, D))
+                r0 += b * n
+        elif nested:
             for blk in octic:
                 ts = [blk.forward_packed(t) for t in ts]
-            out = []
-            for t in ts:
-                B, N, D = t.shape
-                if self.invariant:
-                    inv = self.invariantization.forward_packed(t)
-                    t = OF.LinearFn.apply(_rows(inv), self.invariant_proj.weight, self.invariant_proj.bias, False, True)
-                else:
-                    t = OF.BridgeFn.apply(_rows(t))
-                out.append(t.view(B, N, D))
+            out = [self._bridge_rows(_rows(t)).view(t.shape) for t in ts]
             for blk in dense:
                 out = blk(out)
         else:

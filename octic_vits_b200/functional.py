@@ -503,21 +503,46 @@ class GeluD8Fn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------------------------
 class AttentionFn(torch.autograd.Function):
     """layout: ops.ATTN_DENSE, ops.ATTN_OCTIC_PACKED or ops.ATTN_OCTIC_HEADMAJOR (qkv and the incoming d_o head-major,
-    o and the outgoing dqkv packed octic rows)."""
+    o and the outgoing dqkv packed octic rows).
+    B, N: ints, or equally long tuples -- the rows are then the concatenation of len(B) segments of B[i] images with
+    N[i] tokens each (a DINOv2 crop list: the reference's block-diagonal attention over concatenated crops,
+    dinov2/layers/block.py:212-248, is plain attention inside every image); one launch per segment reads / writes
+    its row slice in place, every per-token kernel around it runs once over all rows."""
 
     @staticmethod
-    def forward(ctx, qkv, B: int, N: int, H: int, hd: int, layout: int):
+    def forward(ctx, qkv, B, N, H: int, hd: int, layout: int):
         qkv = _c(qkv)
-        o, lse = ops.attention_fwd(qkv, B, N, H, hd, layout, want_lse=any(ctx.needs_input_grad))
-        ctx.save_for_backward(qkv, o, lse)
+        want = any(ctx.needs_input_grad)
+        if isinstance(B, int):
+            o, lse = ops.attention_fwd(qkv, B, N, H, hd, layout, want_lse=want)
+            lses = (lse,)
+        else:
+            o = torch.empty(qkv.shape[0], H * hd, dtype=torch.bfloat16, device=qkv.device)
+            lses, r0 = [], 0
+            for b, n in zip(B, N):
+                _, lse = ops.attention_fwd(qkv[r0:r0 + b * n], b, n, H, hd, layout, want_lse=want, out=o[r0:r0 + b * n])
+                lses.append(lse)
+                r0 += b * n
+            if r0 != qkv.shape[0]:
+                raise OcticError(f"segments cover {r0} rows, qkv has {qkv.shape[0]}")
+        ctx.save_for_backward(qkv, o, *[t for t in lses if t is not None])
         ctx.cfg = (B, N, H, hd, layout)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
-        qkv, o, lse = ctx.saved_tensors
+        qkv, o, *lses = ctx.saved_tensors
         B, N, H, hd, layout = ctx.cfg
-        return ops.attention_bwd(qkv, o, _c(d_o), lse, B, N, H, hd, layout), None, None, None, None, None
+        d_o = _c(d_o)
+        if isinstance(B, int):
+            return ops.attention_bwd(qkv, o, d_o, lses[0], B, N, H, hd, layout), None, None, None, None, None
+        dqkv = torch.empty_like(qkv)
+        r0 = 0
+        for (b, n), lse in zip(zip(B, N), lses):
+            sl = slice(r0, r0 + b * n)
+            ops.attention_bwd(qkv[sl], o[sl], d_o[sl], lse, b, n, H, hd, layout, out=dqkv[sl])
+            r0 += b * n
+        return dqkv, None, None, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -33,6 +33,26 @@ def _rows(x: Tensor) -> Tensor:
     return x.reshape(-1, x.shape[-1])
 
 
+Segs = Optional[Tuple[Tuple[int, int], ...]]      # ((images, tokens per image), ...) of a concatenated crop list
+
+
+def _seg_rows(segs) -> int:
+    return sum(b * n for b, n in segs)
+
+
+def _seg_row_scale(per_seg, segs, device) -> Optional[Tensor]:
+    """per-segment per-sample residual factors (scale [B_i] or None for each segment) -> one per-ROW vector (the
+    residual epilogue is then called with rows_per_sample = 1); None when no segment has one."""
+    if all(s is None for s in per_seg):
+        return None
+    parts = []
+    for s, (b, n) in zip(per_seg, segs):
+        if s is None:
+            s = torch.ones(b, dtype=torch.float32, device=device)
+        parts.append(s.repeat_interleave(n))
+    return torch.cat(parts)
+
+
 def _as_bf16(x: Tensor) -> Tensor:
     return x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
 
@@ -284,11 +304,18 @@ class AttentionD8(nn.Module):
         H = self.num_heads
         return (self.dim // (8 * H)) % 2 == 0 and OF.ops.attention_headmajor_ok(N, self.dim // H)
 
-    def core_packed(self, x: Tensor) -> Tensor:
+    def core_packed(self, x: Tensor, segs: Segs = None) -> Tensor:
         """packed bf16/fp32 [B, N, D] -> attention output before `proj`, packed bf16 [B, N, D].  When head_major(N),
-        the consumer (`proj`) must be called with dgrad_heads=num_heads."""
+        the consumer (`proj`) must be called with dgrad_heads=num_heads.
+        segs: x is [1, T, D], the concatenation of segments (B_i images x N_i tokens); every N_i must be head_major."""
         B, N, D = x.shape
         H = self.num_heads
+        if segs is not None:
+            assert _seg_rows(segs) == B * N and all(self.head_major(n) for _, n in segs)
+            qkv = self.qkv.forward_packed(x, head=(H, 3))
+            o = OF.AttentionFn.apply(_rows(qkv), tuple(b for b, _ in segs), tuple(n for _, n in segs), H, D // H,
+                                     OF.ops.ATTN_OCTIC_HEADMAJOR)
+            return o.view(B, N, D)
         if self.head_major(N):
             qkv = self.qkv.forward_packed(x, head=(H, 3))
             o = OF.AttentionFn.apply(_rows(qkv), B, N, H, D // H, OF.ops.ATTN_OCTIC_HEADMAJOR)
@@ -310,13 +337,14 @@ class AttentionD8(nn.Module):
 # octic blocks
 # ----------------------------------------------------------------------------------------------------------------
 def _branch_residual(lin: LinearD8, a: Tensor, scale_mod, x: Tensor, row_scale: Optional[Tensor],
-                     dgrad_heads: int = 0) -> Tensor:
-    """x + row_scale * gamma * lin(a) with everything after the GEMM fused into its epilogue."""
+                     dgrad_heads: int = 0, rows_per_sample: int = 0) -> Tensor:
+    """x + row_scale * gamma * lin(a) with everything after the GEMM fused into its epilogue.  rows_per_sample: rows that
+    share one row_scale entry (default: the N of x; 1 for the per-row vector of a concatenated crop list)."""
     B, N, D = x.shape
     gamma = scale_mod.packed_alpha() if scale_mod is not None else None
     gamma_src = tuple(scale_mod.parameters()) if scale_mod is not None else None
-    out = OF.LinearD8ResidualFn.apply(_as_bf16(_rows(a)), *lin.weights(), lin.lin_A1.bias, gamma, _rows(x), row_scale, N,
-                                      dgrad_heads, gamma_src)
+    out = OF.LinearD8ResidualFn.apply(_as_bf16(_rows(a)), *lin.weights(), lin.lin_A1.bias, gamma, _rows(x), row_scale,
+                                      rows_per_sample or N, dgrad_heads, gamma_src)
     return out.view(B, N, D)
 
 
@@ -336,24 +364,43 @@ class _OcticBlockBase(nn.Module):
                 and all(not isinstance(self._ls(i), AffineD8) or self._ls(i).beta is None for i in (1, 2))
                 and all(isinstance(self._dp(i), (DropPathD8, nn.Identity)) for i in (1, 2)))
 
-    def forward_packed(self, x: Tensor) -> Tensor:
+    def supports_segments(self, segs) -> bool:
+        """concatenated crop lists need the fused path and the head-major tcgen05 attention for every crop length"""
+        return self._fusable() and all(self.attn.head_major(n) for _, n in segs)
+
+    def forward_packed(self, x: Tensor, segs: Segs = None) -> Tensor:
         """fp32 packed [B, N, D] -> fp32 packed [B, N, D]: 8 kernels forward (LN, qkv, attention, proj+ls+dp+res,
-        LN, fc1, D8-GELU, fc2+ls+dp+res)."""
+        LN, fc1, D8-GELU, fc2+ls+dp+res).
+        segs: x is [1, T, D], the concatenated token rows of a crop list (reference NestedTensorBlockD8 list input,
+        d8_layers.py:780-794: every crop batch is its own forward, so DropPath draws one factor per image of every
+        segment); the per-token kernels run once over all rows, attention once per segment."""
         if not self._fusable():
+            assert segs is None
             return OF.pack_five(self._forward_tuple(OF.unpack_five(x)))
         B = x.shape[0]
         ls1 = None if isinstance(self._ls(1), nn.Identity) else self._ls(1)
         ls2 = None if isinstance(self._ls(2), nn.Identity) else self._ls(2)
-        s1 = self._dp(1).sample(B, x.device) if isinstance(self._dp(1), DropPathD8) else None
-        s2 = self._dp(2).sample(B, x.device) if isinstance(self._dp(2), DropPathD8) else None
+        rps = 0
+        if segs is None:
+            s1 = self._dp(1).sample(B, x.device) if isinstance(self._dp(1), DropPathD8) else None
+            s2 = self._dp(2).sample(B, x.device) if isinstance(self._dp(2), DropPathD8) else None
+            hm = self.attn.head_major(x.shape[1])
+        else:
+            dp1, dp2 = self._dp(1), self._dp(2)
+            # same draw order as crop-by-crop forwards: (branch 1, branch 2) of segment 0, then of segment 1, ..
+            draws = [(dp1.sample(b, x.device) if isinstance(dp1, DropPathD8) else None,
+                      dp2.sample(b, x.device) if isinstance(dp2, DropPathD8) else None) for b, _ in segs]
+            s1 = _seg_row_scale([d[0] for d in draws], segs, x.device)
+            s2 = _seg_row_scale([d[1] for d in draws], segs, x.device)
+            hm, rps = True, 1
         xn, x = self.norm1.forward_packed(x, passthrough=True)
-        a = self.attn.core_packed(xn)
-        x = _branch_residual(self.attn.proj, a, ls1, x, s1,
-                             dgrad_heads=self.attn.num_heads if self.attn.head_major(x.shape[1]) else 0)
+        a = self.attn.core_packed(xn, segs)
+        x = _branch_residual(self.attn.proj, a, ls1, x, s1, dgrad_heads=self.attn.num_heads if hm else 0,
+                             rows_per_sample=rps)
         xn, x = self.norm2.forward_packed(x, passthrough=True)
         h = self.mlp.fc1.forward_packed(xn)
         h = self.mlp.act.forward_packed(h)
-        return _branch_residual(self.mlp.fc2, h, ls2, x, s2)
+        return _branch_residual(self.mlp.fc2, h, ls2, x, s2, rows_per_sample=rps)
 
     @OF.opaque_to_compile
     def forward(self, xs):
@@ -720,9 +767,13 @@ class Attention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.fused_attn = fused_attn
 
-    def core_packed(self, x: Tensor) -> Tensor:
+    def core_packed(self, x: Tensor, segs: Segs = None) -> Tensor:
         B, N, D = x.shape
         qkv = OF.LinearFn.apply(_as_bf16(_rows(x)), self.qkv.weight, self.qkv.bias, False, False)
+        if segs is not None:
+            assert _seg_rows(segs) == B * N
+            return OF.AttentionFn.apply(qkv, tuple(b for b, _ in segs), tuple(n for _, n in segs), self.num_heads,
+                                        D // self.num_heads, OF.ops.ATTN_DENSE).view(B, N, D)
         return OF.AttentionFn.apply(qkv, B, N, self.num_heads, D // self.num_heads, OF.ops.ATTN_DENSE).view(B, N, D)
 
     @OF.opaque_to_compile
@@ -777,15 +828,22 @@ class _DenseBlockBase(nn.Module):
         return s1, s2
 
     @OF.opaque_to_compile
-    def forward(self, x, nested: bool = False):
+    def forward(self, x, nested: bool = False, segs: Segs = None):
         """fp32 [B, N, D] -> fp32 [B, N, D]; 7 kernels: LN, qkv, attention, proj+ls+dp+res, LN, fc1+GELU, fc2+ls+dp+res.
-        `nested`: the input is one element of a crop list (only the DINOv2 block's stochastic-depth rule cares)."""
+        `nested`: the input is one element of a crop list (only the DINOv2 block's stochastic-depth rule cares).
+        `segs`: x is [1, T, D], the concatenated rows of a whole crop list (see _OcticBlockBase.forward_packed)."""
         OF.require_cuda(x)
         x = _as_f32(x)
         B, N, D = x.shape
-        s1, s2 = self._drop_scales(B, x.device, nested)
+        if segs is None:
+            s1, s2 = self._drop_scales(B, x.device, nested)
+        else:
+            draws = [self._drop_scales(b, x.device, True) for b, _ in segs]
+            s1 = _seg_row_scale([d[0] for d in draws], segs, x.device)
+            s2 = _seg_row_scale([d[1] for d in draws], segs, x.device)
+            N = 1 if (s1 is not None or s2 is not None) else N      # rows per row_scale entry
         xn, xs = OF.LayerNormFn.apply(_rows(x), self.norm1.weight, self.norm1.bias, self.norm1.eps, False, True, True)
-        a = self.attn.core_packed(xn.view(B, N, D))
+        a = self.attn.core_packed(xn.view(x.shape), segs) if segs is not None else self.attn.core_packed(xn.view(B, N, D))
         x2 = OF.LinearResidualFn.apply(_rows(a), self.attn.proj.weight, self.attn.proj.bias, self._gamma(1), xs,
                                        s1, N, (0, 0, 0))
         xn, x2 = OF.LayerNormFn.apply(x2, self.norm2.weight, self.norm2.bias, self.norm2.eps, False, True, True)
@@ -796,7 +854,7 @@ class _DenseBlockBase(nn.Module):
             h = self.mlp.hidden_packed(xn)
             out = OF.LinearResidualFn.apply(h, self.mlp.fc2.weight, self.mlp.fc2.bias, self._gamma(2), x2, s2, N,
                                             (0, 0, 0))
-        return out.view(B, N, D)
+        return out.view(x.shape)
 
 
 class Layer_scale_init_Block(_DenseBlockBase):

@@ -394,24 +394,40 @@ def attention_headmajor_ok(N: int, hd: int, backward: bool = True) -> bool:
     return bool(_lib.load().octic_attention_headmajor_supported(int(N), int(hd), int(backward)))
 
 
-def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, layout: int, want_lse: bool = True):
+def attention_fwd(qkv: torch.Tensor, B: int, N: int, H: int, hd: int, layout: int, want_lse: bool = True,
+                  out: Optional[torch.Tensor] = None):
+    """`out`: optional preallocated contiguous bf16 [B*N, D] (e.g. a row slice of a larger matrix: the segments of a
+    crop list write into one token matrix)."""
     _req(qkv, torch.bfloat16, "qkv")
     D = H * hd
     if tuple(qkv.shape) != (B * N, 3 * D) or not qkv.is_contiguous():
         raise _lib.OcticError(f"qkv must be contiguous [B*N, 3*D] = [{B * N}, {3 * D}], got {tuple(qkv.shape)}")
-    o = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
+    if out is None:
+        o = torch.empty(B * N, D, dtype=torch.bfloat16, device=qkv.device)
+    else:
+        o = out
+        _req(o, torch.bfloat16, "out")
+        if tuple(o.shape) != (B * N, D) or not o.is_contiguous():
+            raise _lib.OcticError(f"out must be contiguous [B*N, D] = [{B * N}, {D}], got {tuple(o.shape)}")
     lse = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device) if want_lse else None
     call("octic_attention_fwd", qkv.data_ptr(), o.data_ptr(), _ptr(lse), B, N, H, hd, int(layout), _stream(),
          flops=4.0 * B * H * N * N * hd)
     return o, lse
 
 
-def attention_bwd(qkv, o, d_o, lse, B: int, N: int, H: int, hd: int, layout: int) -> torch.Tensor:
+def attention_bwd(qkv, o, d_o, lse, B: int, N: int, H: int, hd: int, layout: int,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     for t, nm in ((qkv, "qkv"), (o, "o"), (d_o, "d_o")):
         _req(t, torch.bfloat16, nm)
         if not t.is_contiguous():
             raise _lib.OcticError(f"{nm} must be contiguous")
-    dqkv = torch.empty_like(qkv)
+    if out is None:
+        dqkv = torch.empty_like(qkv)
+    else:
+        dqkv = out
+        _req(dqkv, torch.bfloat16, "out")
+        if dqkv.shape != qkv.shape or not dqkv.is_contiguous():
+            raise _lib.OcticError("out must be contiguous and shaped like qkv")
     delta = torch.empty(B, H, N, dtype=torch.float32, device=qkv.device)
     ws = _attention_bwd_workspace(N, hd, qkv.device) if layout != 1 else None
     call("octic_attention_bwd_ws", qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), delta.data_ptr(),

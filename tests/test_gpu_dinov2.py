@@ -168,3 +168,49 @@ def test_dinov2_local_crops_dynamic_img_size(golden):
         for g in O.GROUP:
             moved = model(O.image_action(g, small).to(DEV))
             check(moved, base, rel=3e-2, mx=8e-2, what=f"cls invariance under {g} at 96 px")
+
+
+@pytest.mark.parametrize("invariant", [False, True])
+def test_dinov2_concatenated_crops_match_crop_by_crop(invariant):
+    """Crop lists (reference forward_features_list + NestedTensorBlock* list inputs, octic_vits/dinov2_models.py:138-168,
+    dinov2/layers/block.py:212-248): the token rows of all crops are concatenated and every per-token kernel runs once,
+    attention once per crop resolution.  Must equal the crop-by-crop evaluation: same outputs (same kernels per row),
+    same gradients up to the fp32 summation order of the weight gradients, same stochastic-depth draws."""
+    from octic_vits_b200 import _lib
+    torch.manual_seed(3)
+    model = DM.OcticDinoVisionTransformer(img_size=64, patch_size=16, embed_dim=256, depth=4, num_heads=4,
+                                          num_register_tokens=2, invariant=invariant, drop_path_rate=0.3,
+                                          init_values=0.5, dynamic_img_size=True).to(DEV).train()
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if p.requires_grad and p.dim() >= 2:
+                p.mul_(3.0)          # O(1) activations in every branch
+    big, small = torch.randn(2, 3, 64, 64, device=DEV), torch.randn(3, 3, 32, 32, device=DEV)
+    masks = torch.rand(2, 16, device=DEV) < 0.4
+    segs = ((2, 19), (3, 7))
+    assert all(b.supports_segments(segs) for b in model.blocks[:model.octic_equi_break_layer])
+
+    def run(concat):
+        model.concat_crops = concat
+        for p in model.parameters():
+            p.grad = None
+        torch.manual_seed(11)
+        _lib.STATS.reset()
+        outs = model([big, small], masks=[masks, None], is_training=True)
+        ln_calls = _lib.STATS.calls.get("octic_layernorm_d8_fwd", 0)
+        loss = sum((o["x_norm_clstoken"].float() ** 2).mean() + (o["x_norm_patchtokens"].float() ** 2).mean() for o in outs)
+        loss.backward()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        return outs, grads, ln_calls
+
+    outs_a, grads_a, ln_a = run(True)
+    outs_b, grads_b, ln_b = run(False)
+    half = model.octic_equi_break_layer
+    assert ln_a == 2 * half and ln_b == 4 * half, (ln_a, ln_b)      # one LayerNormD8 launch per norm vs one per crop
+    for oa, ob in zip(outs_a, outs_b):
+        for k in KEYS:
+            assert oa[k].shape == ob[k].shape
+            check(oa[k], ob[k], rel=1e-6, mx=1e-5, what=f"concat vs crop-by-crop {k}")
+    assert set(grads_a) == set(grads_b)
+    for n in grads_a:
+        check(grads_a[n], grads_b[n], rel=2e-3, mx=2e-2, what=f"grad {n}")
