@@ -89,13 +89,18 @@ class MemEffAttention(Attention):
 
 def subset_drop_scale(batch: int, sample_drop_ratio: float, device) -> Tensor:
     """drop_add_residual_stochastic_depth (dinov2/layers/block.py:117-140) as a per-sample residual factor: the
-    reference evaluates the branch on a random subset of max(int(b*(1-ratio)), 1) samples and index_adds it back with
-    alpha = b/subset; that equals  x + s * branch(x)  with s = b/subset on the subset and 0 elsewhere."""
+    reference evaluates the branch on a random subset of max(int(b*(1-ratio)), 1) samples (`torch.randperm(b)[:subset]`)
+    and index_adds it back with alpha = b/subset; that equals  x + s * branch(x)  with s = b/subset on the subset and 0
+    elsewhere.  The uniformly random subset is drawn as "the `keep` smallest of b iid uniforms" with elementwise ops only
+    (rank by an all-pairs comparison, b <= a few hundred): no sort, no host synchronisation, so the draw can be
+    captured in a CUDA graph and every replay draws a fresh subset (parallel.GraphedStep)."""
     keep = max(int(batch * (1 - sample_drop_ratio)), 1)
-    brange = torch.randperm(batch, device=device)[:keep]
-    s = torch.zeros(batch, dtype=torch.float32, device=device)
-    s[brange] = batch / keep
-    return s
+    r = torch.rand(batch, device=device)
+    idx = torch.arange(batch, device=device)
+    # rank of sample i = number of samples with a smaller draw (ties, probability ~0, broken by index)
+    before = (r[None, :] < r[:, None]) | ((r[None, :] == r[:, None]) & (idx[None, :] < idx[:, None]))
+    rank = before.sum(dim=1)
+    return (rank < keep).to(torch.float32) * (batch / keep)
 
 
 class Block(_DenseBlockBase):

@@ -8,7 +8,7 @@ simply not part of the buffer, which is what the reference needs find_unused_par
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, List, Optional, Tuple
+from typing import Callable, Dict, Iterable, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -353,3 +353,45 @@ class GraphedTrainStep:
         if self.optimizer is not None:
             self.optimizer.step()             # consumes the all-reduced flat gradients (optim.FusedOptimizer)
         return loss
+
+
+class GraphedStep(GraphedTrainStep):
+    """GraphedTrainStep for any step shape: `forward_loss(inputs) -> scalar loss` over a dict of static device tensors
+    (the DINOv2 step: teacher forward without grad + student forward on a crop list with iBOT
+    masks + loss, reference dinov2/train/ssl_meta_arch.py:122-330 -- the heads and losses themselves are out of scope,
+    the caller supplies them inside `forward_loss`).  Zero grads, forward_loss, backward are captured once and replayed;
+    random draws made on the device inside the step (DropPathD8, dinov2_models.subset_drop_scale) are graph safe and
+    differ from replay to replay.
+
+        step = GraphedStep(student, fg, {"global": g, "local": l, "masks": m}, forward_loss)
+        loss = step(**{"global": g1, "local": l1, "masks": m1})
+
+    `forward_loss` must not synchronise (no boolean-mask indexing, no .item()); if capture fails the step runs eagerly
+    (`graphed` False, `capture_error` says why)."""
+
+    def __init__(self, model: torch.nn.Module, flat_grads: FlatGrads, inputs: Dict[str, torch.Tensor],
+                 forward_loss: Callable[[Dict[str, torch.Tensor]], torch.Tensor], **kw):
+        dev = flat_grads.flat.device
+        self.inputs = {k: torch.zeros(v.shape, dtype=v.dtype, device=dev).copy_(v) for k, v in inputs.items()}
+        self._forward_loss = forward_loss
+        super().__init__(model, flat_grads, (1,), **kw)
+
+    def _eager(self) -> torch.Tensor:
+        from . import ops
+        ops.begin_step()
+        self.fg.begin_step()
+        loss = self._forward_loss(self.inputs)
+        loss.backward()
+        self.fg.join_early()
+        return loss
+
+    def stage(self, *a, **k):
+        raise NotImplementedError("GraphedStep copies its inputs in __call__")
+
+    run = stage
+
+    def __call__(self, **inputs: torch.Tensor) -> torch.Tensor:
+        for k, v in inputs.items():
+            self.inputs[k].copy_(v, non_blocking=True)
+        return self._launch()
+

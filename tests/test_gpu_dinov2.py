@@ -214,3 +214,70 @@ def test_dinov2_concatenated_crops_match_crop_by_crop(invariant):
     assert set(grads_a) == set(grads_b)
     for n in grads_a:
         check(grads_a[n], grads_b[n], rel=2e-3, mx=2e-2, what=f"grad {n}")
+
+
+def _dino_step_pieces(drop_path):
+    from octic_vits_b200.parallel import FlatGrads
+    torch.manual_seed(5)
+    kw = dict(img_size=64, patch_size=16, embed_dim=256, depth=4, num_heads=4, num_register_tokens=2,
+              dynamic_img_size=True)
+    student = DM.OcticDinoVisionTransformer(drop_path_rate=drop_path, **kw).to(DEV).train()
+    teacher = DM.OcticDinoVisionTransformer(**kw).to(DEV).eval()
+    teacher.load_state_dict(student.state_dict())
+    for p in teacher.parameters():
+        p.requires_grad_(False)
+    fg = FlatGrads(student.parameters())
+
+    def forward_loss(inp):
+        # teacher on the global crops without grad, student on [global (iBOT-masked), local]; stand-in losses with the
+        # data flow of ssl_meta_arch.py:122-330 (cls tokens of all crops vs the teacher's, masked patch tokens)
+        with torch.no_grad():
+            t = teacher(inp["global"], is_training=True)
+        sg, sl = student([inp["global"], inp["local"]], masks=[inp["masks"], None], is_training=True)
+        m = inp["masks"].unsqueeze(-1).float()
+        ibot = (((sg["x_norm_patchtokens"] - t["x_norm_patchtokens"]) ** 2) * m).sum() / m.sum().clamp_min(1.0)
+        tc = t["x_norm_clstoken"].mean(0, keepdim=True)
+        dino = ((sg["x_norm_clstoken"] - tc) ** 2).mean() + ((sl["x_norm_clstoken"] - tc) ** 2).mean()
+        return ibot / 256.0 + dino
+
+    def batch(seed):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        return {"global": torch.randn(2, 3, 64, 64, generator=g).to(DEV),
+                "local": torch.randn(4, 3, 32, 32, generator=g).to(DEV),
+                "masks": (torch.rand(2, 16, generator=g) < 0.4).to(DEV)}
+
+    return student, fg, forward_loss, batch
+
+
+def test_dinov2_graphed_step_matches_eager():
+    """the DINOv2 step shape (teacher no-grad forward + student forward on a crop list with iBOT masks
+    + loss + backward) captured in ONE CUDA graph (parallel.GraphedStep) reproduces the eager step on new inputs."""
+    from octic_vits_b200.parallel import GraphedStep
+    student, fg, forward_loss, batch = _dino_step_pieces(0.0)
+    step = GraphedStep(student, fg, batch(0), forward_loss)
+    assert step.graphed, getattr(step, "capture_error", "")
+    for seed in (1, 2):
+        b = batch(seed)
+        loss_g = float(step(**b))
+        grads_g = fg.flat.clone()
+        fg.flat.zero_()
+        loss_e = forward_loss(b)
+        loss_e.backward()
+        assert abs(loss_g - float(loss_e)) <= 1e-5 * max(1.0, abs(loss_g))
+        check(grads_g, fg.flat, rel=1e-4, mx=1e-3, what=f"graphed vs eager gradients (batch {seed})")
+        assert float(grads_g.abs().max()) > 0
+    step.close()
+
+
+def test_dinov2_graphed_step_draws_fresh_stochastic_depth():
+    """drop_path 0.4 inside the graph: the per-sample draws (Bernoulli in the octic blocks, batch-subset rule in the
+    dense blocks, both made on the device without synchronisation) are re-drawn on every replay."""
+    from octic_vits_b200.parallel import GraphedStep
+    student, fg, forward_loss, batch = _dino_step_pieces(0.4)
+    b = batch(3)
+    step = GraphedStep(student, fg, b, forward_loss)
+    assert step.graphed, getattr(step, "capture_error", "")
+    losses = {round(float(step(**b)), 7) for _ in range(6)}
+    assert len(losses) >= 3 and all(l == l for l in losses), losses
+    assert torch.isfinite(fg.flat).all()
+    step.close()
