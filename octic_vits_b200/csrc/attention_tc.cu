@@ -20,10 +20,13 @@
 // warps never issue MMAs and never __syncthreads with the control warp: all hand-offs are mbarriers
 // (MMA -> math: tcgen05.commit; math -> MMA: one arrive per math thread).
 //
-// Forward (CTA = (image, head); 4 math warps = 128 TMEM lanes = 128 query rows per tile; two CTAs per SM):
-//   pass 1  S chunk = Q_tile K_chunk^T -> TMEM (two ping-pong buffers) -> row max           (exact, no online rescale)
-//   pass 2  S chunk again -> p = exp2(s*c - max*c) -> bf16 P written in place over S in TMEM -> O += P V_chunk with
-//           the A operand read from TMEM (tcgen05.mma .ts form), accumulators in TMEM.
+// Forward (CTA = (image, head); 8 math warps on 128 TMEM lanes = 128 query rows per tile; two CTAs per SM), ONE pass:
+//   S chunk = Q_tile K_chunk^T -> TMEM (two ping-pong buffers) -> p = exp2(s*c - ref*c) -> bf16 P written in place over S
+//   -> O += P V_chunk with the A operand read from TMEM (tcgen05.mma .ts form), accumulators in TMEM.
+//   ref = the row's reference maximum, fixed by the first chunk and raised LAZILY: only when a later chunk exceeds it by
+//   more than 2^8 (in the exponent) are O (TMEM read-modify-write) and the row sum rescaled -- P stays <= 256, exact in
+//   bf16's range, and on real score distributions the rescale never runs after the first chunk.  (Round 1 made two
+//   passes -- exact row max first: 8 instead of 4 jobs per tile; 182 -> 170 us per launch, profiles/r02_attn_fwd_onepass.txt.)
 // Backward (CTA = (image, head); 8 math warps: two warps per TMEM lane quarter split the columns; one CTA per SM):
 //   phase 0 (lanes = keys)     S^T = K Q^T, dP^T = V dO^T per query chunk -> P^T, dS^T (bf16, in place) ->
 //                              dV += P^T dO, dK += dS^T Q
@@ -266,6 +269,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   constexpr int NPW = (CW / 16 + 1) / 2;        // max 16-column pieces per warp in one job
   constexpr int KS0 = (KS + 1) / 2;             // epilogue: accumulator pieces handled by column-half 0
   constexpr uint32_t kTmemCols = 256;
+  // BAR_OFULL: one completion per P V job (the lazy rescale waits for the previous job's, the epilogue for the last)
   enum { BAR_K = 0, BAR_V = 1, BAR_Q = 2, BAR_SFULL = 3, BAR_SDONE = 5, BAR_OFULL = 7, BAR_QFREE = 8, NBARS = 9 };
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -275,8 +279,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   uint8_t* Ks = smem;
   uint8_t* Vs = Ks + kv_bytes;
   uint8_t* Qs = Vs + kv_bytes;
-  float* xch = reinterpret_cast<float*>(Qs + q_bytes);           // [2][128] row max exchange between warp pairs
-  float* xcl = xch + 256;                                        // [2][128] row sum exchange (own array: the sum of a
+  float* xch = reinterpret_cast<float*>(Qs + q_bytes);           // [2 job parities][2][128] chunk max exchange between warp pairs
+  float* xcl = xch + 512;                                        // [2][128] row sum exchange (own array: the sum of a
                                                                  // fast warp must not overwrite a max its partner has not read)
   int* ocb = reinterpret_cast<int*>(xcl + 256);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ocb + NU + (NU & 1));
@@ -306,7 +310,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs);
-  const int nt = (Nm + 127) >> 7, nc = cp.n, njobs = 2 * nc;
+  const int nt = (Nm + 127) >> 7, nc = cp.n, njobs = nc;
 
   if (warp == 9) {
     // -------------------------------------------------- tail warp --------------------------------------------------
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
             const uint32_t ak = kk < hsplit ? kk * 8 : hsplit * 16 + (kk - hsplit) * 8;
             umma_ts_lohi(tb + OCOL, a + ak, vb + kk * 32, kDescHiSw32, idesc_pv, !(first && kk == 0));
           }
-        if (last) umma_commit(&bars[BAR_OFULL]);
+        umma_commit(&bars[BAR_OFULL]);
       }
     };
 
@@ -459,18 +463,16 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
       phq ^= 1u;
       tc_fence_after();
       issue_s(0, 0);
-      issue_s(1 < nc ? 1 : 1 - nc, 1);
+      if (nc > 1) issue_s(1, 1);
       for (int j = 0; j < njobs; ++j) {
         const int buf = j & 1;
         if (buf == 0) { mbar_wait(&bars[BAR_SDONE], phd0); phd0 ^= 1u; }
         else { mbar_wait(&bars[BAR_SDONE + 1], phd1); phd1 ^= 1u; }
         tc_fence_after();
         if (leader) OCTIC_TRACE(0, 1);
-        if (j >= nc) {
-          if (!v_ready) { mbar_wait(&bars[BAR_V], 0); v_ready = true; }
-          issue_pv(j - nc, buf, j == nc, j == njobs - 1);
-        }
-        if (j + 2 < njobs) issue_s(j + 2 < nc ? j + 2 : j + 2 - nc, buf);
+        if (!v_ready) { mbar_wait(&bars[BAR_V], 0); v_ready = true; }
+        issue_pv(j, buf, j == 0, j == njobs - 1);
+        if (j + 2 < njobs) issue_s(j + 2, buf);
         if (leader) OCTIC_TRACE(0, 2);
       }
     }
@@ -478,30 +480,27 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     // -------------------------------------------------- math warps --------------------------------------------------
     // Warp (q4, bsel) works on TMEM lane quarter q4 of EVERY job: set bsel = 0 takes the first half of the chunk's
     // 16-column pieces, set 1 the second half (half the math latency per job; the other buffer's job keeps the tensor
-    // pipe busy).  Pass 1: row max.  Pass 2: p = exp2(.), bf16 P written at the start of the set's own column range --
-    // output piece q lands on columns of the set's input piece q/2, already consumed, so the sets need no barrier.
-    // Row max / row sum are combined between the two warps of a quarter once per tile; for the output accumulator the
-    // pair splits the columns (hh = bsel).
+    // pipe busy): chunk max (combined with the partner set through one pair barrier per job), lazy raise of the row's
+    // reference, p = exp2(.), bf16 P written at the start of the set's own column range -- output piece q lands on columns
+    // of the set's input piece q/2, already consumed, so the sets need no barrier for that.  The row sums of the two
+    // warps are combined once per tile; for the output accumulator the pair splits the columns (hh = bsel).
     const int q4 = warp & 3, bsel = warp >> 2, hh = bsel;
     const int rloc = q4 * 32 + lane;                   // row inside the tile
     OCTIC_TRACE_DECL;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-    uint32_t pho = 0u;
-    int gj = 0;                                        // running job index (buffer = gj & 1, phase = (gj >> 1) & 1)
+    // largest exponent gap a row tolerates before it is rescaled (raw score units): p <= 2^kLazyExp
+    constexpr float kLazyExp = 8.0f;
+    const float lazy_gap = kLazyExp / scale_log2;
+    int gj = 0;                                        // jobs done so far = P V jobs committed before the current one
+    uint32_t phs0 = 0u, phs1 = 0u;                     // phases of the two S buffers (nc may be odd: tiles restart at buffer 0)
     for (int t = 0; t < nt; ++t) {
       const bool warp_valid = t * 128 + q4 * 32 < Nm;
-      float mx = -INFINITY, l = 0.f, moff = 0.f;
+      float mx = -INFINITY, l = 0.f, moff = 0.f;       // mx: the row's reference maximum, moff = mx * scale_log2
       for (int j = 0; j < njobs; ++j, ++gj) {
-        const int c = j < nc ? j : j - nc;
-        if (j == nc && warp_valid) {
-          // all pass-1 jobs are done: combine the two partial row maxima
-          xch[bsel * 128 + rloc] = mx;
-          named_bar_sync(1 + q4, 64);
-          mx = fmaxf(mx, xch[(bsel ^ 1) * 128 + rloc]);
-          moff = mx * scale_log2;
-        }
+        const int c = j;
         const int buf = j & 1;
-        mbar_wait(&bars[BAR_SFULL + buf], (gj >> 1) & 1);
+        if (buf == 0) { mbar_wait(&bars[BAR_SFULL], phs0); phs0 ^= 1u; }
+        else { mbar_wait(&bars[BAR_SFULL + 1], phs1); phs1 ^= 1u; }
         tc_fence_after();
         if (tid == 0) OCTIC_TRACE(1, 3);
         if (warp_valid) {
@@ -516,50 +515,77 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
           for (int q = 0; q < QMAX; ++q)
             if (q < cnt) tmem_ld_32x16(ta + q * 16, r[q]);
           tmem_ld_wait();
-          if (j < nc) {
-            float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          // ---- chunk maximum of the row: this set's columns, then the partner set's (pair barrier) ----
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-            for (int q = 0; q < QMAX; ++q)
-              if (q < cnt) {
-                const int nvalid = N - (k0 + (p0 + q) * 16);
-                float v[16];
+          for (int q = 0; q < QMAX; ++q)
+            if (q < cnt) {
+              const int nvalid = N - (k0 + (p0 + q) * 16);
+              if (nvalid < 16) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[q][i]);
-                if (nvalid < 16) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) v[i] = i < nvalid ? v[i] : -INFINITY;
-                }
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  m0 = fmaxf(m0, v[i]); m1 = fmaxf(m1, v[i + 1]); m2 = fmaxf(m2, v[i + 2]); m3 = fmaxf(m3, v[i + 3]);
-                }
+                for (int i = 0; i < 16; ++i) r[q][i] = i < nvalid ? r[q][i] : 0xff800000u;      // -inf
               }
-            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                m0 = fmaxf(m0, __uint_as_float(r[q][i])); m1 = fmaxf(m1, __uint_as_float(r[q][i + 1]));
+                m2 = fmaxf(m2, __uint_as_float(r[q][i + 2])); m3 = fmaxf(m3, __uint_as_float(r[q][i + 3]));
+              }
+            }
+          float* xm = xch + (j & 1) * 256;              // double buffered by job parity: one pair barrier per job suffices
+          const float mloc = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          xm[bsel * 128 + rloc] = mloc;
+          named_bar_sync(1 + q4, 64);
+          const float mc = fmaxf(mloc, xm[(bsel ^ 1) * 128 + rloc]);
+          if (j == 0) {
+            mx = mc;                                     // O is empty: nothing to rescale
+            moff = mx * scale_log2;
           } else {
-            float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+            const bool need = mc > mx + lazy_gap;        // both warps of the pair see the same mc and mx
+            if (__any_sync(0xffffffffu, need)) {
+              // rare: raise the reference of the rows that need it.  O holds the P V sums of jobs < j under the old
+              // reference: wait for the previous job's MMAs (the control warp cannot have issued this job's yet), then
+              // scale this warp's half of the O columns and the partial row sum
+              const float f = need ? exp2f((mx - mc) * scale_log2) : 1.0f;
+              mbar_wait(&bars[BAR_OFULL], static_cast<uint32_t>((gj - 1) & 1));
+              tc_fence_after();
+              const int pa = hh == 0 ? 0 : (KS + 1) / 2, pb = hh == 0 ? (KS + 1) / 2 : KS;
+              for (int pz = pa; pz < pb; ++pz) {
+                uint32_t ov[16];
+                tmem_ld_32x16(t_lane + OCOL + pz * 16, ov);
+                tmem_ld_wait();
+                uint32_t lo[8], hi[8];
 #pragma unroll
-            for (int q = 0; q < QMAX; ++q)
-              if (q < cnt) {
-                const int nvalid = N - (k0 + (p0 + q) * 16);
-                float e[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[q][i]), scale_log2, -moff));
-                if (nvalid < 16) {
-#pragma unroll
-                  for (int i = 0; i < 16; ++i) e[i] = i < nvalid ? e[i] : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                  lo[i] = __float_as_uint(__uint_as_float(ov[i]) * f);
+                  hi[i] = __float_as_uint(__uint_as_float(ov[8 + i]) * f);
                 }
-                uint32_t pk[8];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                  l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
-                  pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
-                  pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
-                }
-                tmem_st_32x8(ta + q * 8, pk);
+                tmem_st_32x8(t_lane + OCOL + pz * 16, lo);
+                tmem_st_32x8(t_lane + OCOL + pz * 16 + 8, hi);
               }
-            l += (l0 + l1) + (l2 + l3);
-            tmem_st_wait();
+              tmem_st_wait();
+              l *= f;
+              if (need) { mx = mc; moff = mx * scale_log2; }
+            }
           }
+          // ---- p = exp2(s * c - ref * c), row sum, bf16 P in place ----
+          float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+          for (int q = 0; q < QMAX; ++q)
+            if (q < cnt) {
+              float e[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) e[i] = exp2f(fmaf(__uint_as_float(r[q][i]), scale_log2, -moff));   // -inf -> 0
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                l0 += e[i]; l1 += e[i + 1]; l2 += e[i + 2]; l3 += e[i + 3];
+                pk[i >> 1] = pack2_bf16(e[i], e[i + 1]);
+                pk[(i >> 1) + 1] = pack2_bf16(e[i + 2], e[i + 3]);
+              }
+              tmem_st_32x8(ta + q * 8, pk);
+            }
+          l += (l0 + l1) + (l2 + l3);
+          tmem_st_wait();
         }
         tc_fence_before();
         if (tid == 0) OCTIC_TRACE(1, 5);
@@ -571,8 +597,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
         named_bar_sync(1 + q4, 64);
         l += xcl[(bsel ^ 1) * 128 + rloc];
       }
-      mbar_wait(&bars[BAR_OFULL], pho);
-      pho ^= 1u;
+      mbar_wait(&bars[BAR_OFULL], static_cast<uint32_t>((gj - 1) & 1));      // the tile's last P V job
       tc_fence_after();
       if (tid == 0) OCTIC_TRACE(1, 6);
       const int row = t * 128 + rloc;
@@ -1253,7 +1278,7 @@ static int make_map_ds(CUtensorMap* map, const void* base, int slots, int Rk, in
 
 static size_t fwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);
-  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 512 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 16 + (hd + 32 * 17) * 4 + 1024;
+  return static_cast<size_t>(2 * Rk + 128) * hd * 2 + 768 * 4 + (nu + 1) * 4 + 9 * 8 + 16 + 16 + (hd + 32 * 17) * 4 + 1024;
 }
 static size_t bwd_smem(int Rk, int hd, int gran) {
   const int nu = hd / (gran / 2);

@@ -459,6 +459,37 @@ def test_attention(B, N, H, hd, layout):
         assert_close(dqkv2, dqkv, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize("growth", [6.0, -6.0])
+@pytest.mark.parametrize("B,N,H,hd", [(2, 257, 16, 80), (3, 197, 6, 64), (1, 261, 16, 64), (2, 129, 2, 80)])
+def test_attention_extreme_score_ranges(B, N, H, hd, growth):
+    """Softmax over score ranges far beyond a comfortable exponent window: keys whose scale grows with the token index
+    (growth > 0: every key chunk overshoots the previous ones by far more than 2^8 in the exponent, so the one-pass
+    forward's lazy rescale of O and of the row sum runs in EVERY job) or shrinks (growth < 0: the first chunk dominates,
+    the rest underflows towards 0).  o, lse and the backward that consumes lse must stay finite and right."""
+    D = H * hd
+    g = torch.Generator().manual_seed(N * 7 + hd)
+    qkv = torch.randn(B, N, 3, H, hd, generator=g) * 1.5
+    ramp = torch.linspace(0.0, 1.0, N).view(1, N, 1, 1)
+    qkv[:, :, 1] *= torch.exp2(ramp * growth) if growth > 0 else torch.exp2((1.0 - ramp) * -growth)
+    qkv = bf(qkv.reshape(B * N, 3 * D)).to(DEV)
+    d_o = bf(torch.randn(B * N, D, generator=g)).to(DEV)
+    qin = qkv.float().clone().requires_grad_(True)
+    want = _attn_reference(qin, B, N, H, hd, False)
+    (want * d_o.float()).sum().backward()
+    o, lse = ops.attention_fwd(qkv, B, N, H, hd, ATTN_DENSE)
+    assert torch.isfinite(o.float()).all() and torch.isfinite(lse).all()
+    assert_close(o, want.detach(), rtol=2e-2, atol=2e-2)
+    t = qkv.float().reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    want_lse = torch.logsumexp(t[0] @ t[1].transpose(-1, -2) / hd ** 0.5, dim=-1)
+    assert_close(lse, want_lse, rtol=1e-3, atol=2e-3)
+    dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, N, H, hd, ATTN_DENSE)
+    # gradients span six orders of magnitude here (dq = dS K with keys scaled by up to 2^6): norm-wise comparison
+    got, ref = dqkv.float(), qin.grad
+    assert torch.isfinite(got).all()
+    assert float((got - ref).norm() / ref.norm()) < 3e-2
+    assert float((got - ref).abs().max() / ref.abs().max()) < 3e-2
+
+
 @pytest.mark.parametrize("layout", [ATTN_DENSE, ATTN_OCTIC_HEADMAJOR])
 def test_attention_bwd_staged_slots_recycle(layout):
     """Staged dQ: 704 CTAs share 2 x SM-count scratch slots (claimed by CAS, released after the last TMA read), launched
