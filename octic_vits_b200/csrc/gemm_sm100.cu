@@ -1239,7 +1239,7 @@ static int roles_low_env() {
   }
   return v;
 }
-// Measured on B200 (tools/gpu_s5_e.sh, profiles/r01_gemm_epilogue_policy_s5.txt): the register-direct epilogue issues
+// Measured on B200 (tools/gpu/r1_s5_e.sh, profiles/r01_gemm_epilogue_policy_s5.txt): the register-direct epilogue issues
 // one 16-byte access per lane to 32 different lines and is bound by L1 line transactions; the staged (coalesced) path
 // wins for every mode, so direct is off by default and kept only as an experiment switch.
 constexpr int kDefaultDirectMask = 0;
@@ -1387,7 +1387,7 @@ int launch_gemm_tn(const octic_gemm_desc* d, cudaStream_t stream) {
   if (stage_cap >= 2 && stages > stage_cap) stages = stage_cap;
   // Epilogue-paced small-K launches (head-major scatter; irrep groups with the fp32 residual epilogue) run FASTER with a
   // shallow ring: a producer that runs far ahead only competes with the epilogue's own global traffic (measured,
-  // tools/gpu_s5_st.sh: qkv head-major 269 -> 214 us, octic proj + residual 152 -> 127 us at 2 stages; K >= 640 and the
+  // tools/gpu/r1_s5_st.sh: qkv head-major 269 -> 214 us, octic proj + residual 152 -> 127 us at 2 stages; K >= 640 and the
   // plain epilogues want the deep ring).
   if (stage_cap == 0 && !p.ws) {
     if (d->mode == EPI_RESID && kmax <= 320 && stages > 2) stages = 2;
