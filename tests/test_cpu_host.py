@@ -470,3 +470,25 @@ def test_optimizer_chunk_table_covers_every_parameter_once():
         FusedOptimizer(model, fg, kind="sgd")
     with pytest.raises(ValueError):
         FusedOptimizer(ema, fg)                                        # fg's parameters are not this model's
+
+
+def test_dinov2_subset_draw_is_uniform_and_segment_row_scales():
+    """The graph-safe subset draw (rank of iid uniforms, no randperm / sort) selects every sample with probability
+    keep / b; per-segment per-sample factors of a concatenated crop list expand to one factor per token ROW."""
+    from octic_vits_b200.dinov2_models import subset_drop_scale
+    from octic_vits_b200.layers import _seg_row_scale, _seg_rows
+    torch.manual_seed(1)
+    b, ratio, trials = 8, 0.5, 4000
+    hits = torch.zeros(b)
+    for _ in range(trials):
+        s = subset_drop_scale(b, ratio, "cpu")
+        assert int((s > 0).sum()) == 4 and float(s.max()) == pytest.approx(2.0)
+        hits += (s > 0).float()
+    assert torch.all((hits / trials - 0.5).abs() < 0.04), hits / trials
+    segs = ((2, 3), (3, 2))
+    assert _seg_rows(segs) == 12
+    assert _seg_row_scale([None, None], segs, "cpu") is None
+    rs = _seg_row_scale([torch.tensor([2.0, 0.0]), None], segs, "cpu")
+    assert rs.tolist() == [2.0] * 3 + [0.0] * 3 + [1.0] * 6
+    rs = _seg_row_scale([torch.tensor([2.0, 0.0]), torch.tensor([0.0, 3.0, 1.5])], segs, "cpu")
+    assert rs.tolist() == [2.0] * 3 + [0.0] * 3 + [0.0] * 2 + [3.0] * 2 + [1.5] * 2
