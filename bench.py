@@ -420,7 +420,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=128, help="images per GPU")
+    ap.add_argument("--batch", type=int, default=192,
+                    help="images per GPU (SURVEY.md section 8d / BASELINE.json configs[3]: 64-256 per GPU; 192 measured "
+                         "+3 %% images/s over 128 on the same box, profiles/r02_bench_batch_sweep.txt)")
     ap.add_argument("--drop-path", type=float, default=0.0)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

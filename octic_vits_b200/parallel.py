@@ -256,6 +256,12 @@ class GraphedTrainStep:
                 self._eager()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
+        # the warm-up steps leave their activations cached in the ordinary allocator pool while the capture allocates
+        # the same amount again in the graph's private pool: hand the cached blocks back first (measured on the headline
+        # model: 176 GB -> OOM at 256 images per GPU with 91 GB in the graph pool; live tensors are untouched)
+        import gc
+        gc.collect()                  # an autograd graph kept alive by a reference cycle would pin its activations
+        torch.cuda.empty_cache()
         if repack_weights or optimizer is not None:
             # parameters change between replays: capture the fp32 -> bf16 weight packs inside the graph (cache miss
             # on first use of every weight) so that each replay re-packs from the current values
