@@ -85,7 +85,13 @@ FOLD_GAMMA = True
 # process-wide kill switch for tests.
 ACCUMULATE_INTO_GRAD = True
 ACCUMULATE_ATTR = "_octic_accumulate"
-_aux_slot = None     # (data_ptr, shape, bf16 copy, column sums) of the most recent layer-norm backward output
+# (data_ptr, shape, bf16 copy, column sums, the tensor itself) of the most recent layer-norm backward output.  One slot on
+# purpose: the consumer is the very next autograd node of the same backward; anything else (a second model, a hook that
+# replaces the gradient) misses on the address / shape test and takes the recompute path -- the parked tensor is held, so
+# its address cannot be recycled while the slot is live.  Measured alternative (round 2, tools/gpu/r2_aw.sh): carrying the
+# by-products as an attribute of the gradient tensor loses them in 46 of 64 hand-offs (autograd re-wraps the tensor), i.e.
+# +46 streaming passes per step -- not adopted.
+_aux_slot = None
 
 
 def reset_step_state() -> None:
