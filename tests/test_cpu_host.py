@@ -23,7 +23,7 @@ def lib():
 
 def header_prototypes():
     hdr = (ROOT / "include" / "octic_b200.h").read_text()
-    return re.findall(r"^(?:int|const char\*)\s+(octic_\w+)\s*\(", hdr, flags=re.M)
+    return re.findall(r"^(?:int|size_t|const char\*)\s+(octic_\w+)\s*\(", hdr, flags=re.M)
 
 
 def test_library_exports_every_header_symbol(lib):
@@ -33,9 +33,12 @@ def test_library_exports_every_header_symbol(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/octic_b200.h but not exported"
     bound = set(_lib.SIGNATURES) | {"octic_strerror", "octic_version", "octic_device_ok",
-                                      "octic_attention_headmajor_supported"}
+                                      "octic_attention_headmajor_supported", "octic_attention_bwd_workspace_bytes"}
     assert set(names) == bound, set(names) ^ bound
-    assert lib.octic_version() >= 100
+    assert lib.octic_version() >= 200
+    if not torch.cuda.is_available():
+        # size query of the staged-dQ scratch: no device -> "the staged path does not apply" (0), never a crash
+        assert lib.octic_attention_bwd_workspace_bytes(257, 80) == 0
     assert lib.octic_strerror(-2).decode().startswith("pointer or leading dimension")
 
 
