@@ -366,6 +366,8 @@ def run_ours(args):
             "config": {"workload": "hybrid_deit_huge_patch14 (embed 1280, depth 32: 16 octic + 16 dense, heads 16, patch 14) "
                                    "DeiT-III training step: fwd + bwd" + (" + NCCL grad all-reduce" if world > 1 else ""),
                        "img": MODEL["img"], "batch_per_gpu": B, "global_batch": world * B, "tokens_per_image": 257,
+                       "batch_policy": "BASELINE configs[3] / SURVEY 8d: 64-256 images per GPU; default 192 (round 1 ran 128; "
+                                       "same-box sweep in profiles/r02_bench_batch_sweep.txt)",
                        "drop_path": args.drop_path, "parallelism": f"dp{world}",
                        "optimizer_step": False if opt is None else f"fused {args.optimizer} (3 launches/step, weight "
                                                                     "re-pack inside the graph)",
