@@ -30,7 +30,10 @@ int main(int argc, char** argv) {
   cudaMalloc(&lse, static_cast<size_t>(B) * H * N * 4);
   cudaMemcpy(qkv, h.data(), nq * 2, cudaMemcpyHostToDevice);
   void* ws = nullptr;
-  const size_t ws_bytes = staged ? attn_bwd_tc_workspace_bytes(N, hd) : 0;
+  // argv[5]: number of scratch slots (default: what the library asks for, 2 x SM count); must be >= the SM count
+  const int slots = argc > 5 ? atoi(argv[5]) : 0;
+  const size_t rk = static_cast<size_t>((N + 15) / 16 * 16);
+  const size_t ws_bytes = !staged ? 0 : slots > 0 ? 4096 + slots * rk * rk * 2 : attn_bwd_tc_workspace_bytes(N, hd);
   if (ws_bytes) { cudaMalloc(&ws, ws_bytes); cudaMemset(ws, 0, ws_bytes); }
   HeadMap m;
   m.octic = octic; m.hd = hd; m.D = D; m.C = D / 8; m.ch = hd / 8;
