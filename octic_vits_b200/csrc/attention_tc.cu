@@ -303,6 +303,13 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     mbar_init(&bars[BAR_OFULL], 1);
     mbar_init(&bars[BAR_QFREE], kFwdMathThreads);
     fence_mbar_init();
+    // first operand loads before the TMEM allocation and the block barrier (this thread initialised their barriers)
+    mbar_arrive_expect_tx(&bars[BAR_K], kv_bytes);
+    tma_load_tile<HD>(smem_u32(Ks), &tmKV, &bars[BAR_K], m.D + h * HD, 0, b, Rk, kv_box_rows);
+    mbar_arrive_expect_tx(&bars[BAR_Q], q_bytes);
+    tma_load_tile<HD>(smem_u32(Qs), &tmQ, &bars[BAR_Q], h * HD, 0, b, 128, 128);
+    mbar_arrive_expect_tx(&bars[BAR_V], kv_bytes);
+    tma_load_tile<HD>(smem_u32(Vs), &tmKV, &bars[BAR_V], 2 * m.D + h * HD, 0, b, Rk, kv_box_rows);
   }
   if (warp == 8) tmem_alloc(tmem_ptr, kTmemCols);
   tc_fence_before();
@@ -410,14 +417,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) attn_fwd_tc_kernel(const __gri
     OCTIC_TRACE_DECL;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int colq = h * HD, colk = m.D + h * HD, colv = 2 * m.D + h * HD;
-    if (leader) {
-      mbar_arrive_expect_tx(&bars[BAR_K], kv_bytes);
-      tma_load_tile<HD>(k_addr, &tmKV, &bars[BAR_K], colk, 0, b, Rk, kv_box_rows);
-      mbar_arrive_expect_tx(&bars[BAR_Q], q_bytes);
-      tma_load_tile<HD>(q_addr, &tmQ, &bars[BAR_Q], colq, 0, b, 128, 128);
-      mbar_arrive_expect_tx(&bars[BAR_V], kv_bytes);
-      tma_load_tile<HD>(v_addr, &tmKV, &bars[BAR_V], colv, 0, b, Rk, kv_box_rows);
-    }
+    // (K, the first Q tile and V were requested by this warp's lane 0 in the prologue)
     const uint32_t q_lo = desc_lo_sw32(q_addr, 0), k_lo = desc_lo_sw32(k_addr, 0), v_lo = desc_lo_sw32(v_addr, Rk * 32);
     const uint32_t q_step = (128 * 32) >> 4, k_step = static_cast<uint32_t>(Rk * 32) >> 4;
     const uint32_t idesc_pv = make_idesc_bf16(128, HD, 0, 1);
@@ -699,6 +699,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     mbar_init(&bars[BAR_DQ], 1); mbar_init(&bars[BAR_DQ + 1], 1);
     mbar_init(&bars[BAR_DQFREE], kBwdMathThreads); mbar_init(&bars[BAR_DQFREE + 1], kBwdMathThreads);
     fence_mbar_init();
+    {
+      // the operand loads go out before anything else (this thread initialised their barriers; nobody touches the tiles
+      // before the __syncthreads below): the scratch-slot claim -- an atomic round trip to L2 -- and the TMEM allocation
+      // then run under the DRAM latency of the loads instead of in front of it
+      const uint32_t q_a = smem_u32(Qs), k_a = smem_u32(Ks), v_a = smem_u32(Vs), do_a = smem_u32(dOs);
+      mbar_arrive_expect_tx(&bars[BAR_KQ], 2 * mat_bytes);
+      tma_load_tile<HD>(k_a, &tmQKV, &bars[BAR_KQ], m.D + h * HD, 0, b, Rk, box_rows);
+      tma_load_tile<HD>(q_a, &tmQKV, &bars[BAR_KQ], h * HD, 0, b, Rk, box_rows);
+      mbar_arrive_expect_tx(&bars[BAR_VDO], 2 * mat_bytes);
+      tma_load_tile<HD>(v_a, &tmQKV, &bars[BAR_VDO], 2 * m.D + h * HD, 0, b, Rk, box_rows);
+      tma_load_tile<HD>(do_a, &tmDO, &bars[BAR_VDO], h * HD, 0, b, Rk, box_rows);
+    }
     if (staged) {
       int sl = static_cast<int>(blockIdx.x % static_cast<unsigned>(n_slots));
       uint32_t spins = 0;
@@ -945,14 +957,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_tc_kernel(const __gri
     const bool leader = lane == 0;
     OCTIC_TRACE_DECL;
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-    if (leader) {
-      mbar_arrive_expect_tx(&bars[BAR_KQ], 2 * mat_bytes);
-      tma_load_tile<HD>(k_addr, &tmQKV, &bars[BAR_KQ], m.D + h * HD, 0, b, Rk, box_rows);
-      tma_load_tile<HD>(q_addr, &tmQKV, &bars[BAR_KQ], h * HD, 0, b, Rk, box_rows);
-      mbar_arrive_expect_tx(&bars[BAR_VDO], 2 * mat_bytes);
-      tma_load_tile<HD>(v_addr, &tmQKV, &bars[BAR_VDO], 2 * m.D + h * HD, 0, b, Rk, box_rows);
-      tma_load_tile<HD>(do_addr, &tmDO, &bars[BAR_VDO], h * HD, 0, b, Rk, box_rows);
-    }
+    // (the operand loads were issued by this warp's lane 0 in the prologue)
     // low descriptor words: K-major views (first level) and MN-major views (second level, LBO = atom-column stride)
     const uint32_t mstep = static_cast<uint32_t>(Rk * 32) >> 4;       // one K-step = next atom column
     const uint32_t qk = desc_lo_sw32(q_addr, 0), kk_ = desc_lo_sw32(k_addr, 0), vk = desc_lo_sw32(v_addr, 0),
